@@ -1,0 +1,169 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes handles onto the CPU oracle (oracle/libmrg_oracle.so, the
+restatement in mrg_oracle.c) and, where it was built, onto the unmodified reference hot path
+(oracle/_ref/libmrgingham_ref.so, see oracle/Makefile).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may import this module.
+Nothing under mrgingham_b200/ does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "libmrg_oracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libmrgingham_ref.so")
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i16p = ctypes.POINTER(ctypes.c_int16)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_i8p = ctypes.POINTER(ctypes.c_int8)
+
+
+def build(ref=True):
+    """compile the oracle (always) and the reference build (only where /root/reference exists)"""
+    subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
+    if ref and os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _check_image(image):
+    image = np.asarray(image)
+    assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1
+    return image
+
+
+class _Lib:
+    def __init__(self, path, prefix):
+        self.lib = ctypes.CDLL(path)
+        self.prefix = prefix
+
+    def fn(self, name):
+        return getattr(self.lib, name)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(_ORACLE_SO):
+            build(ref=False)
+        _oracle = ctypes.CDLL(_ORACLE_SO)
+        _oracle.oracle_find_corners.restype = ctypes.c_int
+        _oracle.oracle_refine_corners.restype = ctypes.c_int
+        _oracle.oracle_pyramid.restype = ctypes.c_int
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(_REF_SO)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(_REF_SO)
+        _ref.ref_find_chessboard_corners.restype = ctypes.c_int
+        _ref.ref_refine_chessboard_corners.restype = ctypes.c_int
+    return _ref
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle (restatement)
+# ---------------------------------------------------------------------------------------------
+def chess_response_5(image, fill=0):
+    """dense int16 response; pixels the reference never writes hold `fill`"""
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.full((h, w), fill, dtype=np.int16)
+    oracle_lib().oracle_chess_response_5(_ptr(out, _i16p), _ptr(image, _u8p), w, h, image.strides[0])
+    return out
+
+
+def pyramid(image, level):
+    image = _check_image(image)
+    h, w = image.shape
+    oh, ow = ctypes.c_int(), ctypes.c_int()
+    rc = oracle_lib().oracle_pyramid(_ptr(image, _u8p), h, w, image.strides[0], level, None,
+                                     ctypes.byref(oh), ctypes.byref(ow))
+    if rc != 0:
+        return None
+    out = np.empty((oh.value, ow.value), dtype=np.uint8)
+    oracle_lib().oracle_pyramid(_ptr(image, _u8p), h, w, image.strides[0], level, _ptr(out, _u8p),
+                                ctypes.byref(oh), ctypes.byref(ow))
+    return out
+
+
+def find_corners(image, level=0, cap=1 << 20, want_double=False):
+    """(N,2) int32 PointInt list (x,y scaled by 1000), in the reference's output order"""
+    image = _check_image(image)
+    h, w = image.shape
+    xy = np.empty((cap, 2), dtype=np.int32)
+    xyd = np.empty((cap, 2), dtype=np.float64) if want_double else None
+    n = oracle_lib().oracle_find_corners(_ptr(image, _u8p), h, w, image.strides[0], level,
+                                         _ptr(xy, _i32p), _ptr(xyd, _f64p) if want_double else None, cap)
+    assert n <= cap
+    return (xy[:n].copy(), xyd[:n].copy()) if want_double else xy[:n].copy()
+
+
+def refine_corners(image, level, xy, levels):
+    """returns (nrefined, xy', levels')"""
+    image = _check_image(image)
+    h, w = image.shape
+    xy = np.ascontiguousarray(xy, dtype=np.float64).copy()
+    levels = np.ascontiguousarray(levels, dtype=np.int8).copy()
+    n = oracle_lib().oracle_refine_corners(_ptr(image, _u8p), h, w, image.strides[0], level,
+                                           _ptr(xy, _f64p), _ptr(levels, _i8p), len(levels))
+    return n, xy, levels
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference itself (oracle/_ref)
+# ---------------------------------------------------------------------------------------------
+def ref_chess_response_5(image, fill=0):
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.full((h, w), fill, dtype=np.int16)
+    ref_lib().ref_ChESS_response_5(_ptr(out, _i16p), _ptr(image, _u8p), w, h, image.strides[0])
+    return out
+
+
+def ref_find_corners(image, level=0, cap=1 << 20):
+    image = _check_image(image)
+    h, w = image.shape
+    xy = np.empty((cap, 2), dtype=np.int32)
+    n = ref_lib().ref_find_chessboard_corners(_ptr(image, _u8p), h, w, image.strides[0], level,
+                                              _ptr(xy, _i32p), cap)
+    assert n <= cap
+    return xy[:n].copy()
+
+
+def ref_refine_corners(image, level, xy, levels):
+    image = _check_image(image)
+    h, w = image.shape
+    xy = np.ascontiguousarray(xy, dtype=np.float64).copy()
+    levels = np.ascontiguousarray(levels, dtype=np.int8).copy()
+    n = ref_lib().ref_refine_chessboard_corners(_ptr(image, _u8p), h, w, image.strides[0], level,
+                                                _ptr(xy, _f64p), _ptr(levels, _i8p), len(levels))
+    return n, xy, levels
+
+
+def ref_shim_resize(image, level):
+    image = _check_image(image)
+    h, w = image.shape
+    oh, ow = ctypes.c_int(), ctypes.c_int()
+    ref_lib().ref_shim_resize(_ptr(image, _u8p), h, w, image.strides[0], level, None,
+                              ctypes.byref(oh), ctypes.byref(ow))
+    out = np.empty((oh.value, ow.value), dtype=np.uint8)
+    ref_lib().ref_shim_resize(_ptr(image, _u8p), h, w, image.strides[0], level, _ptr(out, _u8p),
+                              ctypes.byref(oh), ctypes.byref(ow))
+    return out
