@@ -1,0 +1,162 @@
+/*
+  mrgingham_b200 -- C ABI of the B200-native (sm_100a) chessboard-corner detector.
+
+  This library replaces ONE hot path of dkogan/mrgingham: the per-image corner detector
+  (ChESS response -> pyramid level -> connected-component clustering -> sub-pixel centroid).
+  All compute runs in hand-written CUDA kernels; there is no CPU fallback: every entry point
+  fails (returns false / <0 and prints a diagnostic) when no CUDA device is usable.
+
+  Section A re-exports, with identical names, signatures and error behaviour, the C symbols the
+  reference library already exposes for this path, so a build of the reference can link this
+  library in place of ChESS.c + find_chessboard_corners.cc.
+  Section B is the C mirror of the reference's C++ API for the path (the C++ spellings live in
+  include/mrgingham_b200/find_chessboard_corners.hh as inline adapters over these).
+  Section C is additive: batched, device-resident entry points that the reference has no
+  equivalent of (precedent for batch semantics: the Python ChESS_response_5 broadcasts over
+  leading dimensions, mrgingham_pywrap.c:84-103).
+
+  Conventions (same as the reference): 8-bit single-channel images, rows
+  contiguous, `stride` in bytes; the caller owns every buffer; no exceptions cross this ABI;
+  diagnostics go to stderr as "file:line in func(): ... Sorry.". All functions are thread-safe.
+*/
+#ifndef MRGINGHAM_B200_H
+#define MRGINGHAM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===========================================================================================
+   A. Drop-in symbols (names and signatures of the reference)
+   =========================================================================================== */
+
+/* Replaces ChESS.c:55-106 (declared in ChESS.h:31-34).
+   response: dense int16 [h][w] HOST buffer; image: uint8 HOST buffer with row pitch `stride`.
+   Writes 7 <= x < w-7, 7 <= y < h-7 only; every other element of `response` is left untouched,
+   exactly as the reference does. */
+void mrgingham_ChESS_response_5(int16_t*       response,
+                                const uint8_t* image,
+                                int w, int h, int stride);
+
+/* Replaces mrgingham_pywrap_cplusplus_bridge.cc:28-70 (declared in
+   mrgingham_pywrap_cplusplus_bridge.h:10-23): the C bridge the reference's Python module binds.
+   Returns false when nothing was found, on error, or when doblobs is set (the blob detector is
+   not built yet: see DESIGN.md, scope); otherwise calls
+   add_points(xy, N, 1/1000., cookie) once and returns its result. */
+bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols,
+                                                int stride,
+                                                char* imagebuffer, /* const */
+                                                int image_pyramid_level,
+                                                bool doblobs,
+                                                bool debug,
+                                                bool (*add_points)(int* xy, int N, double scale, void* cookie),
+                                                void* cookie);
+
+/* ===========================================================================================
+   B. C mirror of the reference's C++ API for the path
+   =========================================================================================== */
+
+/* mrgingham::find_chessboard_corners_from_image_array(), find_chessboard_corners.cc:568-587.
+   Returns the number of corners found (0 on any of the reference's error paths: level outside
+   [0,10], level 0 with stride != Ncols) or <0 on a CUDA failure; writes min(N, cap) points into
+   xy_out as (x,y) pairs scaled by 1000 (mrgingham-internal.h:3), in the reference's order. */
+int mrg_b200_find_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride,
+                                     int image_pyramid_level,
+                                     int* xy_out, int cap);
+
+/* mrgingham::refine_chessboard_corners_from_image_array(), find_chessboard_corners.cc:591-619.
+   xy_inout: Npoints (x,y) doubles in full-resolution pixels, level[]: per-point pyramid level;
+   points with level[i] == image_pyramid_level+1 are refined in place and their level lowered.
+   Returns the number of points refined, <0 on a CUDA failure. */
+int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride,
+                                       int image_pyramid_level,
+                                       double* xy_inout, signed char* level, int Npoints);
+
+/* ===========================================================================================
+   C. Batched / device-resident entry points (additive)
+   =========================================================================================== */
+
+typedef struct mrg_b200_detector mrg_b200_detector;
+
+typedef struct
+{
+    int device;               /* CUDA device ordinal; <0 = the calling thread's current device  */
+    int max_frames;           /* frames processed per internal chunk (scratch is sized for it)  */
+    int max_rows, max_cols;   /* largest frame this detector will be given                      */
+    int candidate_capacity;   /* per-frame capacity of the sparse {response>15} list; rounded up
+                                 to a power of two; 0 = default. Frames that overflow it are
+                                 re-run on the GPU with a capacity of rows*cols.                 */
+    int max_points;           /* per-frame output capacity (corners); 0 = default 1024           */
+    int kernel_variant;       /* 0 = default; 1 = the simple one-thread-per-pixel ChESS kernel   */
+} mrg_b200_detector_config;
+
+/* returns 0 and a detector, or <0 */
+int  mrg_b200_detector_create (mrg_b200_detector** det, const mrg_b200_detector_config* config);
+void mrg_b200_detector_destroy(mrg_b200_detector* det);
+
+/* Corner detection over a batch of equally-sized frames.
+     images           first frame; frame i starts at images + i*frame_stride; rows are row_pitch apart
+     images_on_device nonzero: device pointer (no copy); zero: host pointer (copied inside)
+     xy_out           HOST int32 [nframes][max_points][2], scaled by 1000
+     counts_out       HOST int32 [nframes]: corners found per frame (may exceed max_points; only
+                      the first max_points are stored)
+     stream           a cudaStream_t (as void*) to run on, or NULL for the detector's own stream
+   Synchronous: results are in host memory on return. Returns 0 or <0. */
+int mrg_b200_find_corners_batch(mrg_b200_detector* det,
+                                const uint8_t* images, int images_on_device,
+                                int nframes, int rows, int cols,
+                                size_t row_pitch, size_t frame_stride,
+                                int image_pyramid_level,
+                                int32_t* xy_out, int32_t* counts_out,
+                                void* stream);
+
+/* Same work, split so a caller can time the device part with its own CUDA events:
+   enqueue() only enqueues (copies, kernels, result copies into the detector's pinned buffers) on
+   `stream`; collect() synchronises that stream, handles overflowed frames and fills the outputs. */
+int mrg_b200_find_corners_batch_enqueue(mrg_b200_detector* det,
+                                        const uint8_t* images, int images_on_device,
+                                        int nframes, int rows, int cols,
+                                        size_t row_pitch, size_t frame_stride,
+                                        int image_pyramid_level, void* stream);
+int mrg_b200_find_corners_batch_collect(mrg_b200_detector* det,
+                                        int32_t* xy_out, int32_t* counts_out);
+
+/* Dense ChESS response over a batch (the batched form of section A's function).
+   response: int16 [nframes][rows][cols]; elements outside the 7-pixel interior are not written. */
+int mrg_b200_chess_response_batch(mrg_b200_detector* det,
+                                  const uint8_t* images, int images_on_device,
+                                  int nframes, int rows, int cols,
+                                  size_t row_pitch, size_t frame_stride,
+                                  int16_t* response, int response_on_device,
+                                  void* stream);
+
+/* Pyramid level image (what the reference gets from cv::resize, find_chessboard_corners.cc:449-450).
+   out: HOST uint8 [orows][ocols] dense; returns 0 and the size, or <0. */
+int mrg_b200_pyramid_level(mrg_b200_detector* det,
+                           const uint8_t* image, int rows, int cols, size_t row_pitch,
+                           int image_pyramid_level,
+                           uint8_t* out, int* orows, int* ocols);
+
+/* Accumulated device time (CUDA events on the launching stream) of the kernels launched by the
+   most recent batch call, and how many kernels that call launched. which: 0 = ChESS+candidate
+   kernel, 1 = clustering kernel, 2 = pyramid kernel. */
+int mrg_b200_last_kernel_ms(mrg_b200_detector* det, int which, float* ms, int* launches);
+void mrg_b200_set_profiling(mrg_b200_detector* det, int enabled);
+
+/* per-frame size of the sparse candidate list seen by the most recent batch call (HOST int32
+   [nframes]); for tests and capacity planning */
+int mrg_b200_last_candidate_counts(mrg_b200_detector* det, int32_t* counts_out, int nframes);
+
+const char* mrg_b200_version(void);
+
+/* number of CUDA devices this process can use; 0 means every other entry point will fail */
+int mrg_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

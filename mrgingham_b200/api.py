@@ -1,0 +1,301 @@
+"""ctypes binding of libmrgingham_b200.so and the Python mirror of the reference's module."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmrgingham_b200.so")
+_lib = None
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i16p = ctypes.POINTER(ctypes.c_int16)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_i8p = ctypes.POINTER(ctypes.c_int8)
+_ADD_POINTS = ctypes.CFUNCTYPE(ctypes.c_bool, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_double, ctypes.c_void_p)
+
+EXPORTS = (
+    "mrgingham_ChESS_response_5", "find_chessboard_corners_from_image_array_C",
+    "mrg_b200_find_chessboard_corners", "mrg_b200_refine_chessboard_corners",
+    "mrg_b200_detector_create", "mrg_b200_detector_destroy",
+    "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
+    "mrg_b200_chess_response_batch", "mrg_b200_pyramid_level",
+    "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
+    "mrg_b200_device_count",
+)
+
+
+class DetectorConfig(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("max_frames", ctypes.c_int),
+                ("max_rows", ctypes.c_int), ("max_cols", ctypes.c_int),
+                ("candidate_capacity", ctypes.c_int), ("max_points", ctypes.c_int),
+                ("kernel_variant", ctypes.c_int)]
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def lib():
+    """the loaded C-ABI library; raises if it is missing (there is no other implementation)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} is missing: build it with `python -m mrgingham_b200.build` "
+                          "(needs nvcc). mrgingham_b200 has no CPU fallback.")
+    L = ctypes.CDLL(_LIB_PATH)
+    L.mrgingham_ChESS_response_5.restype = None
+    L.mrgingham_ChESS_response_5.argtypes = [_i16p, _u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.find_chessboard_corners_from_image_array_C.restype = ctypes.c_bool
+    L.find_chessboard_corners_from_image_array_C.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_bool, ctypes.c_bool,
+        _ADD_POINTS, ctypes.c_void_p]
+    L.mrg_b200_find_chessboard_corners.restype = ctypes.c_int
+    L.mrg_b200_find_chessboard_corners.argtypes = [_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, ctypes.c_int]
+    L.mrg_b200_refine_chessboard_corners.restype = ctypes.c_int
+    L.mrg_b200_refine_chessboard_corners.argtypes = [_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p, _i8p, ctypes.c_int]
+    L.mrg_b200_detector_create.restype = ctypes.c_int
+    L.mrg_b200_detector_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(DetectorConfig)]
+    L.mrg_b200_detector_destroy.restype = None
+    L.mrg_b200_detector_destroy.argtypes = [ctypes.c_void_p]
+    batch_args = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                  ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
+    L.mrg_b200_find_corners_batch.restype = ctypes.c_int
+    L.mrg_b200_find_corners_batch.argtypes = batch_args + [_i32p, _i32p, ctypes.c_void_p]
+    L.mrg_b200_find_corners_batch_enqueue.restype = ctypes.c_int
+    L.mrg_b200_find_corners_batch_enqueue.argtypes = batch_args + [ctypes.c_void_p]
+    L.mrg_b200_find_corners_batch_collect.restype = ctypes.c_int
+    L.mrg_b200_find_corners_batch_collect.argtypes = [ctypes.c_void_p, _i32p, _i32p]
+    L.mrg_b200_chess_response_batch.restype = ctypes.c_int
+    L.mrg_b200_chess_response_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.mrg_b200_pyramid_level.restype = ctypes.c_int
+    L.mrg_b200_pyramid_level.argtypes = [ctypes.c_void_p, _u8p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int,
+                                         _u8p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    L.mrg_b200_last_kernel_ms.restype = ctypes.c_int
+    L.mrg_b200_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]
+    L.mrg_b200_set_profiling.restype = None
+    L.mrg_b200_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.mrg_b200_last_candidate_counts.restype = ctypes.c_int
+    L.mrg_b200_last_candidate_counts.argtypes = [ctypes.c_void_p, _i32p, ctypes.c_int]
+    L.mrg_b200_version.restype = ctypes.c_char_p
+    L.mrg_b200_device_count.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def version():
+    return lib().mrg_b200_version().decode()
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _require_gpu():
+    if lib().mrg_b200_device_count() <= 0:
+        raise RuntimeError("mrgingham_b200: no usable CUDA device, and there is no CPU fallback")
+
+
+def _check_image(image, ndim_exact=None):
+    image = np.asarray(image)
+    if ndim_exact is not None and image.ndim != ndim_exact:
+        raise RuntimeError(f"The input image array must have exactly {ndim_exact} dims (broadcasting not supported here); got {image.ndim}")
+    if image.dtype != np.uint8:
+        raise RuntimeError("The input image array must contain 8-bit unsigned data")
+    if image.strides[-1] != 1:
+        raise RuntimeError("Image rows must live in contiguous memory")
+    return image
+
+
+# ---------------------------------------------------------------------------------------------
+# Mirror of the reference's Python module (mrgingham_pywrap.c)
+# ---------------------------------------------------------------------------------------------
+def ChESS_response_5(image):
+    """mrgingham.ChESS_response_5 (mrgingham_pywrap.c:40-112): int16 response of uint8 image(s)
+    [..., H, W]; leading dimensions are broadcast. Elements within 7 pixels of the border, which
+    the reference leaves uninitialised, are 0 here."""
+    image = np.asarray(image)
+    if image.ndim < 2:
+        raise RuntimeError(f"The input image array must have at least 2 dims (extra ones will be broadcasted); got {image.ndim}")
+    image = _check_image(image)
+    _require_gpu()
+    out = np.zeros(image.shape, dtype=np.int16)
+    h, w = image.shape[-2:]
+    L = lib()
+    for idx in np.ndindex(*image.shape[:-2]):
+        sl = image[idx]
+        L.mrgingham_ChESS_response_5(_ptr(out[idx], _i16p), _ptr(sl, _u8p), w, h, sl.strides[0])
+    return out
+
+
+def find_points(image, image_pyramid_level=0, blobs=False, debug=False):
+    """mrgingham.find_points (mrgingham_pywrap.c:128-225): (N,2) float64 corner coordinates
+    (x,y) in full-resolution pixels; (0,2) if nothing was found."""
+    if blobs and image_pyramid_level != 0:
+        raise RuntimeError("blob detector requires that image_pyramid_level == 0")
+    image = _check_image(image, ndim_exact=2)
+    _require_gpu()
+    result = {}
+
+    def add_points(xy, n, scale, cookie):
+        a = np.ctypeslib.as_array(xy, shape=(2 * n,)).astype(np.float64)
+        result["xy"] = (scale * a).reshape(n, 2)
+        return True
+
+    cb = _ADD_POINTS(add_points)
+    ok = lib().find_chessboard_corners_from_image_array_C(image.shape[0], image.shape[1], image.strides[0],
+                                                          image.ctypes.data, int(image_pyramid_level),
+                                                          bool(blobs), bool(debug), cb, None)
+    if not ok or "xy" not in result:
+        return np.zeros((0, 2), dtype=np.float64)
+    return result["xy"]
+
+
+find_chessboard_corners = find_points
+
+
+def find_board(*args, **kwargs):
+    """mrgingham.find_board needs the grid finder (find_grid.cc), which is outside the hot path
+    this package replaces."""
+    raise NotImplementedError("find_board: the grid search is not part of mrgingham_b200; feed find_points() "
+                              "output to the reference's find_grid_from_points()")
+
+
+find_chessboard = find_board
+
+
+# ---------------------------------------------------------------------------------------------
+# C++ API mirrors and batch interface
+# ---------------------------------------------------------------------------------------------
+def find_chessboard_corners_int(image, image_pyramid_level=0, cap=1 << 16):
+    """mrgingham::find_chessboard_corners_from_image_array: (N,2) int32 PointInt list (x1000)"""
+    image = _check_image(image, ndim_exact=2)
+    _require_gpu()
+    xy = np.empty((cap, 2), dtype=np.int32)
+    n = lib().mrg_b200_find_chessboard_corners(_ptr(image, _u8p), image.shape[0], image.shape[1], image.strides[0],
+                                               int(image_pyramid_level), _ptr(xy, _i32p), cap)
+    if n < 0:
+        raise RuntimeError("mrg_b200_find_chessboard_corners() failed")
+    if n > cap:
+        return find_chessboard_corners_int(image, image_pyramid_level, cap=n)
+    return xy[:n].copy()
+
+
+def refine_chessboard_corners(image, image_pyramid_level, xy, levels):
+    """mrgingham::refine_chessboard_corners_from_image_array: returns (nrefined, xy', levels')"""
+    image = _check_image(image, ndim_exact=2)
+    xy = np.ascontiguousarray(xy, dtype=np.float64).copy()
+    levels = np.ascontiguousarray(levels, dtype=np.int8).copy()
+    n = lib().mrg_b200_refine_chessboard_corners(_ptr(image, _u8p), image.shape[0], image.shape[1], image.strides[0],
+                                                 int(image_pyramid_level), _ptr(xy, _f64p), _ptr(levels, _i8p), len(levels))
+    if n < 0:
+        raise RuntimeError("mrg_b200_refine_chessboard_corners() failed")
+    return n, xy, levels
+
+
+class Detector:
+    """Batched detector over equally-sized frames (include/mrgingham_b200.h section C)."""
+
+    def __init__(self, max_frames=64, max_rows=0, max_cols=0, candidate_capacity=0, max_points=0, device=-1,
+                 kernel_variant=0):
+        self._h = ctypes.c_void_p()
+        cfg = DetectorConfig(device, max_frames, max_rows, max_cols, candidate_capacity, max_points, kernel_variant)
+        if lib().mrg_b200_detector_create(ctypes.byref(self._h), ctypes.byref(cfg)) != 0:
+            raise RuntimeError("mrg_b200_detector_create() failed (no CUDA device?)")
+        self.max_points = max_points if max_points > 0 else 1024
+
+    def close(self):
+        if self._h:
+            lib().mrg_b200_detector_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _describe(images):
+        """(pointer, on_device, n, rows, cols, pitch, frame_stride, keepalive) of a numpy array or a
+        torch tensor shaped [n, rows, cols] uint8 with contiguous rows"""
+        if isinstance(images, np.ndarray):
+            a = images if images.ndim == 3 else images[None]
+            if a.shape[0] == 0:
+                return 0, 0, 0, a.shape[1], a.shape[2], a.shape[2], a.shape[1] * a.shape[2], a
+            assert a.dtype == np.uint8 and a.strides[2] == 1
+            return a.ctypes.data, 0, a.shape[0], a.shape[1], a.shape[2], a.strides[1], a.strides[0] if a.shape[0] > 1 else a.strides[1] * a.shape[1], a
+        import torch
+        assert isinstance(images, torch.Tensor) and images.dtype == torch.uint8
+        t = images if images.dim() == 3 else images[None]
+        assert t.stride(2) == 1
+        fstride = t.stride(0) if t.shape[0] > 1 else t.stride(1) * t.shape[1]
+        return t.data_ptr(), 1 if t.is_cuda else 0, t.shape[0], t.shape[1], t.shape[2], t.stride(1), fstride, t
+
+    def enqueue(self, images, level=0, stream=None):
+        ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
+        self._pending = (n, keep)
+        rc = lib().mrg_b200_find_corners_batch_enqueue(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(level),
+                                                      ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_find_corners_batch_enqueue() failed")
+
+    def collect(self):
+        n, _ = self._pending
+        xy = np.empty((n, self.max_points, 2), dtype=np.int32)
+        counts = np.empty(n, dtype=np.int32)
+        if lib().mrg_b200_find_corners_batch_collect(self._h, _ptr(xy, _i32p), _ptr(counts, _i32p)) != 0:
+            raise RuntimeError("mrg_b200_find_corners_batch_collect() failed")
+        self._pending = None
+        return xy, counts
+
+    def find_corners(self, images, level=0, stream=None):
+        """returns (xy int32 [n, max_points, 2] scaled by 1000, counts int32 [n])"""
+        self.enqueue(images, level, stream)
+        return self.collect()
+
+    def chess_response(self, images):
+        """dense int16 response of host images [n, rows, cols] (border elements are 0)"""
+        ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
+        assert not on_dev
+        out = np.zeros((n, rows, cols), dtype=np.int16)
+        if lib().mrg_b200_chess_response_batch(self._h, ptr, 0, n, rows, cols, pitch, fstride, out.ctypes.data, 0, None) != 0:
+            raise RuntimeError("mrg_b200_chess_response_batch() failed")
+        return out
+
+    def set_profiling(self, enabled=True):
+        lib().mrg_b200_set_profiling(self._h, 1 if enabled else 0)
+
+    def last_kernel_ms(self, which):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        lib().mrg_b200_last_kernel_ms(self._h, which, ctypes.byref(ms), ctypes.byref(n))
+        return ms.value, n.value
+
+    def last_candidate_counts(self, n):
+        c = np.empty(n, dtype=np.int32)
+        lib().mrg_b200_last_candidate_counts(self._h, _ptr(c, _i32p), n)
+        return c
+
+    def pyramid_level(self, image, level):
+        image = _check_image(image, ndim_exact=2)
+        oh, ow = ctypes.c_int(), ctypes.c_int()
+        if lib().mrg_b200_pyramid_level(self._h, _ptr(image, _u8p), image.shape[0], image.shape[1], image.strides[0], level,
+                                        None, ctypes.byref(oh), ctypes.byref(ow)) != 0:
+            return None
+        out = np.empty((oh.value, ow.value), dtype=np.uint8)
+        lib().mrg_b200_pyramid_level(self._h, _ptr(image, _u8p), image.shape[0], image.shape[1], image.strides[0], level,
+                                     _ptr(out, _u8p), ctypes.byref(oh), ctypes.byref(ow))
+        return out
+
+
+_default_detector = None
+
+
+def pyramid_level(image, level):
+    global _default_detector
+    if _default_detector is None:
+        _default_detector = Detector(max_frames=1)
+    return _default_detector.pyramid_level(image, level)

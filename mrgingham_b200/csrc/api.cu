@@ -1,0 +1,582 @@
+// Host side of libmrgingham_b200.so: the C ABI of include/mrgingham_b200.h over the kernels.
+// No CPU implementation of anything lives here: if CUDA is unusable every entry point fails loudly.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/mrgingham_b200.h"
+#include "kernels.cuh"
+
+using namespace mrgb200;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+#define MSG(fmt, ...) fprintf(stderr, "%s:%d in %s(): " fmt " Sorry.\n", __FILE__, __LINE__, __func__, ##__VA_ARGS__)
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            MSG("CUDA failure '%s' in " #expr ".", cudaGetErrorString(_e));              \
+            return -1;                                                                   \
+        }                                                                                \
+    } while (0)
+
+static int next_pow2(long long v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static int cv_round_div(int n, int d)  // cvRound(n/d): round half to even, d a power of two
+{
+    int q = n / d, r = n % d;
+    if (2*r > d || (2*r == d && (q & 1))) q++;
+    return q;
+}
+
+namespace
+{
+struct DeviceBuffer
+{
+    void*  p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t want)
+    {
+        if (want <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        CUDA_TRY(cudaMalloc(&p, want));
+        bytes = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+struct PinnedBuffer
+{
+    void*  p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t want)
+    {
+        if (want <= bytes) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        CUDA_TRY(cudaMallocHost(&p, want));
+        bytes = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+};
+
+struct KernelTimer
+{
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    std::vector<cudaEvent_t> pool;
+    float ms = 0; int launches = 0;
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void reset() { for (auto& s : spans) { pool.push_back(s.first); pool.push_back(s.second); } spans.clear(); ms = 0; launches = 0; }
+    void resolve()
+    {
+        for (auto& s : spans) { float t = 0; if (cudaEventElapsedTime(&t, s.first, s.second) == cudaSuccess) ms += t; pool.push_back(s.first); pool.push_back(s.second); }
+        spans.clear();
+    }
+    void release() { reset(); for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};
+}
+
+struct mrg_b200_detector
+{
+    mrg_b200_detector_config cfg;
+    int          device = 0;
+    cudaStream_t own_stream = nullptr;
+    std::mutex   mtx;
+
+    // per-chunk scratch
+    DeviceBuffer stage, level_img, cand, counts, table, dfs, records, xy, outcounts;
+    // scratch for single frames whose candidate list overflowed the default capacity
+    DeviceBuffer big_cand, big_table, big_dfs, big_records;
+    // refinement
+    DeviceBuffer pts, lvls;
+    // results of the batch in flight
+    PinnedBuffer h_xy, h_counts, h_candcounts;
+
+    bool profiling = false;
+    KernelTimer timers[3];
+
+    struct Pending
+    {
+        bool active = false;
+        const uint8_t* images; int on_device, nframes, rows, cols, level; size_t pitch, fstride;
+        cudaStream_t stream;
+    } pending;
+};
+
+namespace
+{
+struct Launch
+{
+    mrg_b200_detector* det; int which; cudaStream_t stream; cudaEvent_t e0 = nullptr;
+    Launch(mrg_b200_detector* d, int w, cudaStream_t s) : det(d), which(w), stream(s)
+    {
+        det->timers[which].launches++;
+        if (det->profiling) { e0 = det->timers[which].get(); cudaEventRecord(e0, stream); }
+    }
+    ~Launch()
+    {
+        if (det->profiling) { cudaEvent_t e1 = det->timers[which].get(); cudaEventRecord(e1, stream); det->timers[which].spans.push_back({e0, e1}); }
+    }
+};
+
+int chess_sparse(mrg_b200_detector* det, const FrameSet& fs, cand_t* cand, uint32_t* counts, int cap, cudaStream_t stream)
+{
+    Launch l(det, 0, stream);
+    if (det->cfg.kernel_variant == 1) CUDA_TRY(launch_chess_sparse_simple(fs, cand, counts, cap, stream));
+    else                              CUDA_TRY(launch_chess_sparse_tiled (fs, cand, counts, cap, stream));
+    return 0;
+}
+
+// geometry of a pyramid level of a rows x cols frame
+struct LevelGeom { int w, h, pitch; size_t frame_bytes; };
+LevelGeom level_geom(int rows, int cols, int level)
+{
+    LevelGeom g;
+    g.w = cv_round_div(cols, 1 << level);
+    g.h = cv_round_div(rows, 1 << level);
+    g.pitch = round_up(std::max(g.w, 1), 16);
+    g.frame_bytes = (size_t)g.pitch * std::max(g.h, 1);
+    return g;
+}
+
+// Puts `n` frames on the device (if they are not there already) and, for level > 0, builds the
+// level image. On return `out` describes the image the detector kernels must read.
+int stage_frames(mrg_b200_detector* det, const uint8_t* images, int on_device, int n, int rows, int cols,
+                 size_t pitch, size_t fstride, int level, cudaStream_t stream, FrameSet* out)
+{
+    FrameSet src;
+    if (on_device)
+    {
+        src.base = images; src.frame_stride = fstride; src.pitch = (int)pitch;
+    }
+    else
+    {
+        const int spitch = round_up(cols, 16);
+        const size_t sframe = (size_t)spitch * rows;
+        if (det->stage.ensure(sframe * n)) return -1;
+        if (fstride == pitch * (size_t)rows)
+            CUDA_TRY(cudaMemcpy2DAsync(det->stage.p, spitch, images, pitch, cols, (size_t)rows * n, cudaMemcpyHostToDevice, stream));
+        else
+            for (int i = 0; i < n; i++)
+                CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)det->stage.p + i * sframe, spitch, images + i * fstride, pitch, cols, rows,
+                                           cudaMemcpyHostToDevice, stream));
+        src.base = (const uint8_t*)det->stage.p; src.frame_stride = sframe; src.pitch = spitch;
+    }
+    src.w = cols; src.h = rows; src.nframes = n;
+    if (level == 0) { *out = src; return 0; }
+
+    const LevelGeom g = level_geom(rows, cols, level);
+    if (det->level_img.ensure(g.frame_bytes * n)) return -1;
+    {
+        Launch l(det, 2, stream);
+        CUDA_TRY(launch_pyramid(src, level, (uint8_t*)det->level_img.p, g.pitch, g.frame_bytes, g.w, g.h, stream));
+    }
+    out->base = (const uint8_t*)det->level_img.p; out->frame_stride = g.frame_bytes; out->pitch = g.pitch;
+    out->w = g.w; out->h = g.h; out->nframes = n;
+    return 0;
+}
+
+int ensure_chunk_scratch(mrg_b200_detector* det, int n)
+{
+    const size_t cap = det->cfg.candidate_capacity, mp = det->cfg.max_points;
+    if (det->cand.ensure(sizeof(cand_t) * cap * n)) return -1;
+    if (det->counts.ensure(sizeof(uint32_t) * n)) return -1;
+    if (det->table.ensure(sizeof(uint32_t) * 2 * cap * n)) return -1;
+    if (det->dfs.ensure(sizeof(uint32_t) * cap * n)) return -1;
+    if (det->records.ensure(cluster_record_bytes() * 2 * mp * n)) return -1;
+    if (det->xy.ensure(sizeof(int32_t) * 2 * mp * n)) return -1;
+    if (det->outcounts.ensure(sizeof(int32_t) * n)) return -1;
+    return 0;
+}
+
+// One frame whose candidate list (or component list) overflowed the chunk scratch: run it again
+// on the GPU with worst-case capacities.
+int rerun_big(mrg_b200_detector* det, const uint8_t* image, int on_device, int rows, int cols, size_t pitch,
+              int level, cudaStream_t stream, int32_t* xy_out, int32_t* count_out, int32_t* candcount_out)
+{
+    FrameSet fs;
+    if (stage_frames(det, image, on_device, 1, rows, cols, pitch, pitch * rows, level, stream, &fs)) return -1;
+    const int cap = next_pow2((long long)fs.w * fs.h);
+    const int mp = det->cfg.max_points;
+    const int reccap = cap / 2 + 1;
+    if (det->big_cand.ensure(sizeof(cand_t) * cap)) return -1;
+    if (det->big_table.ensure(sizeof(uint32_t) * 2 * cap)) return -1;
+    if (det->big_dfs.ensure(sizeof(uint32_t) * cap)) return -1;
+    if (det->big_records.ensure(cluster_record_bytes() * reccap)) return -1;
+    if (ensure_chunk_scratch(det, 1)) return -1;
+    CUDA_TRY(cudaMemsetAsync(det->counts.p, 0, sizeof(uint32_t), stream));
+    if (chess_sparse(det, fs, (cand_t*)det->big_cand.p, (uint32_t*)det->counts.p, cap, stream)) return -1;
+    ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = reccap; p.records = det->big_records.p;
+    {
+        Launch l(det, 1, stream);
+        CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)det->big_cand.p, (uint32_t*)det->counts.p, (uint32_t*)det->big_table.p,
+                                     (uint32_t*)det->big_dfs.p, (int32_t*)det->xy.p, nullptr, (int32_t*)det->outcounts.p, stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(xy_out, det->xy.p, sizeof(int32_t) * 2 * mp, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(count_out, det->outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(candcount_out, det->counts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (*count_out < 0) { MSG("Frame still overflows at worst-case capacity; this is a bug."); return -1; }
+    return 0;
+}
+
+int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device, int nframes, int rows, int cols,
+                   size_t pitch, size_t fstride, int level, cudaStream_t stream)
+{
+    if (det->pending.active) { MSG("A batch is already in flight on this detector: collect it first."); return -1; }
+    if (nframes < 0 || rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767 || pitch < (size_t)cols)
+    { MSG("Bad batch geometry (nframes=%d rows=%d cols=%d pitch=%zu).", nframes, rows, cols, pitch); return -1; }
+    if (rows > det->cfg.max_rows || cols > det->cfg.max_cols)
+    { MSG("Frame %dx%d exceeds the detector's configured maximum %dx%d.", cols, rows, det->cfg.max_cols, det->cfg.max_rows); return -1; }
+    if (level < 0 || level > 10)
+    { MSG("Got an unreasonable image_pyramid_level = %d.", level); return -1; }
+    CUDA_TRY(cudaSetDevice(det->device));
+    for (auto& t : det->timers) t.reset();
+
+    const int mp = det->cfg.max_points, cap = det->cfg.candidate_capacity;
+    if (det->h_xy.ensure(sizeof(int32_t) * 2 * mp * std::max(nframes, 1))) return -1;
+    if (det->h_counts.ensure(sizeof(int32_t) * std::max(nframes, 1))) return -1;
+    if (det->h_candcounts.ensure(sizeof(int32_t) * std::max(nframes, 1))) return -1;
+
+    const int chunk = det->cfg.max_frames;
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        FrameSet fs;
+        if (stage_frames(det, images + (size_t)f0 * fstride, on_device, n, rows, cols, pitch, fstride, level, stream, &fs)) return -1;
+        if (ensure_chunk_scratch(det, n)) return -1;
+        CUDA_TRY(cudaMemsetAsync(det->counts.p, 0, sizeof(uint32_t) * n, stream));
+        if (chess_sparse(det, fs, (cand_t*)det->cand.p, (uint32_t*)det->counts.p, cap, stream)) return -1;
+        ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = 2 * mp; p.records = det->records.p;
+        {
+            Launch l(det, 1, stream);
+            CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)det->cand.p, (uint32_t*)det->counts.p, (uint32_t*)det->table.p,
+                                         (uint32_t*)det->dfs.p, (int32_t*)det->xy.p, nullptr, (int32_t*)det->outcounts.p, stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_xy.p + (size_t)f0 * 2 * mp, det->xy.p, sizeof(int32_t) * 2 * mp * n, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_counts.p + f0, det->outcounts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_candcounts.p + f0, det->counts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream));
+    }
+    det->pending.active = true;
+    det->pending.images = images; det->pending.on_device = on_device; det->pending.nframes = nframes;
+    det->pending.rows = rows; det->pending.cols = cols; det->pending.level = level;
+    det->pending.pitch = pitch; det->pending.fstride = fstride; det->pending.stream = stream;
+    return 0;
+}
+
+int collect_locked(mrg_b200_detector* det, int32_t* xy_out, int32_t* counts_out)
+{
+    if (!det->pending.active) { MSG("No batch in flight."); return -1; }
+    auto& pd = det->pending;
+    pd.active = false;
+    CUDA_TRY(cudaSetDevice(det->device));
+    CUDA_TRY(cudaStreamSynchronize(pd.stream));
+    for (auto& t : det->timers) t.resolve();
+    const int mp = det->cfg.max_points;
+    int32_t* hxy = (int32_t*)det->h_xy.p; int32_t* hc = (int32_t*)det->h_counts.p; int32_t* hcc = (int32_t*)det->h_candcounts.p;
+    for (int f = 0; f < pd.nframes; f++)
+        if (hc[f] < 0)
+            if (rerun_big(det, pd.images + (size_t)f * pd.fstride, pd.on_device, pd.rows, pd.cols, pd.pitch, pd.level, pd.stream,
+                          hxy + (size_t)f * 2 * mp, hc + f, hcc + f)) return -1;
+    if (xy_out)     memcpy(xy_out, hxy, sizeof(int32_t) * 2 * mp * pd.nframes);
+    if (counts_out) memcpy(counts_out, hc, sizeof(int32_t) * pd.nframes);
+    return 0;
+}
+}
+
+// =================================================================================================
+// C. batched API
+// =================================================================================================
+API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detector_config* config)
+{
+    if (!out || !config) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    {
+        MSG("No usable CUDA device: this library has no CPU implementation.");
+        return -1;
+    }
+    mrg_b200_detector* det = new mrg_b200_detector;
+    det->cfg = *config;
+    if (det->cfg.device < 0) { if (cudaGetDevice(&det->cfg.device) != cudaSuccess) { delete det; return -1; } }
+    det->device = det->cfg.device;
+    if (det->cfg.max_frames <= 0) det->cfg.max_frames = 64;
+    if (det->cfg.max_rows <= 0) det->cfg.max_rows = 32767;
+    if (det->cfg.max_cols <= 0) det->cfg.max_cols = 32767;
+    if (det->cfg.candidate_capacity <= 0) det->cfg.candidate_capacity = 32768;
+    det->cfg.candidate_capacity = next_pow2(det->cfg.candidate_capacity);
+    if (det->cfg.max_points <= 0) det->cfg.max_points = 1024;
+    if (cudaSetDevice(det->device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&det->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        MSG("Could not initialise CUDA device %d.", det->device);
+        delete det;
+        return -1;
+    }
+    *out = det;
+    return 0;
+}
+
+API void mrg_b200_detector_destroy(mrg_b200_detector* det)
+{
+    if (!det) return;
+    cudaSetDevice(det->device);
+    cudaDeviceSynchronize();
+    for (DeviceBuffer* b : { &det->stage, &det->level_img, &det->cand, &det->counts, &det->table, &det->dfs, &det->records,
+                             &det->xy, &det->outcounts, &det->big_cand, &det->big_table, &det->big_dfs, &det->big_records,
+                             &det->pts, &det->lvls }) b->release();
+    for (PinnedBuffer* b : { &det->h_xy, &det->h_counts, &det->h_candcounts }) b->release();
+    for (auto& t : det->timers) t.release();
+    if (det->own_stream) cudaStreamDestroy(det->own_stream);
+    delete det;
+}
+
+API int mrg_b200_find_corners_batch_enqueue(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                            int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                            int image_pyramid_level, void* stream)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    return enqueue_locked(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, image_pyramid_level,
+                          stream ? (cudaStream_t)stream : det->own_stream);
+}
+
+API int mrg_b200_find_corners_batch_collect(mrg_b200_detector* det, int32_t* xy_out, int32_t* counts_out)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    return collect_locked(det, xy_out, counts_out);
+}
+
+API int mrg_b200_find_corners_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                    int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                    int image_pyramid_level, int32_t* xy_out, int32_t* counts_out, void* stream)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (enqueue_locked(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, image_pyramid_level,
+                       stream ? (cudaStream_t)stream : det->own_stream)) return -1;
+    return collect_locked(det, xy_out, counts_out);
+}
+
+API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                      int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                      int16_t* response, int response_on_device, void* stream_)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+    if (nframes <= 0 || rows <= 0 || cols <= 0 || row_pitch < (size_t)cols) { MSG("Bad batch geometry."); return -1; }
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    CUDA_TRY(cudaSetDevice(det->device));
+    const size_t fe = (size_t)rows * cols;
+    const int chunk = response_on_device ? nframes : std::max(1, det->cfg.max_frames);
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        FrameSet fs;
+        if (stage_frames(det, images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride, 0, stream, &fs)) return -1;
+        int16_t* dresp;
+        if (response_on_device) dresp = response + (size_t)f0 * fe;
+        else
+        {
+            // scratch: reuse the candidate buffer allocation
+            if (det->cand.ensure(sizeof(int16_t) * fe * n)) return -1;
+            dresp = (int16_t*)det->cand.p;
+        }
+        CUDA_TRY(launch_chess_dense(fs, dresp, fe, stream));
+        if (!response_on_device && cols > 2*kMargin && rows > 2*kMargin)
+        {
+            // only the interior travels back: the caller's border elements stay untouched (ChESS.c:62-63)
+            for (int i = 0; i < n; i++)
+            {
+                const size_t off = (size_t)i * fe + (size_t)kMargin * cols + kMargin;
+                CUDA_TRY(cudaMemcpy2DAsync(response + (size_t)(f0 + i) * fe + (size_t)kMargin * cols + kMargin, sizeof(int16_t) * cols,
+                                           dresp + off, sizeof(int16_t) * cols,
+                                           sizeof(int16_t) * (cols - 2*kMargin), rows - 2*kMargin, cudaMemcpyDeviceToHost, stream));
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+API int mrg_b200_pyramid_level(mrg_b200_detector* det, const uint8_t* image, int rows, int cols, size_t row_pitch,
+                               int level, uint8_t* out, int* orows, int* ocols)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (level < 0 || level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); return -1; }
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t stream = det->own_stream;
+    FrameSet fs;
+    if (stage_frames(det, image, 0, 1, rows, cols, row_pitch, row_pitch * rows, level, stream, &fs)) return -1;
+    *orows = fs.h; *ocols = fs.w;
+    if (out && fs.w > 0 && fs.h > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(out, fs.w, fs.base, fs.pitch, fs.w, fs.h, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+API int mrg_b200_last_kernel_ms(mrg_b200_detector* det, int which, float* ms, int* launches)
+{
+    if (!det || which < 0 || which > 2) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (ms) *ms = det->timers[which].ms;
+    if (launches) *launches = det->timers[which].launches;
+    return 0;
+}
+API void mrg_b200_set_profiling(mrg_b200_detector* det, int enabled) { if (det) { std::lock_guard<std::mutex> g(det->mtx); det->profiling = enabled != 0; } }
+
+API int mrg_b200_last_candidate_counts(mrg_b200_detector* det, int32_t* counts_out, int nframes)
+{
+    if (!det || !det->h_candcounts.p) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    memcpy(counts_out, det->h_candcounts.p, sizeof(int32_t) * nframes);
+    return 0;
+}
+
+API const char* mrg_b200_version(void) { return "mrgingham_b200 0.1 (sm_100a)"; }
+
+API int mrg_b200_device_count(void)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 0;
+    return ndev;
+}
+
+// =================================================================================================
+// A/B. single-image entry points on a process-wide default detector
+// =================================================================================================
+static std::mutex g_default_mtx;
+static mrg_b200_detector* g_default = nullptr;
+
+static mrg_b200_detector* default_detector()
+{
+    // callers hold g_default_mtx
+    if (g_default) return g_default;
+    mrg_b200_detector_config cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.device = -1; cfg.max_frames = 1; cfg.candidate_capacity = 65536; cfg.max_points = 4096;
+    if (mrg_b200_detector_create(&g_default, &cfg)) return nullptr;
+    return g_default;
+}
+
+API int mrg_b200_find_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride, int level,
+                                         int* xy_out, int cap)
+{
+    // the reference's error paths give "no points" (find_chessboard_corners.cc:433-441, :461-466)
+    if (level < 0 || level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); return 0; }
+    if (level == 0 && Nrows > 1 && stride != Ncols) { MSG("I can only handle continuous arrays (stride == width) currently."); return 0; }
+    std::lock_guard<std::mutex> g(g_default_mtx);
+    mrg_b200_detector* det = default_detector();
+    if (!det) return -1;
+    const int mp = det->cfg.max_points;
+    std::vector<int32_t> xy((size_t)2 * mp);
+    int32_t n = 0;
+    if (mrg_b200_find_corners_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, xy.data(), &n, nullptr)) return -1;
+    if (n > mp)
+    {
+        // more corners than the default output capacity: grow it and run again
+        det->cfg.max_points = next_pow2(n);
+        xy.resize((size_t)2 * det->cfg.max_points);
+        if (mrg_b200_find_corners_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, xy.data(), &n, nullptr)) return -1;
+    }
+    for (int i = 0; i < n && i < cap; i++) { xy_out[2*i] = xy[2*i]; xy_out[2*i + 1] = xy[2*i + 1]; }
+    return n;
+}
+
+API bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols, int stride, char* imagebuffer,
+                                                    int image_pyramid_level, bool doblobs, bool debug,
+                                                    bool (*add_points)(int* xy, int N, double scale, void* cookie), void* cookie)
+{
+    (void)debug; // the reference's debug mode only writes /tmp dumps
+    if (doblobs)
+    {
+        if (image_pyramid_level != 0) return false;
+        MSG("The blob detector is not part of this build (chessboard corners only).");
+        return false;
+    }
+    int cap = 4096;
+    std::vector<int> xy((size_t)2 * cap);
+    int n = mrg_b200_find_chessboard_corners((const uint8_t*)imagebuffer, Nrows, Ncols, stride, image_pyramid_level, xy.data(), cap);
+    if (n > cap)
+    {
+        cap = n; xy.resize((size_t)2 * cap);
+        n = mrg_b200_find_chessboard_corners((const uint8_t*)imagebuffer, Nrows, Ncols, stride, image_pyramid_level, xy.data(), cap);
+    }
+    if (n <= 0) return false;
+    return (*add_points)(xy.data(), n, 1.0 / kFindGridScale, cookie);
+}
+
+API void mrgingham_ChESS_response_5(int16_t* response, const uint8_t* image, int w, int h, int stride)
+{
+    if (w <= 2*kMargin || h <= 2*kMargin) return; // nothing is written for such sizes (ChESS.c:62-63)
+    std::lock_guard<std::mutex> g(g_default_mtx);
+    mrg_b200_detector* det = default_detector();
+    if (!det) { MSG("No CUDA device: response NOT computed."); abort(); }
+    if (mrg_b200_chess_response_batch(det, image, 0, 1, h, w, (size_t)stride, (size_t)stride * h, response, 0, nullptr))
+    { MSG("ChESS response failed on the GPU."); abort(); }
+}
+
+API int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride, int level,
+                                           double* xy_inout, signed char* levels, int Npoints)
+{
+    if (level < 0 || level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); return 0; }
+    if (level == 0 && Nrows > 1 && stride != Ncols) { MSG("I can only handle continuous arrays (stride == width) currently."); return 0; }
+    if (Npoints <= 0) return 0;
+    std::lock_guard<std::mutex> g(g_default_mtx);
+    mrg_b200_detector* det = default_detector();
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g2(det->mtx);
+    CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t stream = det->own_stream;
+    FrameSet fs;
+    if (stage_frames(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, stream, &fs)) return -1;
+    if (det->pts.ensure(sizeof(double) * 2 * Npoints)) return -1;
+    if (det->lvls.ensure(Npoints)) return -1;
+    if (ensure_chunk_scratch(det, 1)) return -1;
+    int cap = det->cfg.candidate_capacity, reccap = std::max(Npoints, 1);
+    cand_t* cand = (cand_t*)det->cand.p; uint32_t* table = (uint32_t*)det->table.p; uint32_t* dfs = (uint32_t*)det->dfs.p;
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        if (det->big_records.ensure(cluster_record_bytes() * reccap)) return -1;
+        CUDA_TRY(cudaMemcpyAsync(det->pts.p, xy_inout, sizeof(double) * 2 * Npoints, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(det->lvls.p, levels, Npoints, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemsetAsync(det->counts.p, 0, sizeof(uint32_t), stream));
+        if (chess_sparse(det, fs, cand, (uint32_t*)det->counts.p, cap, stream)) return -1;
+        ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = det->cfg.max_points; p.record_capacity = reccap; p.records = det->big_records.p;
+        CUDA_TRY(launch_cluster_refine(fs, p, cand, (uint32_t*)det->counts.p, table, dfs, (double*)det->pts.p, (signed char*)det->lvls.p,
+                                       Npoints, (int32_t*)det->outcounts.p, stream));
+        int32_t nref = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nref, det->outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (nref >= 0)
+        {
+            CUDA_TRY(cudaMemcpy(xy_inout, det->pts.p, sizeof(double) * 2 * Npoints, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(levels, det->lvls.p, Npoints, cudaMemcpyDeviceToHost));
+            return nref;
+        }
+        // candidate list overflowed: once more with worst-case capacity
+        cap = next_pow2((long long)fs.w * fs.h);
+        if (det->big_cand.ensure(sizeof(cand_t) * cap)) return -1;
+        if (det->big_table.ensure(sizeof(uint32_t) * 2 * cap)) return -1;
+        if (det->big_dfs.ensure(sizeof(uint32_t) * cap)) return -1;
+        cand = (cand_t*)det->big_cand.p; table = (uint32_t*)det->big_table.p; dfs = (uint32_t*)det->big_dfs.p;
+    }
+    MSG("Frame still overflows at worst-case capacity; this is a bug.");
+    return -1;
+}

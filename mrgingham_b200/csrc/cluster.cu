@@ -1,0 +1,425 @@
+// K2 / K2r: exact emulation of the reference's connected-component stage on the SPARSE candidate
+// set {(x,y,r) : r > 15} that K1 emits, one CTA per frame.
+//
+// Why the sparse set is enough (note N2): the reference's traversal
+// (find_chessboard_corners.cc:228-267) only ever expands through pixels whose response is > 15;
+// pixels with 0 < r <= 15 can be pushed, but when popped they are merely zeroed, which nothing
+// observes. So every accepted pixel, every rejected-by-ratio pixel and every seed is a candidate.
+//
+// What is emulated literally:
+//   * raster-order seeding over [8,w-8) x [8,h-8)                         (:332-335)
+//   * LIFO traversal, neighbours pushed +x,-x,+y,-y  => visited -y,+y,-x,+x (:252-255)
+//   * membership test at POP time against the RUNNING max: r > 15 && r > (max >> 4) (:159-171)
+//   * rejected pixels are zeroed and not expanded                         (:243-247)
+//   * a neighbour outside [7,w-7) x [7,h-7) poisons the component          (:216-221)
+//   * accept iff !poisoned && N >= 2 && max > 120 && 21x21 variance > 400  (:193-209, :50-88)
+//   * centroid = sum(r*x)/sum(r) in double, rescale, x1000 and truncate   (:262-263,:278-279,:350-351)
+// The explicit stack of the reference (which may hold duplicates) is replaced by a stackless
+// depth-first walk with a parent link and a next-direction counter per candidate: a LIFO stack
+// whose stale duplicates pop as no-ops visits pixels in exactly the order of a recursive DFS
+// that tries -y,+y,-x,+x and skips pixels that are dead by the time their turn comes.
+#include "kernels.cuh"
+
+namespace mrgb200
+{
+
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kRoot  = 0x1FFFFFFFu;
+constexpr int      kClusterThreads = 256;
+
+struct Component
+{
+    unsigned long long swx, swy, sw;
+    int  n, peak, peak_x, peak_y;
+    bool poisoned;
+};
+
+// Accepted-so-far component, parked in global scratch between the sequential walk and the
+// parallel variance gate
+struct ComponentRecord
+{
+    unsigned long long swx, swy, sw;
+    uint32_t peak_xy;   // y << 16 | x
+    int32_t  tag;       // find: unused; refine: point index. Set to -1 when the variance gate fails
+};
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int bits) { return (key * 2654435761u) >> (32 - bits); }
+
+__device__ __forceinline__ int table_lookup(const cand_t* cand, const uint32_t* table, int bits, uint32_t key)
+{
+    const uint32_t mask = (1u << bits) - 1;
+    uint32_t slot = hash_slot(key, bits);
+    for (;;)
+    {
+        const uint32_t i = table[slot];
+        if (i == kEmpty) return -1;
+        if (cand_key(cand[i]) == key) return (int)i;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// Grows one component from `nroots` start pixels (candidate indices, in the order they are to be
+// VISITED, i.e. reverse push order). Single thread.
+__device__ void grow_component(Component& c, cand_t* cand, const uint32_t* table, int bits, uint32_t* dfs,
+                               const int* roots, int nroots, int w, int h)
+{
+    c.swx = c.swy = c.sw = 0; c.n = 0; c.peak = 0; c.peak_x = c.peak_y = 0; c.poisoned = false;
+    for (int ir = 0; ir < nroots; ir++)
+    {
+        uint32_t cur = (uint32_t)roots[ir], parent = kRoot;
+        for (;;)
+        {
+            // ---- "pop" cur
+            const cand_t cc = cand[cur];
+            const int r = cand_r(cc);
+            const bool member = r != 0 && r > (c.peak >> 4);   // alive => r > 15 already
+            if (r != 0) cand[cur] = cc & ~0xFFFFull;           // member or not, it is zeroed
+            if (member)
+            {
+                const int x = cand_x(cc), y = cand_y(cc);
+                if (r > c.peak) { c.peak = r; c.peak_x = x; c.peak_y = y; }
+                c.swx += (unsigned long long)(r * x);
+                c.swy += (unsigned long long)(r * y);
+                c.sw  += (unsigned long long)r;
+                c.n++;
+                if (x + 1 >= w - kMargin || x - 1 < kMargin || y + 1 >= h - kMargin || y - 1 < kMargin)
+                    c.poisoned = true;
+                dfs[cur] = parent << 3;
+            }
+            else
+                cur = parent;
+
+            // ---- advance to the next pixel to pop, climbing back up as directions run out
+            bool found = false;
+            while (cur != kRoot)
+            {
+                const uint32_t st = dfs[cur];
+                const int d = (int)(st & 7);
+                if (d == 4) { cur = st >> 3; continue; }
+                dfs[cur] = st + 1;
+                const cand_t pc = cand[cur];
+                int nx = cand_x(pc), ny = cand_y(pc);
+                if      (d == 0) ny -= 1;
+                else if (d == 1) ny += 1;
+                else if (d == 2) nx -= 1;
+                else             nx += 1;
+                if (nx < kMargin || nx >= w - kMargin || ny < kMargin || ny >= h - kMargin) continue;
+                const int q = table_lookup(cand, table, bits, ((uint32_t)ny << 16) | (uint32_t)nx);
+                if (q < 0 || cand_r(cand[q]) == 0) continue;   // never pushed, or a stale stack entry
+                parent = cur; cur = (uint32_t)q; found = true;
+                break;
+            }
+            if (!found) break;
+        }
+    }
+}
+
+// 21x21 variance gate around (x,y) of the level image, one warp (find_chessboard_corners.cc:50-88)
+__device__ bool variance_gate_warp(const uint8_t* img, int pitch, int w, int h, int x, int y, int lane)
+{
+    if (x - kVarWindowR < 0 || x + kVarWindowR >= w || y - kVarWindowR < 0 || y + kVarWindowR >= h)
+        return false;
+    constexpr int D = 2*kVarWindowR + 1, NPIX = D*D;
+    int vals[(NPIX + 31) / 32];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < (NPIX + 31) / 32; k++)
+    {
+        const int i = lane + 32*k;
+        int v = 0;
+        if (i < NPIX) v = img[(size_t)(y - kVarWindowR + i / D) * pitch + (x - kVarWindowR + i % D)];
+        vals[k] = v; sum += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int mean = sum / NPIX;
+    int ssd = 0;
+#pragma unroll
+    for (int k = 0; k < (NPIX + 31) / 32; k++)
+        if (lane + 32*k < NPIX) { const int e = vals[k] - mean; ssd += e*e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ssd += __shfl_xor_sync(0xffffffffu, ssd, o);
+    return ssd / NPIX > kVarMin;
+}
+
+__device__ __forceinline__ double rescale_coord(double p, double scale)
+{
+    // (p + 0.5)*scale - 0.5 with every operation rounded separately (no FMA contraction), as the
+    // reference's x86-64 build does (find_chessboard_corners.cc:278-279)
+    return __dadd_rn(__dmul_rn(__dadd_rn(p, 0.5), scale), -0.5);
+}
+
+// Everything up to "candidates sorted + hash table built", shared by find and refine.
+// Returns false (after writing the overflow marker) if the frame's list overflowed.
+struct FrameWork
+{
+    cand_t*   cand;
+    uint32_t* table;
+    uint32_t* dfs;
+    int       n, bits;
+};
+
+__device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, const uint32_t* counts,
+                              uint32_t* scratch_table, uint32_t* scratch_dfs, uint8_t* smem)
+{
+    const int tid = threadIdx.x;
+    const uint32_t total = counts[f];
+    if (total > (uint32_t)cap) return false;
+    const int n = (int)total;
+    int P = 1, lg = 0;
+    while (P < n) { P <<= 1; lg++; }
+    cand_t* gcand = cand_all + (size_t)f * cap;
+    const bool in_smem = P <= kClusterSmemCands;
+    cand_t*   cand  = in_smem ? (cand_t*)smem : gcand;
+    uint32_t* table = in_smem ? (uint32_t*)(smem + sizeof(cand_t) * kClusterSmemCands) : scratch_table + (size_t)f * 2 * cap;
+    uint32_t* dfs   = in_smem ? (uint32_t*)(smem + (sizeof(cand_t) + 2*sizeof(uint32_t)) * kClusterSmemCands) : scratch_dfs + (size_t)f * cap;
+
+    for (int i = tid; i < P; i += kClusterThreads)
+        cand[i] = i < n ? gcand[i] : ~0ull;
+    __syncthreads();
+
+    // bitonic sort: ascending word order == raster order
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            for (int i = tid; i < P; i += kClusterThreads)
+            {
+                const int l = i ^ j;
+                if (l > i)
+                {
+                    const cand_t a = cand[i], b = cand[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { cand[i] = b; cand[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+
+    const int bits = lg + 1;
+    for (int i = tid; i < (1 << bits); i += kClusterThreads) table[i] = kEmpty;
+    __syncthreads();
+    const uint32_t mask = (1u << bits) - 1;
+    for (int i = tid; i < n; i += kClusterThreads)
+    {
+        uint32_t slot = hash_slot(cand_key(cand[i]), bits);
+        while (atomicCAS(&table[slot], kEmpty, (uint32_t)i) != kEmpty) slot = (slot + 1) & mask;
+    }
+    __syncthreads();
+    fw.cand = cand; fw.table = table; fw.dfs = dfs; fw.n = n; fw.bits = bits;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: find branch
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kClusterThreads)
+cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32_t* counts,
+                    uint32_t* scratch_table, uint32_t* scratch_dfs,
+                    int32_t* xy_int, double* xy_dbl, int32_t* out_counts)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_nrec;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    FrameWork fw;
+    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem))
+    {
+        if (tid == 0) out_counts[f] = -1;
+        return;
+    }
+    const int w = fs.w, h = fs.h;
+    const int record_cap = p.record_capacity;
+    ComponentRecord* rec = (ComponentRecord*)p.records + (size_t)f * record_cap;
+
+    if (tid == 0)
+    {
+        int nrec = 0;
+        for (int s = 0; s < fw.n; s++)
+        {
+            const cand_t sc = fw.cand[s];
+            if (cand_r(sc) == 0) continue;
+            const int x = cand_x(sc), y = cand_y(sc);
+            if (x < kMargin + 1 || x >= w - kMargin - 1 || y < kMargin + 1 || y >= h - kMargin - 1) continue;
+            Component c;
+            grow_component(c, fw.cand, fw.table, fw.bits, fw.dfs, &s, 1, w, h);
+            if (c.poisoned || c.n < kComponentMinN || c.peak <= kPeakMin) continue;
+            if (nrec < record_cap)
+            {
+                ComponentRecord r;
+                r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
+                r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x; r.tag = 0;
+                rec[nrec] = r;
+            }
+            nrec++;
+        }
+        s_nrec = nrec;
+    }
+    __syncthreads();
+    const int nrec = s_nrec;
+    if (nrec > record_cap)
+    {
+        if (tid == 0) out_counts[f] = -1;
+        return;
+    }
+
+    // variance gate: one warp per record
+    const uint8_t* img = fs.base + (size_t)f * fs.frame_stride;
+    for (int k = tid >> 5; k < nrec; k += kClusterThreads / 32)
+    {
+        const uint32_t pk = rec[k].peak_xy;
+        const bool ok = variance_gate_warp(img, fs.pitch, w, h, (int)(pk & 0xFFFF), (int)(pk >> 16), tid & 31);
+        if ((tid & 31) == 0 && !ok) rec[k].tag = -1;
+    }
+    __syncthreads();
+
+    if (tid == 0)
+    {
+        const double scale = (double)(1 << p.level);
+        int nout = 0;
+        for (int k = 0; k < nrec; k++)
+        {
+            if (rec[k].tag < 0) continue;
+            if (nout < p.max_points)
+            {
+                const double sw = __ull2double_rn(rec[k].sw);
+                const double fx = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swx), sw), scale);
+                const double fy = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swy), sw), scale);
+                const size_t o = ((size_t)f * p.max_points + nout) * 2;
+                xy_int[o]     = __double2int_rz(__dadd_rn(0.5, __dmul_rn(fx, kFindGridScale)));
+                xy_int[o + 1] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(fy, kFindGridScale)));
+                if (xy_dbl) { xy_dbl[o] = fx; xy_dbl[o + 1] = fy; }
+            }
+            nout++;
+        }
+        out_counts[f] = nout;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2r: refine branch (find_chessboard_corners.cc:356-397). Points are visited in index order on
+// one shared, mutable candidate set.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kClusterThreads)
+cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32_t* counts,
+                      uint32_t* scratch_table, uint32_t* scratch_dfs,
+                      double* points_xy, signed char* levels, int npoints, int32_t* out_refined)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_nrec, s_nrefined;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_nrefined = 0;
+    FrameWork fw;
+    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem))
+    {
+        if (tid == 0) out_refined[f] = -1;
+        return;
+    }
+    const int w = fs.w, h = fs.h;
+    const int record_cap = p.record_capacity;
+    ComponentRecord* rec = (ComponentRecord*)p.records + (size_t)f * record_cap;
+    double*      xy  = points_xy + (size_t)f * npoints * 2;
+    signed char* lvl = levels    + (size_t)f * npoints;
+    const double scale = (double)(1 << p.level), inv_scale = 1.0 / scale;
+
+    if (tid == 0)
+    {
+        int nrec = 0;
+        for (int i = 0; i < npoints; i++)
+        {
+            if (lvl[i] != p.level + 1) continue;
+            const int x = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i],     inv_scale), 0.5));
+            const int y = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i + 1], inv_scale), 0.5));
+            // 3x3 seeds, pushed dx-outer / dy-inner, hence visited in the reverse order
+            int roots[9], nroots = 0;
+            for (int dx = 1; dx >= -1; dx--)
+                for (int dy = 1; dy >= -1; dy--)
+                {
+                    const int u = x + dx, v = y + dy;
+                    if (u < kMargin || u >= w - kMargin || v < kMargin || v >= h - kMargin) continue; // response is 0 there
+                    const int q = table_lookup(fw.cand, fw.table, fw.bits, ((uint32_t)v << 16) | (uint32_t)u);
+                    if (q >= 0 && cand_r(fw.cand[q]) != 0) roots[nroots++] = q;
+                }
+            Component c;
+            grow_component(c, fw.cand, fw.table, fw.bits, fw.dfs, roots, nroots, w, h);
+            if (c.poisoned || c.n < kComponentMinN || c.peak <= kPeakMin) continue;
+            if (nrec < record_cap)
+            {
+                ComponentRecord r;
+                r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
+                r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x; r.tag = i;
+                rec[nrec] = r;
+            }
+            nrec++;
+        }
+        s_nrec = nrec;
+    }
+    __syncthreads();
+    const int nrec = s_nrec;
+    if (nrec > record_cap)
+    {
+        if (tid == 0) out_refined[f] = -1;
+        return;
+    }
+    const uint8_t* img = fs.base + (size_t)f * fs.frame_stride;
+    for (int k = tid >> 5; k < nrec; k += kClusterThreads / 32)
+    {
+        const uint32_t pk = rec[k].peak_xy;
+        const bool ok = variance_gate_warp(img, fs.pitch, w, h, (int)(pk & 0xFFFF), (int)(pk >> 16), tid & 31);
+        if ((tid & 31) == 0 && ok)
+        {
+            const int i = rec[k].tag;
+            const double sw = __ull2double_rn(rec[k].sw);
+            xy[2*i]     = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swx), sw), scale);
+            xy[2*i + 1] = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swy), sw), scale);
+            lvl[i] = (signed char)p.level;
+            atomicAdd(&s_nrefined, 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) out_refined[f] = s_nrefined;
+}
+
+static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 3*sizeof(uint32_t)) * (size_t)kClusterSmemCands; }
+
+size_t cluster_record_bytes() { return sizeof(ComponentRecord); }
+
+cudaError_t launch_cluster_find(const FrameSet& fs, const ClusterParams& p,
+                                cand_t* cand, const uint32_t* counts,
+                                uint32_t* scratch_table, uint32_t* scratch_dfs,
+                                int32_t* xy_int, double* xy_dbl, int32_t* out_counts,
+                                cudaStream_t stream)
+{
+    if (fs.nframes <= 0) return cudaSuccess;
+    static bool attr_done = false;
+    const size_t smem = cluster_smem_bytes();
+    if (!attr_done)
+    {
+        cudaError_t e = cudaFuncSetAttribute(cluster_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    cluster_find_kernel<<<fs.nframes, kClusterThreads, smem, stream>>>(fs, p, cand, counts, scratch_table, scratch_dfs,
+                                                                       xy_int, xy_dbl, out_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cluster_refine(const FrameSet& fs, const ClusterParams& p,
+                                  cand_t* cand, const uint32_t* counts,
+                                  uint32_t* scratch_table, uint32_t* scratch_dfs,
+                                  double* points_xy, signed char* levels, int npoints,
+                                  int32_t* out_refined, cudaStream_t stream)
+{
+    if (fs.nframes <= 0) return cudaSuccess;
+    static bool attr_done = false;
+    const size_t smem = cluster_smem_bytes();
+    if (!attr_done)
+    {
+        cudaError_t e = cudaFuncSetAttribute(cluster_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    cluster_refine_kernel<<<fs.nframes, kClusterThreads, smem, stream>>>(fs, p, cand, counts, scratch_table, scratch_dfs,
+                                                                         points_xy, levels, npoints, out_refined);
+    return cudaGetLastError();
+}
+
+}

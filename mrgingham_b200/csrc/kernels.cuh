@@ -1,0 +1,93 @@
+// Internal declarations shared by the kernel translation units and the host API (api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mrgb200
+{
+// Detector constants of the reference (find_chessboard_corners.cc:18,22,27,29,38,39,564).
+// Bit-exactness depends on them, so they are compile-time constants here as they are there.
+constexpr int kPeakMin        = 120;  // RESPONSE_MIN_PEAK_THRESHOLD
+constexpr int kRespMin        = 15;   // RESPONSE_MIN_THRESHOLD
+constexpr int kComponentMinN  = 2;    // CONNECTED_COMPONENT_MIN_SIZE
+constexpr int kVarWindowR     = 10;   // CONSTANCY_WINDOW_R
+constexpr int kVarMin         = 400;  // STDEV_THRESHOLD^2
+constexpr int kMargin         = 7;    // ChESS leaves a 7-pixel border unwritten
+constexpr double kFindGridScale = 1000.0; // FIND_GRID_SCALE, mrgingham-internal.h:3
+
+// A candidate = one pixel whose clamped ChESS response exceeds kRespMin, inside
+// [7,w-7) x [7,h-7):   bits 47..32 = y, 31..16 = x, 15..0 = response.
+// Numeric order of the word == raster order of the pixel.
+typedef unsigned long long cand_t;
+__host__ __device__ inline cand_t   cand_pack(int x, int y, int r) { return ((cand_t)y << 32) | ((cand_t)x << 16) | (cand_t)(unsigned)r; }
+__host__ __device__ inline int      cand_x(cand_t c)   { return (int)((c >> 16) & 0xFFFF); }
+__host__ __device__ inline int      cand_y(cand_t c)   { return (int)(c >> 32); }
+__host__ __device__ inline int      cand_r(cand_t c)   { return (int)(c & 0xFFFF); }
+__host__ __device__ inline uint32_t cand_key(cand_t c) { return (uint32_t)(c >> 16); }
+
+// One level image of one batch, as the kernels see it
+struct FrameSet
+{
+    const uint8_t* base;      // first frame
+    size_t frame_stride;      // bytes between frames
+    int    pitch;             // bytes between rows
+    int    w, h;              // pixels
+    int    nframes;
+};
+
+// Output of the clustering kernel per accepted component, before ordering/finalisation is
+// done in the same kernel. Kept for debugging entry points.
+struct ClusterParams
+{
+    int      level;           // pyramid level the FrameSet is at (coordinates scale by 2^level)
+    int      cand_capacity;   // per-frame capacity of the candidate lists (power of two)
+    int      max_points;      // per-frame capacity of the outputs
+    int      record_capacity; // per-frame capacity of `records`
+    void*    records;         // [nframes][record_capacity] scratch, cluster_record_bytes() each
+};
+size_t cluster_record_bytes();
+
+// ---- launchers (each enqueues on `stream`, returns cudaGetLastError()) ----
+
+// K0: level-L image from the full-resolution frames (model N1 of cv::resize INTER_LINEAR)
+cudaError_t launch_pyramid(const FrameSet& src, int level, uint8_t* dst, int dst_pitch,
+                           size_t dst_frame_stride, int ow, int oh, cudaStream_t stream);
+
+// K1 (simple variant): ChESS response, one thread per pixel, emits candidates
+cudaError_t launch_chess_sparse_simple(const FrameSet& fs, cand_t* cand, uint32_t* counts,
+                                       int cand_capacity, cudaStream_t stream);
+// K1 (tiled variant): TMA/shared-memory staged, packed-lane arithmetic
+cudaError_t launch_chess_sparse_tiled(const FrameSet& fs, cand_t* cand, uint32_t* counts,
+                                      int cand_capacity, cudaStream_t stream);
+// dense int16 response (interior only), for the ChESS_response_5 API
+cudaError_t launch_chess_dense(const FrameSet& fs, int16_t* response, size_t response_frame_stride_elems,
+                               cudaStream_t stream);
+
+// K2: per-frame clustering of the candidate lists, exact emulation of
+// process_connected_components()'s find branch. One CTA per frame.
+//   cand/counts      from K1 (lists are sorted in place)
+//   scratch_table    [nframes][2*cand_capacity] uint32, only touched for frames whose list does
+//                    not fit shared memory
+//   scratch_dfs      [nframes][cand_capacity]   uint32, idem
+//   xy_int           [nframes][max_points][2] int32  (scaled by 1000)
+//   xy_dbl           [nframes][max_points][2] double (un-quantised), may be NULL
+//   out_counts       [nframes] int32: corners found; -1 = candidate list overflowed
+cudaError_t launch_cluster_find(const FrameSet& fs, const ClusterParams& p,
+                                cand_t* cand, const uint32_t* counts,
+                                uint32_t* scratch_table, uint32_t* scratch_dfs,
+                                int32_t* xy_int, double* xy_dbl, int32_t* out_counts,
+                                cudaStream_t stream);
+
+// K2r: refinement branch. points/levels are [nframes][npoints] (in/out), out_refined [nframes]
+// (-1 = candidate list overflowed)
+cudaError_t launch_cluster_refine(const FrameSet& fs, const ClusterParams& p,
+                                  cand_t* cand, const uint32_t* counts,
+                                  uint32_t* scratch_table, uint32_t* scratch_dfs,
+                                  double* points_xy, signed char* levels, int npoints,
+                                  int32_t* out_refined, cudaStream_t stream);
+
+// shared-memory candidate capacity of the clustering kernel (lists up to this size never touch
+// the global scratch)
+constexpr int kClusterSmemCands = 4096;
+}

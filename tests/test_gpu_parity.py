@@ -1,0 +1,257 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle and the committed golden vectors (generated from the reference itself). Bit-exact bar:
+integer corner lists identical in value AND order; dense responses identical; refined doubles
+bit-identical (north_star asks for 1e-3 px; we hold the stronger bar and state it here)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+
+from mrgingham_b200 import synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mrgingham_b200
+    assert mrgingham_b200.lib().mrg_b200_device_count() > 0, "no CUDA device: these tests need the B200"
+    return mrgingham_b200
+
+
+@pytest.fixture(scope="module")
+def api(m):
+    from mrgingham_b200 import api
+    return api
+
+
+def _names(golden):
+    return sorted({k.split("/")[0] for k in golden.files})
+
+
+def _extra_images():
+    yield "board_720p", synth.board_frame(1280, 720, 10, seed=100)
+    yield "board_n14_1080p", synth.board_frame(1920, 1080, 14, seed=101)
+    yield "board_odd", synth.board_frame(611, 457, 10, seed=102)
+    yield "noise", synth.noise_frame(333, 222, seed=103)
+    yield "blurred_noise", synth.blurred_noise_frame(320, 256, seed=104, passes=1)
+    yield "checker6", synth.checker_frame(300, 260, period=6, seed=105)
+    yield "checker11", synth.checker_frame(480, 270, period=11, seed=106, noise_sigma=3.0)
+    yield "blobs", synth.blob_frame(400, 300, seed=107)
+    rng = np.random.default_rng(108)
+    for i in range(10):
+        w, h = int(rng.integers(1, 140)), int(rng.integers(1, 140))
+        yield f"rand_{w}x{h}", synth.blurred_noise_frame(w, h, seed=200 + i, passes=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# A1: dense response (mrgingham_ChESS_response_5)
+# ---------------------------------------------------------------------------------------------
+def test_dense_response_matches_golden(m, golden):
+    for name in _names(golden):
+        img = golden[f"{name}/image"]
+        got = m.ChESS_response_5(img)
+        assert np.array_equal(got, golden[f"{name}/response"]), name
+
+
+def test_dense_response_leaves_border_untouched(m, api, oracle):
+    img = synth.board_frame(200, 150, 10, seed=1)
+    out = np.full(img.shape, -999, dtype=np.int16)
+    api.lib().mrgingham_ChESS_response_5(out.ctypes.data_as(api._i16p), img.ctypes.data_as(api._u8p), 200, 150, 200)
+    assert np.array_equal(out, oracle.chess_response_5(img, fill=-999))
+
+
+def test_dense_response_strided_and_batched(m, oracle):
+    big = synth.board_frame(700, 500, 10, seed=110)
+    view = big[10:490, 20:660]
+    assert np.array_equal(m.ChESS_response_5(view), oracle.chess_response_5(view, fill=0))
+    stack = np.stack([synth.noise_frame(96, 80, seed=s) for s in range(6)]).reshape(2, 3, 80, 96)
+    got = m.ChESS_response_5(stack)
+    for i in range(2):
+        for j in range(3):
+            assert np.array_equal(got[i, j], oracle.chess_response_5(stack[i, j], fill=0))
+
+
+# ---------------------------------------------------------------------------------------------
+# A2: pyramid level
+# ---------------------------------------------------------------------------------------------
+def test_pyramid_matches_oracle(m, oracle):
+    rng = np.random.default_rng(5)
+    for (w, h) in ((43, 35), (47, 39), (64, 48), (99, 77), (403, 351), (640, 480), (1920, 1080)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        for level in (1, 2, 3, 4):
+            got, want = m.pyramid_level(img, level), oracle.pyramid(img, level)
+            assert got.shape == want.shape and np.array_equal(got, want), (w, h, level)
+
+
+# ---------------------------------------------------------------------------------------------
+# A3-A7: find_chessboard_corners_from_image_array
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("level", cases.LEVELS)
+def test_corners_match_golden(api, golden, level):
+    for name in _names(golden):
+        img = golden[f"{name}/image"]
+        got = api.find_chessboard_corners_int(img, level)
+        want = golden[f"{name}/corners_L{level}"]
+        assert got.shape == want.shape and np.array_equal(got, want), (name, level)
+
+
+def test_corners_match_oracle_wider_set(api, oracle):
+    for name, img in _extra_images():
+        for level in (0, 1, 2, 3):
+            got, want = api.find_chessboard_corners_int(img, level), oracle.find_corners(img, level)
+            assert got.shape == want.shape and np.array_equal(got, want), (name, level)
+
+
+def test_find_points_python_surface(m, oracle):
+    img = synth.board_frame(640, 480, 10, seed=0)
+    pts = m.find_points(img)
+    want = oracle.find_corners(img, 0)
+    assert pts.shape == (100, 2) and pts.dtype == np.float64
+    assert np.array_equal(pts, (1.0 / 1000.0) * want.astype(np.float64))
+    assert m.find_points(np.full((64, 64), 128, np.uint8)).shape == (0, 2)
+    # reference error paths: bad level, non-continuous at level 0 -> nothing
+    assert m.find_points(img, image_pyramid_level=-1).shape == (0, 2)
+    assert m.find_points(img, image_pyramid_level=11).shape == (0, 2)
+    big = synth.board_frame(700, 500, 10, seed=110)
+    assert m.find_points(big[10:490, 20:660], image_pyramid_level=0).shape == (0, 2)
+    v = big[10:490, 20:660]
+    assert np.array_equal(m.find_points(v, image_pyramid_level=1), (1.0 / 1000.0) * oracle.find_corners(v, 1).astype(np.float64))
+    with pytest.raises(RuntimeError):
+        m.find_points(img, image_pyramid_level=1, blobs=True)
+    with pytest.raises(RuntimeError):
+        m.find_points(img.astype(np.float32))
+
+
+def test_config_sizes_1080p_4k(api, oracle):
+    for (w, h, n, seed) in ((1920, 1080, 10, 31), (3840, 2160, 10, 32), (3840, 2160, 14, 33)):
+        img = synth.board_frame(w, h, n, seed=seed)
+        for level in (0, 1, 2, 3):
+            got, want = api.find_chessboard_corners_int(img, level), oracle.find_corners(img, level)
+            assert np.array_equal(got, want), (w, h, n, level)
+        assert len(oracle.find_corners(img, 0)) == n * n
+
+
+# ---------------------------------------------------------------------------------------------
+# A8: refinement
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("start", (1, 2, 3))
+def test_refine_chain_matches_golden(api, golden, start):
+    for name in _names(golden):
+        img = golden[f"{name}/image"]
+        xy, levels, counts = cases.refine_chain(api.find_chessboard_corners_int, api.refine_chessboard_corners, img, start)
+        assert np.array_equal(counts, golden[f"{name}/refine_from_L{start}/counts"]), name
+        assert np.array_equal(levels, golden[f"{name}/refine_from_L{start}/levels"]), name
+        assert np.array_equal(xy.view(np.uint64), golden[f"{name}/refine_from_L{start}/xy"].view(np.uint64)), name
+
+
+def test_refine_shuffled_foreign_points(api, oracle):
+    img = synth.board_frame(800, 600, 10, seed=112)
+    rng = np.random.default_rng(113)
+    pts = oracle.find_corners(img, 2).astype(np.float64) / 1000.0
+    rng.shuffle(pts)
+    extra = np.stack([rng.uniform(-20, 820, 40), rng.uniform(-20, 620, 40)], axis=1)
+    xy = np.concatenate([pts, extra, pts[:10] + 0.7])
+    levels = np.full(len(xy), 2, dtype=np.int8)
+    levels[::7] = 1
+    for level in (1, 0):
+        na, xa, la = api.refine_chessboard_corners(img, level, xy, levels)
+        nb, xb, lb = oracle.refine_corners(img, level, xy, levels)
+        assert na == nb and np.array_equal(la, lb)
+        assert np.array_equal(xa.view(np.uint64), xb.view(np.uint64))
+        xy, levels = xb, lb
+
+
+def test_refine_4k_n14(api, oracle):
+    img = synth.board_frame(3840, 2160, 14, seed=33)
+    xa, la, ca = cases.refine_chain(api.find_chessboard_corners_int, api.refine_chessboard_corners, img, 3)
+    xb, lb, cb = cases.refine_chain(oracle.find_corners, oracle.refine_corners, img, 3)
+    assert np.array_equal(ca, cb) and np.array_equal(la, lb)
+    assert np.array_equal(xa.view(np.uint64), xb.view(np.uint64))
+
+
+# ---------------------------------------------------------------------------------------------
+# batch API, device-resident frames, overflow path, kernel variants
+# ---------------------------------------------------------------------------------------------
+def _check_batch(xy, counts, frames, oracle, level=0):
+    for i, img in enumerate(frames):
+        want = oracle.find_corners(np.ascontiguousarray(img), level)
+        assert counts[i] == len(want), (i, counts[i], len(want))
+        assert np.array_equal(xy[i, :counts[i]], want), i
+
+
+def test_batch_host_frames(api, oracle):
+    frames = np.stack([synth.board_frame(480, 360, 10, seed=s) for s in range(9)] +
+                      [synth.noise_frame(480, 360, seed=50), synth.checker_frame(480, 360, 8, seed=51)])
+    det = api.Detector(max_frames=4, max_points=4096)      # forces 3 chunks
+    for level in (0, 1):
+        xy, counts = det.find_corners(frames, level)
+        _check_batch(xy, counts, frames, oracle, level)
+    det.close()
+
+
+def test_batch_device_frames_torch(api, oracle):
+    import torch
+    frames = np.stack([synth.board_frame(640, 480, 10, seed=60 + s) for s in range(5)])
+    t = torch.from_numpy(frames).cuda()
+    det = api.Detector(max_frames=8)
+    xy, counts = det.find_corners(t, 0, stream=torch.cuda.current_stream().cuda_stream)
+    _check_batch(xy, counts, frames, oracle, 0)
+    # pitched device frames (row pitch 768 > 640)
+    tp = torch.zeros((5, 480, 768), dtype=torch.uint8, device="cuda")
+    tp[:, :, :640] = t
+    xy, counts = det.find_corners(tp[:, :, :640], 0)
+    _check_batch(xy, counts, frames, oracle, 0)
+    xy, counts = det.find_corners(tp[:, :, :640], 2)
+    _check_batch(xy, counts, frames, oracle, 2)
+    det.close()
+
+
+def test_candidate_overflow_reruns_on_gpu(api, oracle):
+    frames = np.stack([synth.noise_frame(400, 300, seed=70), synth.board_frame(400, 300, 10, seed=71),
+                       synth.checker_frame(400, 300, 6, seed=72)])
+    det = api.Detector(max_frames=3, candidate_capacity=256, max_points=4096)
+    xy, counts = det.find_corners(frames, 0)
+    cand = det.last_candidate_counts(3)
+    assert (cand > 256).all(), cand          # every frame overflowed the tiny capacity ...
+    _check_batch(xy, counts, frames, oracle, 0)   # ... and is still exact
+    det.close()
+
+
+def test_large_candidate_lists_use_global_scratch(api, oracle):
+    # > 4096 candidates per frame: the clustering kernel leaves shared memory
+    frames = np.stack([synth.noise_frame(640, 480, seed=80), synth.checker_frame(640, 480, 8, seed=81)])
+    det = api.Detector(max_frames=2, candidate_capacity=1 << 17, max_points=8192)
+    xy, counts = det.find_corners(frames, 0)
+    cand = det.last_candidate_counts(2)
+    assert (cand > 4096).all() and (cand < (1 << 17)).all(), cand
+    _check_batch(xy, counts, frames, oracle, 0)
+    det.close()
+
+
+def test_kernel_variants_agree(api, oracle):
+    frames = np.stack([synth.board_frame(800, 608, 10, seed=90), synth.blurred_noise_frame(800, 608, seed=91)])
+    a = api.Detector(max_frames=2, max_points=4096, kernel_variant=0)
+    b = api.Detector(max_frames=2, max_points=4096, kernel_variant=1)
+    xa, ca = a.find_corners(frames, 0)
+    xb, cb = b.find_corners(frames, 0)
+    assert np.array_equal(ca, cb) and np.array_equal(a.last_candidate_counts(2), b.last_candidate_counts(2))
+    for i in range(2):
+        assert np.array_equal(xa[i, :ca[i]], xb[i, :cb[i]])
+    _check_batch(xa, ca, frames, oracle, 0)
+    a.close(); b.close()
+
+
+def test_empty_batch_and_tiny_frames(api, oracle):
+    det = api.Detector(max_frames=4)
+    xy, counts = det.find_corners(np.zeros((0, 32, 32), np.uint8), 0)
+    assert len(counts) == 0
+    for (w, h) in ((1, 1), (14, 14), (15, 15), (16, 40), (40, 16)):
+        frames = np.stack([synth.noise_frame(w, h, seed=s) for s in range(3)])
+        xy, counts = det.find_corners(frames, 0)
+        _check_batch(xy, counts, frames, oracle, 0)
+    det.close()
