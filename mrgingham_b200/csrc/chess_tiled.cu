@@ -5,8 +5,8 @@
 //   and the r > 15 seed/member test of :159-171 -- only pixels with response > 15 are written out.
 //
 // Data movement. A CTA (4 warps) owns a 256-pixel-wide column strip of one frame and walks down
-// it. Rows arrive through a 4-stage shared-memory ring filled by TMA (cp.async.bulk.tensor.3d,
-// one 288-byte x 10-row box per stage: the strip plus a 16-byte halo each side), completion
+// it. Rows arrive through an 8-stage shared-memory ring filled by TMA (cp.async.bulk.tensor.3d,
+// one 288-byte x 11-row box per stage: the strip plus a 16-byte halo each side), completion
 // signalled on mbarriers; stages are handed back through a second set of mbarriers. Out-of-image
 // rows/columns are zero-filled by TMA. Frames whose base/pitch do not meet TMA's 16-byte rules
 // take the same kernel with a cooperative ld.global -> st.shared loader instead.
@@ -21,9 +21,9 @@
 //     mixed on the same registers, which spreads the work over both the ALU and the FMA pipe;
 //   * warps are specialised by pixel-pair alignment (x = 0 or 2 mod 4) so that every ring sample
 //     of a pair lies in ONE staged 32-bit word (two words for one of the seven column offsets);
-//   * each thread walks down its column keeping the unpacked ring samples of the last 10 rows in
+//   * each thread walks down its column keeping the unpacked ring samples of the last 11 rows in
 //     registers (rows y-5..y+5 are needed per output row, but only row y+5 is new), the row loop
-//     is unrolled x10 so the window is addressed statically;
+//     is unrolled x11 so the window is addressed statically;
 //   * exact early-outs: response = sum - diff - |mean - local_mean| <= sum - diff <= sum, so a
 //     warp first forms only `sum` (always), then `diff` if some lane has sum > 15, then the rest if
 //     some lane has sum - diff > 15. Whenever a response can exceed 15 it is computed exactly.
@@ -32,6 +32,7 @@
 #include <mutex>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -42,9 +43,12 @@ constexpr int kTileW      = 256;                 // output pixels per strip
 constexpr int kHalo       = 16;                  // bytes staged left of the strip (and right): the ring needs 8,
                                                  // but TMA wants the box to start on a 16-byte boundary
 constexpr int kRowBytes   = kTileW + 2*kHalo;    // 288
-constexpr int kStageRows  = 10;                  // == unroll factor of the row loop
-constexpr int kStages     = 4;
-constexpr int kStageBytes = 2944;                // 10*288 = 2880 rounded up to 128
+constexpr int kStageRows  = 11;                  // == unroll factor of the row loop == register-window length
+constexpr int kStages     = 8;
+constexpr int kLookahead  = 2;                   // stages requested ahead of the fastest warp. The ring is much
+                                                 // deeper than that so the warp that issues never has to wait
+                                                 // for a slower warp to hand a stage back.
+constexpr int kStageBytes = 3200;                // 11*288 = 3168 rounded up to 128
 constexpr int kTileThreads = 128;
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -71,7 +75,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
@@ -133,16 +137,39 @@ __device__ __forceinline__ RowSamples unpack_row(const uint8_t* row)
     return s;
 }
 
-// Rare path (entered warp-uniformly): exact response of both pixels of every pair of the warp,
-// append the ones > 15. `centre` points at the staged byte of pixel x in the centre row.
-__device__ __noinline__ void emit_candidates(uint32_t sum, uint32_t diff, uint32_t mean, const uint8_t* centre,
-                                             int x, int y, int w, cand_t* __restrict__ out, uint32_t* __restrict__ count, int cap)
+// Rare path (entered warp-uniformly, after the 11-row block that flagged it): some pixel of this
+// warp's 64-pixel row segment may have response > 15. Recompute both pixels of every lane exactly,
+// straight from the staged bytes (scalar, as ChESS.c:62-105 reads), and append the hits.
+// rows[k] points at the staged byte of pixel x in row y + dy_k, dy = {-5,-4,-2,0,+2,+4,+5}.
+__device__ __forceinline__ int chess_from_rows(const uint8_t* const* rows)
 {
-    const int cm1 = centre[-1], c0 = centre[0], c1 = centre[1], c2 = centre[2];
-    const int lm0 = (cm1 + c0 + c1) * 16 / 3;          // ChESS.c:86
-    const int lm1 = (c0 + c1 + c2) * 16 / 3;
-    const int r0 = (int)(sum & 0xFFFF) - (int)(diff & 0xFFFF) - abs((int)(mean & 0xFFFF) - lm0);
-    const int r1 = (int)(sum >> 16)    - (int)(diff >> 16)    - abs((int)(mean >> 16)    - lm1);
+    const uint8_t *m5 = rows[0], *m4 = rows[1], *m2 = rows[2], *c = rows[3], *p2 = rows[4], *p4 = rows[5], *p5 = rows[6];
+    const int s0 = m5[2],  s1 = m5[0],  s2  = m5[-2], s3  = m4[-4], s4  = m2[-5], s5  = c[-5], s6  = p2[-5], s7  = p4[-4];
+    const int s8 = p5[-2], s9 = p5[0],  s10 = p5[2],  s11 = p4[4],  s12 = p2[5],  s13 = c[5],  s14 = m2[5],  s15 = m4[4];
+    const int q0 = s0 + s8, q1 = s1 + s9, q2 = s2 + s10, q3 = s3 + s11, q4 = s4 + s12, q5 = s5 + s13, q6 = s6 + s14, q7 = s7 + s15;
+    const int sum  = abs(q0 - q4) + abs(q1 - q5) + abs(q2 - q6) + abs(q3 - q7);
+    const int diff = abs(s0 - s8) + abs(s1 - s9) + abs(s2 - s10) + abs(s3 - s11) + abs(s4 - s12) + abs(s5 - s13) + abs(s6 - s14) + abs(s7 - s15);
+    const int mean = (q0 + q1 + q2 + q3) + (q4 + q5 + q6 + q7);
+    const int local_mean = (c[-1] + c[0] + c[1]) * 16 / 3;
+    return sum - diff - abs(mean - local_mean);
+}
+
+__device__ __noinline__ void emit_row(const uint8_t* cur_stage, const uint8_t* prev_stage, int j, int col /* byte of pixel x in a staged row */,
+                                      int x, int y, int w, cand_t* __restrict__ out, uint32_t* __restrict__ count, int cap)
+{
+    // row y + dy is (5 - dy) rows behind the newest staged row (slot j of the current stage)
+    const int behind[7] = { 10, 9, 7, 5, 3, 1, 0 };
+    const uint8_t* rows[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+    {
+        const int r = j - behind[k];
+        rows[k] = (r >= 0 ? cur_stage + r * kRowBytes : prev_stage + (r + kStageRows) * kRowBytes) + col;
+    }
+    const int r0 = chess_from_rows(rows);
+#pragma unroll
+    for (int k = 0; k < 7; k++) rows[k] += 1;
+    const int r1 = chess_from_rows(rows);
     const bool hit0 = r0 > kRespMin && x     >= kMargin && x     < w - kMargin;
     const bool hit1 = r1 > kRespMin && x + 1 >= kMargin && x + 1 < w - kMargin;
     const uint32_t b0 = __ballot_sync(kFull, hit0), b1 = __ballot_sync(kFull, hit1);
@@ -168,11 +195,12 @@ struct TileParams
 {
     int nstrips, nsegs, seg_rows;   // work decomposition: item = (frame, segment, strip)
     int cap;
+    int lookahead;                  // stages kept in flight ahead of the consumers (<= kStages-2)
 };
 
 template<int CLS, bool USE_TMA>
 __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameSet& fs, const TileParams& tp,
-                                           uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar,
+                                           uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar, int* next_issue,
                                            cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
 {
     const int tid = threadIdx.x, lane = tid & 31, span = tid >> 6;
@@ -184,8 +212,10 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
     const int xs = strip * kTileW;                       // first output column of the strip
     const int ys = kMargin + seg * tp.seg_rows;          // first output row of the segment
     const int ye = min(ys + tp.seg_rows, h - kMargin);
-    const int rbase = ys - 5;                            // newest row of iteration 0, step 0
-    const int nit = 1 + (ye - ys + kStageRows - 1) / kStageRows;
+    // Iteration `it`, step j stages row rbase + it*11 + j (the "+5" row of output row y = that - 5).
+    // The first ten staged rows (ys-5 .. ys+4) only prime the register window.
+    const int rbase = ys - 5;
+    const int nit = (ye - ys + 10 + kStageRows - 1) / kStageRows;
 
     const int X = xs + span * 128 + 4 * lane;            // this thread's word-aligned column
     const int x = X + CLS;                               // its pixel pair is (x, x+1)
@@ -219,8 +249,10 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
     if (USE_TMA)
     {
         if (tid == 0)
-            for (int it = 0; it < kStages - 2 && it < nit; it++) issue(it);
+            for (int it = 0; it < tp.lookahead && it < nit; it++) issue(it);
     }
+    // Whichever warp reaches an iteration first requests the stage `lookahead` iterations ahead
+    // (claimed through *next_issue), so no warp ever waits on a slower warp's producer duty.
 
     uint32_t Um2[kStageRows], U0[kStageRows], Up2[kStageRows];   // offsets -2, 0, +2 (needed at dy = +5 and -5)
     uint32_t U4m[kStageRows], U4p[kStageRows];                   // offsets -4, +4   (dy = +4 and -4)
@@ -233,8 +265,11 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
         const int s = it % kStages;
         if (USE_TMA)
         {
-            if (tid == 0 && it + kStages - 2 < nit) issue(it + kStages - 2);
+            if (lane == 0 && it + tp.lookahead < nit &&
+                atomicCAS(next_issue, it + tp.lookahead, it + tp.lookahead + 1) == it + tp.lookahead)
+                issue(it + tp.lookahead);
             mbar_wait(&full_bar[s], (it / kStages) & 1);
+            __syncwarp();
         }
         else
         {
@@ -243,25 +278,26 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
             __syncthreads();
         }
         const uint8_t* stage = ring + s * kStageBytes + lane_off;
-        const bool compute = it > 0;       // iteration 0 only primes the register window
-        const int ybase = rbase + it * kStageRows - 5;
+        const int ybase = rbase + it * kStageRows - 5;   // output row of step 0 (its +5 row is staged row 0)
+        uint32_t pending = 0;                            // warp-uniform: steps whose row may hold candidates
 
 #pragma unroll
         for (int j = 0; j < kStageRows; j++)
         {
             const RowSamples n = unpack_row<CLS>(stage + j * kRowBytes);
-            const int y = ybase + j;       // output row whose +5 row just arrived
-            if (compute && y < ye)
+            // Rows outside [ys,ye) (window priming, segment tail) are computed like any other and
+            // dropped below: cheaper than a test on the always-executed path.
             {
                 // opposite ring samples (s_k, s_k+8), k = 0..7
-                const uint32_t a0 = Up2[j],              b0 = n.m2;                    // (+2,-5) (-2,+5)
-                const uint32_t a1 = U0[j],               b1 = n.c0;                    // ( 0,-5) ( 0,+5)
-                const uint32_t a2 = Um2[j],              b2 = n.p2;                    // (-2,-5) (+2,+5)
-                const uint32_t a3 = U4m[(j + 1) % 10],   b3 = U4p[(j + 9) % 10];       // (-4,-4) (+4,+4)
-                const uint32_t a4 = U5m[(j + 3) % 10],   b4 = U5p[(j + 7) % 10];       // (-5,-2) (+5,+2)
-                const uint32_t a5 = U5m[(j + 5) % 10],   b5 = U5p[(j + 5) % 10];       // (-5, 0) (+5, 0)
-                const uint32_t a6 = U5m[(j + 7) % 10],   b6 = U5p[(j + 3) % 10];       // (-5,+2) (+5,-2)
-                const uint32_t a7 = U4m[(j + 9) % 10],   b7 = U4p[(j + 1) % 10];       // (-4,+4) (+4,-4)
+                // the window slot of row R-k is (j + 11 - k) % 11; the new row R goes to slot j
+                const uint32_t a0 = Up2[(j + 1) % 11],   b0 = n.m2;                    // (+2,-5) (-2,+5)
+                const uint32_t a1 = U0[(j + 1) % 11],    b1 = n.c0;                    // ( 0,-5) ( 0,+5)
+                const uint32_t a2 = Um2[(j + 1) % 11],   b2 = n.p2;                    // (-2,-5) (+2,+5)
+                const uint32_t a3 = U4m[(j + 2) % 11],   b3 = U4p[(j + 10) % 11];      // (-4,-4) (+4,+4)
+                const uint32_t a4 = U5m[(j + 4) % 11],   b4 = U5p[(j + 8) % 11];       // (-5,-2) (+5,+2)
+                const uint32_t a5 = U5m[(j + 6) % 11],   b5 = U5p[(j + 6) % 11];       // (-5, 0) (+5, 0)
+                const uint32_t a6 = U5m[(j + 8) % 11],   b6 = U5p[(j + 4) % 11];       // (-5,+2) (+5,-2)
+                const uint32_t a7 = U4m[(j + 10) % 11],  b7 = U4p[(j + 2) % 11];       // (-4,+4) (+4,-4)
                 const uint32_t p0 = a0 + b0, p1 = a1 + b1, p2 = a2 + b2, p3 = a3 + b3;
                 const uint32_t p4 = a4 + b4, p5 = a5 + b5, p6 = a6 + b6, p7 = a7 + b7;
                 // sum_response = sum_i |p_i - p_i+4|   (half2 lanes, exact: |values| <= 2040)
@@ -275,18 +311,20 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
                                           (__vabsdiffu4(a4, b4) + __vabsdiffu4(a5, b5)) + (__vabsdiffu4(a6, b6) + __vabsdiffu4(a7, b7));
                     // lanes of (sumr - diff + 2048 + 0x77F0) reach 0x8000 iff sumr - diff >= 16
                     const uint32_t t = sumr - diff + 0x7FF07FF0u;
-                    if (__any_sync(kFull, (t & 0x80008000u) != 0))
-                    {
-                        const uint32_t mean = ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7));
-                        // centre row = newest row - 5: same stage if j >= 5, else the previous one
-                        const uint8_t* crow = (j >= 5)
-                            ? ring + s * kStageBytes + (j - 5) * kRowBytes
-                            : ring + ((it - 1) % kStages) * kStageBytes + (j + 5) * kRowBytes;
-                        emit_candidates(sumr, diff, mean, crow + kHalo + (x - xs), x, y, w, out, count, tp.cap);
-                    }
+                    if (__any_sync(kFull, (t & 0x80008000u) != 0)) pending |= 1u << j;   // settled after the block
                 }
             }
             Um2[j] = n.m2; U0[j] = n.c0; Up2[j] = n.p2; U4m[j] = n.m4; U4p[j] = n.p4; U5m[j] = n.m5; U5p[j] = n.p5;
+        }
+
+        while (pending)
+        {
+            const int j = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const int y = ybase + j;
+            if (y >= ys && y < ye)
+                emit_row(ring + s * kStageBytes, ring + ((it + kStages - 1) % kStages) * kStageBytes, j,
+                         kHalo + (x - xs), x, y, w, out, count, tp.cap);
         }
 
         if (USE_TMA && it >= 1)
@@ -305,18 +343,20 @@ chess_tiled_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, TilePa
 {
     __shared__ __align__(128) uint8_t ring[kStages * kStageBytes];
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+    __shared__ int next_issue;
     if (USE_TMA)
     {
         if (threadIdx.x == 0)
         {
+            next_issue = tp.lookahead;   // the prologue below requests iterations 0 .. lookahead-1
             for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kTileThreads / 32); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
     }
     // warps alternate between the two pixel-pair alignments of the same 128-pixel span
-    if (((threadIdx.x >> 5) & 1) == 0) strip_walk<0, USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, cand, counts);
-    else                               strip_walk<2, USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, cand, counts);
+    if (((threadIdx.x >> 5) & 1) == 0) strip_walk<0, USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, &next_issue, cand, counts);
+    else                               strip_walk<2, USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, &next_issue, cand, counts);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,6 +405,8 @@ cudaError_t launch_chess_sparse_tiled(const FrameSet& fs, cand_t* cand, uint32_t
     if (fs.w <= 2*kMargin || fs.h <= 2*kMargin || fs.nframes <= 0) return cudaSuccess;
     TileParams tp;
     tp.cap = cand_capacity;
+    tp.lookahead = kLookahead;
+    if (const char* e = getenv("MRG_B200_K1_LOOKAHEAD")) { int v = atoi(e); if (v >= 1 && v <= kStages - 2) tp.lookahead = v; }
     tp.nstrips = (fs.w - kMargin + kTileW - 1) / kTileW;       // strips start at x = 0
     const int out_rows = fs.h - 2*kMargin;
     // enough work items to fill the chip a few times over, but segments no shorter than 40 rows
