@@ -156,7 +156,9 @@ struct FrameWork
     cand_t*   cand;
     uint32_t* table;
     uint32_t* dfs;
-    int       n, bits;
+    uint32_t* keys2;     // shared-memory path only: scratch for the (region, index) sort
+    int       n, bits, P;
+    bool      in_smem;
 };
 
 __device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, const uint32_t* counts,
@@ -205,7 +207,8 @@ __device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, c
         while (atomicCAS(&table[slot], kEmpty, (uint32_t)i) != kEmpty) slot = (slot + 1) & mask;
     }
     __syncthreads();
-    fw.cand = cand; fw.table = table; fw.dfs = dfs; fw.n = n; fw.bits = bits;
+    fw.cand = cand; fw.table = table; fw.dfs = dfs; fw.n = n; fw.bits = bits; fw.P = P; fw.in_smem = in_smem;
+    fw.keys2 = (uint32_t*)(smem + (sizeof(cand_t) + 3*sizeof(uint32_t)) * kClusterSmemCands);
     return true;
 }
 
@@ -218,7 +221,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
                     int32_t* xy_int, double* xy_dbl, int32_t* out_counts)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_nrec;
+    __shared__ int s_nrec, s_nout;
     const int f = blockIdx.x, tid = threadIdx.x;
     FrameWork fw;
     if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem))
@@ -230,28 +233,91 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
     const int record_cap = p.record_capacity;
     ComponentRecord* rec = (ComponentRecord*)p.records + (size_t)f * record_cap;
 
-    if (tid == 0)
+    if (tid == 0) s_nrec = 0;
+    __syncthreads();
+
+    // One seed's component, grown by the calling thread; parks it if it passes the cheap tests.
+    auto try_seed = [&](int s)
     {
-        int nrec = 0;
-        for (int s = 0; s < fw.n; s++)
+        const cand_t sc = fw.cand[s];
+        if (cand_r(sc) == 0) return;
+        const int x = cand_x(sc), y = cand_y(sc);
+        if (x < kMargin + 1 || x >= w - kMargin - 1 || y < kMargin + 1 || y >= h - kMargin - 1) return;
+        Component c;
+        grow_component(c, fw.cand, fw.table, fw.bits, fw.dfs, &s, 1, w, h);
+        if (c.poisoned || c.n < kComponentMinN || c.peak <= kPeakMin) return;
+        const int slot = atomicAdd(&s_nrec, 1);
+        if (slot < record_cap)
         {
-            const cand_t sc = fw.cand[s];
-            if (cand_r(sc) == 0) continue;
-            const int x = cand_x(sc), y = cand_y(sc);
-            if (x < kMargin + 1 || x >= w - kMargin - 1 || y < kMargin + 1 || y >= h - kMargin - 1) continue;
-            Component c;
-            grow_component(c, fw.cand, fw.table, fw.bits, fw.dfs, &s, 1, w, h);
-            if (c.poisoned || c.n < kComponentMinN || c.peak <= kPeakMin) continue;
-            if (nrec < record_cap)
-            {
-                ComponentRecord r;
-                r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
-                r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x; r.tag = 0;
-                rec[nrec] = r;
-            }
-            nrec++;
+            ComponentRecord r;
+            r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
+            r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x; r.tag = s;   // seed index = output order
+            rec[slot] = r;
         }
-        s_nrec = nrec;
+    };
+
+    if (!fw.in_smem)
+    {
+        // Big candidate lists live in global scratch: one thread replays the frame in raster order.
+        if (tid == 0)
+            for (int s = 0; s < fw.n; s++) try_seed(s);
+    }
+    else
+    {
+        // The reference's scan is sequential only WITHIN a 4-connected region of the candidate set
+        // (nothing a component does reaches outside its region), so: label the regions in parallel,
+        // bring each region's pixels together in raster order, and let one thread replay each region.
+        uint32_t* label = fw.dfs;     // the walk only needs dfs[] afterwards
+        const int n = fw.n;
+        for (int i = tid; i < n; i += kClusterThreads) label[i] = (uint32_t)i;
+        __syncthreads();
+        for (;;)
+        {
+            bool changed = false;
+            for (int i = tid; i < n; i += kClusterThreads)
+            {
+                const cand_t c = fw.cand[i];
+                const uint32_t key = cand_key(c);
+                uint32_t l = label[i];
+                const uint32_t nk[4] = { key - 0x10000u, key + 0x10000u, key - 1u, key + 1u };
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                {
+                    const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
+                    if (q >= 0) l = min(l, label[q]);
+                }
+                l = min(l, label[l]);                    // pointer jumping
+                if (l < label[i]) { label[i] = l; changed = true; }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        // (region label, index) sort: regions become contiguous, their pixels stay in raster order
+        const int P = fw.P;
+        for (int i = tid; i < P; i += kClusterThreads) fw.keys2[i] = i < n ? ((label[i] << 16) | (uint32_t)i) : 0xFFFFFFFFu;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1)
+            {
+                for (int i = tid; i < P; i += kClusterThreads)
+                {
+                    const int l = i ^ j;
+                    if (l > i)
+                    {
+                        const uint32_t a = fw.keys2[i], b = fw.keys2[l];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { fw.keys2[i] = b; fw.keys2[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        // one thread per region
+        for (int m = tid; m < n; m += kClusterThreads)
+        {
+            const uint32_t km = fw.keys2[m];
+            if (m > 0 && (fw.keys2[m - 1] >> 16) == (km >> 16)) continue;    // not the head of its region
+            for (int e = m; e < n && (fw.keys2[e] >> 16) == (km >> 16); e++)
+                try_seed((int)(fw.keys2[e] & 0xFFFFu));
+        }
     }
     __syncthreads();
     const int nrec = s_nrec;
@@ -271,27 +337,35 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
     }
     __syncthreads();
 
-    if (tid == 0)
+    // Output order = raster order of the seeds (find_chessboard_corners.cc:332-351): rank the
+    // surviving records by seed index.
+    if (tid == 0) s_nout = 0;
+    __syncthreads();
+    const double scale = (double)(1 << p.level);
+    for (int k = tid; k < nrec; k += kClusterThreads)
     {
-        const double scale = (double)(1 << p.level);
-        int nout = 0;
-        for (int k = 0; k < nrec; k++)
+        const int tag = rec[k].tag;
+        if (tag < 0) continue;
+        int rank = 0;
+        for (int j = 0; j < nrec; j++)
         {
-            if (rec[k].tag < 0) continue;
-            if (nout < p.max_points)
-            {
-                const double sw = __ull2double_rn(rec[k].sw);
-                const double fx = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swx), sw), scale);
-                const double fy = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swy), sw), scale);
-                const size_t o = ((size_t)f * p.max_points + nout) * 2;
-                xy_int[o]     = __double2int_rz(__dadd_rn(0.5, __dmul_rn(fx, kFindGridScale)));
-                xy_int[o + 1] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(fy, kFindGridScale)));
-                if (xy_dbl) { xy_dbl[o] = fx; xy_dbl[o + 1] = fy; }
-            }
-            nout++;
+            const int tj = rec[j].tag;
+            rank += (tj >= 0 && tj < tag) ? 1 : 0;
         }
-        out_counts[f] = nout;
+        atomicAdd(&s_nout, 1);
+        if (rank < p.max_points)
+        {
+            const double sw = __ull2double_rn(rec[k].sw);
+            const double fx = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swx), sw), scale);
+            const double fy = rescale_coord(__ddiv_rn(__ull2double_rn(rec[k].swy), sw), scale);
+            const size_t o = ((size_t)f * p.max_points + rank) * 2;
+            xy_int[o]     = __double2int_rz(__dadd_rn(0.5, __dmul_rn(fx, kFindGridScale)));
+            xy_int[o + 1] = __double2int_rz(__dadd_rn(0.5, __dmul_rn(fy, kFindGridScale)));
+            if (xy_dbl) { xy_dbl[o] = fx; xy_dbl[o + 1] = fy; }
+        }
     }
+    __syncthreads();
+    if (tid == 0) out_counts[f] = s_nout;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -378,7 +452,7 @@ cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint
     if (tid == 0) out_refined[f] = s_nrefined;
 }
 
-static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 3*sizeof(uint32_t)) * (size_t)kClusterSmemCands; }
+static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 4*sizeof(uint32_t)) * (size_t)kClusterSmemCands; }
 
 size_t cluster_record_bytes() { return sizeof(ComponentRecord); }
 
