@@ -156,13 +156,14 @@ struct FrameWork
     cand_t*   cand;
     uint32_t* table;
     uint32_t* dfs;
-    uint32_t* keys2;     // shared-memory path only: scratch for the (region, index) sort
     int       n, bits, P;
     bool      in_smem;
 };
 
+// sort_mode: 0 = never sort (caller orders what it needs itself; only valid for the shared-memory
+// path), 1 = always sort into raster order, 2 = sort only lists that live in global scratch
 __device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, const uint32_t* counts,
-                              uint32_t* scratch_table, uint32_t* scratch_dfs, uint8_t* smem)
+                              uint32_t* scratch_table, uint32_t* scratch_dfs, uint8_t* smem, int sort_mode)
 {
     const int tid = threadIdx.x;
     const uint32_t total = counts[f];
@@ -181,6 +182,7 @@ __device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, c
     __syncthreads();
 
     // bitonic sort: ascending word order == raster order
+    if (sort_mode == 1 || (sort_mode == 2 && !in_smem))
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1)
         {
@@ -208,7 +210,6 @@ __device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, c
     }
     __syncthreads();
     fw.cand = cand; fw.table = table; fw.dfs = dfs; fw.n = n; fw.bits = bits; fw.P = P; fw.in_smem = in_smem;
-    fw.keys2 = (uint32_t*)(smem + (sizeof(cand_t) + 3*sizeof(uint32_t)) * kClusterSmemCands);
     return true;
 }
 
@@ -224,7 +225,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
     __shared__ int s_nrec, s_nout;
     const int f = blockIdx.x, tid = threadIdx.x;
     FrameWork fw;
-    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem))
+    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 2))
     {
         if (tid == 0) out_counts[f] = -1;
         return;
@@ -251,33 +252,29 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         {
             ComponentRecord r;
             r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
-            r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x; r.tag = s;   // seed index = output order
+            r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x;
+            r.tag = (int32_t)cand_key(sc);          // raster position of the seed = output order
             rec[slot] = r;
         }
     };
 
-    if (!fw.in_smem)
-    {
-        // Big candidate lists live in global scratch: one thread replays the frame in raster order.
-        if (tid == 0)
-            for (int s = 0; s < fw.n; s++) try_seed(s);
-    }
-    else
+    bool sequential = !fw.in_smem;
+    if (fw.in_smem)
     {
         // The reference's scan is sequential only WITHIN a 4-connected region of the candidate set
-        // (nothing a component does reaches outside its region), so: label the regions in parallel,
-        // bring each region's pixels together in raster order, and let one thread replay each region.
-        uint32_t* label = fw.dfs;     // the walk only needs dfs[] afterwards
+        // (nothing a component does reaches outside its region). So: label the regions in parallel
+        // (label = smallest raster key in the region), let the thread that owns a region's first
+        // pixel collect the region, put it in raster order and replay it.
+        uint32_t* label = fw.dfs;     // grow_component() only needs dfs[] once a region is collected
         const int n = fw.n;
-        for (int i = tid; i < n; i += kClusterThreads) label[i] = (uint32_t)i;
+        for (int i = tid; i < n; i += kClusterThreads) label[i] = cand_key(fw.cand[i]);
         __syncthreads();
         for (;;)
         {
             bool changed = false;
             for (int i = tid; i < n; i += kClusterThreads)
             {
-                const cand_t c = fw.cand[i];
-                const uint32_t key = cand_key(c);
+                const uint32_t key = cand_key(fw.cand[i]);
                 uint32_t l = label[i];
                 const uint32_t nk[4] = { key - 0x10000u, key + 0x10000u, key - 1u, key + 1u };
 #pragma unroll
@@ -286,39 +283,55 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
                     const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
                     if (q >= 0) l = min(l, label[q]);
                 }
-                l = min(l, label[l]);                    // pointer jumping
                 if (l < label[i]) { label[i] = l; changed = true; }
             }
             if (!__syncthreads_or(changed)) break;
         }
-        // (region label, index) sort: regions become contiguous, their pixels stay in raster order
-        const int P = fw.P;
-        for (int i = tid; i < P; i += kClusterThreads) fw.keys2[i] = i < n ? ((label[i] << 16) | (uint32_t)i) : 0xFFFFFFFFu;
-        __syncthreads();
-        for (int k = 2; k <= P; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1)
-            {
-                for (int i = tid; i < P; i += kClusterThreads)
-                {
-                    const int l = i ^ j;
-                    if (l > i)
-                    {
-                        const uint32_t a = fw.keys2[i], b = fw.keys2[l];
-                        const bool up = (i & k) == 0;
-                        if ((a > b) == up) { fw.keys2[i] = b; fw.keys2[l] = a; }
-                    }
-                }
-                __syncthreads();
-            }
-        // one thread per region
-        for (int m = tid; m < n; m += kClusterThreads)
+
+        constexpr int kRegionMax = 64;
+        constexpr uint32_t kCollected = 0xFFFFFFFFu;
+        for (int i = tid; i < n && !sequential; i += kClusterThreads)
         {
-            const uint32_t km = fw.keys2[m];
-            if (m > 0 && (fw.keys2[m - 1] >> 16) == (km >> 16)) continue;    // not the head of its region
-            for (int e = m; e < n && (fw.keys2[e] >> 16) == (km >> 16); e++)
-                try_seed((int)(fw.keys2[e] & 0xFFFFu));
+            const uint32_t key = cand_key(fw.cand[i]);
+            if (label[i] != key) continue;              // not the first pixel of its region
+            // collect the region (breadth first through the hash table), marking what was taken
+            int members[kRegionMax], count = 1;
+            members[0] = i; label[i] = kCollected;
+            for (int head = 0; head < count && !sequential; head++)
+            {
+                const uint32_t mk = cand_key(fw.cand[members[head]]);
+                const uint32_t nk[4] = { mk - 0x10000u, mk + 0x10000u, mk - 1u, mk + 1u };
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                {
+                    const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
+                    if (q < 0 || label[q] != key) continue;
+                    if (count == kRegionMax) { sequential = true; break; }
+                    label[q] = kCollected; members[count++] = q;
+                }
+            }
+            if (sequential) break;
+            // raster order (insertion sort on the keys; regions are a dozen pixels)
+            for (int a = 1; a < count; a++)
+            {
+                const int m = members[a]; const uint32_t mk = cand_key(fw.cand[m]);
+                int b = a - 1;
+                while (b >= 0 && cand_key(fw.cand[members[b]]) > mk) { members[b + 1] = members[b]; b--; }
+                members[b + 1] = m;
+            }
+            for (int a = 0; a < count; a++) try_seed(members[a]);
+        }
+        // a region too large for one thread's scratch: redo the whole frame the sequential way
+        sequential = __syncthreads_or(sequential) != 0;
+        if (sequential)
+        {
+            if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 1)) return;
+            if (tid == 0) s_nrec = 0;
+            __syncthreads();
         }
     }
+    if (sequential && tid == 0)
+        for (int s = 0; s < fw.n; s++) try_seed(s);     // raster order: the list is sorted on this path
     __syncthreads();
     const int nrec = s_nrec;
     if (nrec > record_cap)
@@ -382,7 +395,7 @@ cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint
     const int f = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) s_nrefined = 0;
     FrameWork fw;
-    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem))
+    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 1))
     {
         if (tid == 0) out_refined[f] = -1;
         return;
@@ -452,7 +465,7 @@ cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint
     if (tid == 0) out_refined[f] = s_nrefined;
 }
 
-static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 4*sizeof(uint32_t)) * (size_t)kClusterSmemCands; }
+static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 3*sizeof(uint32_t)) * (size_t)kClusterSmemCands; }
 
 size_t cluster_record_bytes() { return sizeof(ComponentRecord); }
 
