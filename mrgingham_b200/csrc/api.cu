@@ -95,8 +95,17 @@ struct mrg_b200_detector
     cudaStream_t own_stream = nullptr;
     std::mutex   mtx;
 
-    // per-chunk scratch
-    DeviceBuffer stage, level_img, cand, counts, table, dfs, records, xy, outcounts;
+    // Per-chunk scratch, double-buffered: chunk c uses slot c&1, so the clustering kernel of chunk
+    // c (aux stream) and the host->device copy of chunk c+1 (copy stream) overlap the ChESS kernel
+    // of chunk c+1 (main stream).
+    struct Slot
+    {
+        DeviceBuffer stage, level_img, cand, counts, table, dfs, records, xy, outcounts;
+        cudaEvent_t staged = nullptr, k1done = nullptr, k2done = nullptr;
+        bool used = false;
+    } slot[2];
+    cudaStream_t aux_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t  ev_fork = nullptr;
     // scratch for single frames whose candidate list overflowed the default capacity
     DeviceBuffer big_cand, big_table, big_dfs, big_records;
     // refinement
@@ -151,10 +160,11 @@ LevelGeom level_geom(int rows, int cols, int level)
     return g;
 }
 
-// Puts `n` frames on the device (if they are not there already) and, for level > 0, builds the
-// level image. On return `out` describes the image the detector kernels must read.
-int stage_frames(mrg_b200_detector* det, const uint8_t* images, int on_device, int n, int rows, int cols,
-                 size_t pitch, size_t fstride, int level, cudaStream_t stream, FrameSet* out)
+// Puts `n` frames on the device (if they are not there already; the copy goes on `cstream` and
+// `stream` is made to wait for it) and, for level > 0, builds the level image on `stream`.
+// On return `out` describes the image the detector kernels must read.
+int stage_frames(mrg_b200_detector* det, mrg_b200_detector::Slot& S, const uint8_t* images, int on_device, int n, int rows, int cols,
+                 size_t pitch, size_t fstride, int level, cudaStream_t stream, cudaStream_t cstream, FrameSet* out)
 {
     FrameSet src;
     if (on_device)
@@ -165,39 +175,44 @@ int stage_frames(mrg_b200_detector* det, const uint8_t* images, int on_device, i
     {
         const int spitch = round_up(cols, 16);
         const size_t sframe = (size_t)spitch * rows;
-        if (det->stage.ensure(sframe * n)) return -1;
+        if (S.stage.ensure(sframe * n)) return -1;
         if (fstride == pitch * (size_t)rows)
-            CUDA_TRY(cudaMemcpy2DAsync(det->stage.p, spitch, images, pitch, cols, (size_t)rows * n, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpy2DAsync(S.stage.p, spitch, images, pitch, cols, (size_t)rows * n, cudaMemcpyHostToDevice, cstream));
         else
             for (int i = 0; i < n; i++)
-                CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)det->stage.p + i * sframe, spitch, images + i * fstride, pitch, cols, rows,
-                                           cudaMemcpyHostToDevice, stream));
-        src.base = (const uint8_t*)det->stage.p; src.frame_stride = sframe; src.pitch = spitch;
+                CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)S.stage.p + i * sframe, spitch, images + i * fstride, pitch, cols, rows,
+                                           cudaMemcpyHostToDevice, cstream));
+        if (cstream != stream)
+        {
+            CUDA_TRY(cudaEventRecord(S.staged, cstream));
+            CUDA_TRY(cudaStreamWaitEvent(stream, S.staged, 0));
+        }
+        src.base = (const uint8_t*)S.stage.p; src.frame_stride = sframe; src.pitch = spitch;
     }
     src.w = cols; src.h = rows; src.nframes = n;
     if (level == 0) { *out = src; return 0; }
 
     const LevelGeom g = level_geom(rows, cols, level);
-    if (det->level_img.ensure(g.frame_bytes * n)) return -1;
+    if (S.level_img.ensure(g.frame_bytes * n)) return -1;
     {
         Launch l(det, 2, stream);
-        CUDA_TRY(launch_pyramid(src, level, (uint8_t*)det->level_img.p, g.pitch, g.frame_bytes, g.w, g.h, stream));
+        CUDA_TRY(launch_pyramid(src, level, (uint8_t*)S.level_img.p, g.pitch, g.frame_bytes, g.w, g.h, stream));
     }
-    out->base = (const uint8_t*)det->level_img.p; out->frame_stride = g.frame_bytes; out->pitch = g.pitch;
+    out->base = (const uint8_t*)S.level_img.p; out->frame_stride = g.frame_bytes; out->pitch = g.pitch;
     out->w = g.w; out->h = g.h; out->nframes = n;
     return 0;
 }
 
-int ensure_chunk_scratch(mrg_b200_detector* det, int n)
+int ensure_chunk_scratch(mrg_b200_detector* det, mrg_b200_detector::Slot& S, int n)
 {
     const size_t cap = det->cfg.candidate_capacity, mp = det->cfg.max_points;
-    if (det->cand.ensure(sizeof(cand_t) * cap * n)) return -1;
-    if (det->counts.ensure(sizeof(uint32_t) * n)) return -1;
-    if (det->table.ensure(sizeof(uint32_t) * 2 * cap * n)) return -1;
-    if (det->dfs.ensure(sizeof(uint32_t) * cap * n)) return -1;
-    if (det->records.ensure(cluster_record_bytes() * 2 * mp * n)) return -1;
-    if (det->xy.ensure(sizeof(int32_t) * 2 * mp * n)) return -1;
-    if (det->outcounts.ensure(sizeof(int32_t) * n)) return -1;
+    if (S.cand.ensure(sizeof(cand_t) * cap * n)) return -1;
+    if (S.counts.ensure(sizeof(uint32_t) * n)) return -1;
+    if (S.table.ensure(sizeof(uint32_t) * 2 * cap * n)) return -1;
+    if (S.dfs.ensure(sizeof(uint32_t) * cap * n)) return -1;
+    if (S.records.ensure(cluster_record_bytes() * 2 * mp * n)) return -1;
+    if (S.xy.ensure(sizeof(int32_t) * 2 * mp * n)) return -1;
+    if (S.outcounts.ensure(sizeof(int32_t) * n)) return -1;
     return 0;
 }
 
@@ -206,8 +221,9 @@ int ensure_chunk_scratch(mrg_b200_detector* det, int n)
 int rerun_big(mrg_b200_detector* det, const uint8_t* image, int on_device, int rows, int cols, size_t pitch,
               int level, cudaStream_t stream, int32_t* xy_out, int32_t* count_out, int32_t* candcount_out)
 {
+    mrg_b200_detector::Slot& S = det->slot[0];
     FrameSet fs;
-    if (stage_frames(det, image, on_device, 1, rows, cols, pitch, pitch * rows, level, stream, &fs)) return -1;
+    if (stage_frames(det, S, image, on_device, 1, rows, cols, pitch, pitch * rows, level, stream, stream, &fs)) return -1;
     const int cap = next_pow2((long long)fs.w * fs.h);
     const int mp = det->cfg.max_points;
     const int reccap = cap / 2 + 1;
@@ -215,18 +231,18 @@ int rerun_big(mrg_b200_detector* det, const uint8_t* image, int on_device, int r
     if (det->big_table.ensure(sizeof(uint32_t) * 2 * cap)) return -1;
     if (det->big_dfs.ensure(sizeof(uint32_t) * cap)) return -1;
     if (det->big_records.ensure(cluster_record_bytes() * reccap)) return -1;
-    if (ensure_chunk_scratch(det, 1)) return -1;
-    CUDA_TRY(cudaMemsetAsync(det->counts.p, 0, sizeof(uint32_t), stream));
-    if (chess_sparse(det, fs, (cand_t*)det->big_cand.p, (uint32_t*)det->counts.p, cap, stream)) return -1;
+    if (ensure_chunk_scratch(det, S, 1)) return -1;
+    CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t), stream));
+    if (chess_sparse(det, fs, (cand_t*)det->big_cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
     ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = reccap; p.records = det->big_records.p;
     {
         Launch l(det, 1, stream);
-        CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)det->big_cand.p, (uint32_t*)det->counts.p, (uint32_t*)det->big_table.p,
-                                     (uint32_t*)det->big_dfs.p, (int32_t*)det->xy.p, nullptr, (int32_t*)det->outcounts.p, stream));
+        CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)det->big_cand.p, (uint32_t*)S.counts.p, (uint32_t*)det->big_table.p,
+                                     (uint32_t*)det->big_dfs.p, (int32_t*)S.xy.p, nullptr, (int32_t*)S.outcounts.p, stream));
     }
-    CUDA_TRY(cudaMemcpyAsync(xy_out, det->xy.p, sizeof(int32_t) * 2 * mp, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(count_out, det->outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(candcount_out, det->counts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(xy_out, S.xy.p, sizeof(int32_t) * 2 * mp, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(count_out, S.outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(candcount_out, S.counts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     if (*count_out < 0) { MSG("Frame still overflows at worst-case capacity; this is a bug."); return -1; }
     return 0;
@@ -251,24 +267,52 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
     if (det->h_candcounts.ensure(sizeof(int32_t) * std::max(nframes, 1))) return -1;
 
     const int chunk = det->cfg.max_frames;
-    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    cudaStream_t aux = det->aux_stream, cpy = det->copy_stream;
+    // size both slots before anything is in flight (growing a buffer frees it)
+    for (int b = 0; b < 2 && b * chunk < nframes; b++)
+    {
+        mrg_b200_detector::Slot& S = det->slot[b];
+        const int n = std::min(chunk, nframes);
+        if (ensure_chunk_scratch(det, S, n)) return -1;
+        if (!on_device && S.stage.ensure((size_t)round_up(cols, 16) * rows * n)) return -1;
+        if (level > 0 && S.level_img.ensure(level_geom(rows, cols, level).frame_bytes * n)) return -1;
+        S.used = false;
+    }
+    CUDA_TRY(cudaEventRecord(det->ev_fork, stream));
+    CUDA_TRY(cudaStreamWaitEvent(aux, det->ev_fork, 0));
+    CUDA_TRY(cudaStreamWaitEvent(cpy, det->ev_fork, 0));
+    int c = 0;
+    for (int f0 = 0; f0 < nframes; f0 += chunk, c++)
     {
         const int n = std::min(chunk, nframes - f0);
-        FrameSet fs;
-        if (stage_frames(det, images + (size_t)f0 * fstride, on_device, n, rows, cols, pitch, fstride, level, stream, &fs)) return -1;
-        if (ensure_chunk_scratch(det, n)) return -1;
-        CUDA_TRY(cudaMemsetAsync(det->counts.p, 0, sizeof(uint32_t) * n, stream));
-        if (chess_sparse(det, fs, (cand_t*)det->cand.p, (uint32_t*)det->counts.p, cap, stream)) return -1;
-        ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = 2 * mp; p.records = det->records.p;
+        mrg_b200_detector::Slot& S = det->slot[c & 1];
+        if (S.used)
         {
-            Launch l(det, 1, stream);
-            CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)det->cand.p, (uint32_t*)det->counts.p, (uint32_t*)det->table.p,
-                                         (uint32_t*)det->dfs.p, (int32_t*)det->xy.p, nullptr, (int32_t*)det->outcounts.p, stream));
+            // the slot's previous chunk must have left the clustering kernel
+            CUDA_TRY(cudaStreamWaitEvent(stream, S.k2done, 0));
+            CUDA_TRY(cudaStreamWaitEvent(cpy, S.k2done, 0));
         }
-        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_xy.p + (size_t)f0 * 2 * mp, det->xy.p, sizeof(int32_t) * 2 * mp * n, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_counts.p + f0, det->outcounts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_candcounts.p + f0, det->counts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream));
+        FrameSet fs;
+        if (stage_frames(det, S, images + (size_t)f0 * fstride, on_device, n, rows, cols, pitch, fstride, level, stream, cpy, &fs)) return -1;
+        CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t) * n, stream));
+        if (chess_sparse(det, fs, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
+        CUDA_TRY(cudaEventRecord(S.k1done, stream));
+        CUDA_TRY(cudaStreamWaitEvent(aux, S.k1done, 0));
+        ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = 2 * mp; p.records = S.records.p;
+        {
+            Launch l(det, 1, aux);
+            CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, (uint32_t*)S.table.p,
+                                         (uint32_t*)S.dfs.p, (int32_t*)S.xy.p, nullptr, (int32_t*)S.outcounts.p, aux));
+        }
+        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_xy.p + (size_t)f0 * 2 * mp, S.xy.p, sizeof(int32_t) * 2 * mp * n, cudaMemcpyDeviceToHost, aux));
+        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_counts.p + f0, S.outcounts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, aux));
+        CUDA_TRY(cudaMemcpyAsync((int32_t*)det->h_candcounts.p + f0, S.counts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, aux));
+        CUDA_TRY(cudaEventRecord(S.k2done, aux));
+        S.used = true;
     }
+    // join: everything this call enqueued is ordered before whatever the caller puts on `stream` next
+    for (int b = 0; b < 2; b++)
+        if (det->slot[b].used) CUDA_TRY(cudaStreamWaitEvent(stream, det->slot[b].k2done, 0));
     det->pending.active = true;
     det->pending.images = images; det->pending.on_device = on_device; det->pending.nframes = nframes;
     det->pending.rows = rows; det->pending.cols = cols; det->pending.level = level;
@@ -319,8 +363,17 @@ API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detecto
     if (det->cfg.candidate_capacity <= 0) det->cfg.candidate_capacity = 32768;
     det->cfg.candidate_capacity = next_pow2(det->cfg.candidate_capacity);
     if (det->cfg.max_points <= 0) det->cfg.max_points = 1024;
-    if (cudaSetDevice(det->device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&det->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    bool ok = cudaSetDevice(det->device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&det->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              // clustering runs at high priority so its few CTAs slot in as ChESS CTAs retire
+              cudaStreamCreateWithPriority(&det->aux_stream, cudaStreamNonBlocking, -1) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&det->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&det->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int b = 0; b < 2 && ok; b++)
+        ok = cudaEventCreateWithFlags(&det->slot[b].staged, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&det->slot[b].k1done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&det->slot[b].k2done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok)
     {
         MSG("Could not initialise CUDA device %d.", det->device);
         delete det;
@@ -335,9 +388,15 @@ API void mrg_b200_detector_destroy(mrg_b200_detector* det)
     if (!det) return;
     cudaSetDevice(det->device);
     cudaDeviceSynchronize();
-    for (DeviceBuffer* b : { &det->stage, &det->level_img, &det->cand, &det->counts, &det->table, &det->dfs, &det->records,
-                             &det->xy, &det->outcounts, &det->big_cand, &det->big_table, &det->big_dfs, &det->big_records,
-                             &det->pts, &det->lvls }) b->release();
+    for (auto& S : det->slot)
+    {
+        for (DeviceBuffer* b : { &S.stage, &S.level_img, &S.cand, &S.counts, &S.table, &S.dfs, &S.records, &S.xy, &S.outcounts }) b->release();
+        for (cudaEvent_t e : { S.staged, S.k1done, S.k2done }) if (e) cudaEventDestroy(e);
+    }
+    for (DeviceBuffer* b : { &det->big_cand, &det->big_table, &det->big_dfs, &det->big_records, &det->pts, &det->lvls }) b->release();
+    if (det->ev_fork) cudaEventDestroy(det->ev_fork);
+    if (det->aux_stream) cudaStreamDestroy(det->aux_stream);
+    if (det->copy_stream) cudaStreamDestroy(det->copy_stream);
     for (PinnedBuffer* b : { &det->h_xy, &det->h_counts, &det->h_candcounts }) b->release();
     for (auto& t : det->timers) t.release();
     if (det->own_stream) cudaStreamDestroy(det->own_stream);
@@ -387,15 +446,16 @@ API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* ima
     for (int f0 = 0; f0 < nframes; f0 += chunk)
     {
         const int n = std::min(chunk, nframes - f0);
+        mrg_b200_detector::Slot& S = det->slot[0];
         FrameSet fs;
-        if (stage_frames(det, images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride, 0, stream, &fs)) return -1;
+        if (stage_frames(det, S, images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride, 0, stream, stream, &fs)) return -1;
         int16_t* dresp;
         if (response_on_device) dresp = response + (size_t)f0 * fe;
         else
         {
             // scratch: reuse the candidate buffer allocation
-            if (det->cand.ensure(sizeof(int16_t) * fe * n)) return -1;
-            dresp = (int16_t*)det->cand.p;
+            if (S.cand.ensure(sizeof(int16_t) * fe * n)) return -1;
+            dresp = (int16_t*)S.cand.p;
         }
         CUDA_TRY(launch_chess_dense(fs, dresp, fe, stream));
         if (!response_on_device && cols > 2*kMargin && rows > 2*kMargin)
@@ -424,7 +484,7 @@ API int mrg_b200_pyramid_level(mrg_b200_detector* det, const uint8_t* image, int
     CUDA_TRY(cudaSetDevice(det->device));
     cudaStream_t stream = det->own_stream;
     FrameSet fs;
-    if (stage_frames(det, image, 0, 1, rows, cols, row_pitch, row_pitch * rows, level, stream, &fs)) return -1;
+    if (stage_frames(det, det->slot[0], image, 0, 1, rows, cols, row_pitch, row_pitch * rows, level, stream, stream, &fs)) return -1;
     *orows = fs.h; *ocols = fs.w;
     if (out && fs.w > 0 && fs.h > 0)
         CUDA_TRY(cudaMemcpy2DAsync(out, fs.w, fs.base, fs.pitch, fs.w, fs.h, cudaMemcpyDeviceToHost, stream));
@@ -544,25 +604,27 @@ API int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int 
     std::lock_guard<std::mutex> g2(det->mtx);
     CUDA_TRY(cudaSetDevice(det->device));
     cudaStream_t stream = det->own_stream;
+    mrg_b200_detector::Slot& S = det->slot[0];
+    if (det->pending.active) { MSG("A batch is in flight on the default detector."); return -1; }
     FrameSet fs;
-    if (stage_frames(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, stream, &fs)) return -1;
+    if (stage_frames(det, S, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, stream, stream, &fs)) return -1;
     if (det->pts.ensure(sizeof(double) * 2 * Npoints)) return -1;
     if (det->lvls.ensure(Npoints)) return -1;
-    if (ensure_chunk_scratch(det, 1)) return -1;
+    if (ensure_chunk_scratch(det, S, 1)) return -1;
     int cap = det->cfg.candidate_capacity, reccap = std::max(Npoints, 1);
-    cand_t* cand = (cand_t*)det->cand.p; uint32_t* table = (uint32_t*)det->table.p; uint32_t* dfs = (uint32_t*)det->dfs.p;
+    cand_t* cand = (cand_t*)S.cand.p; uint32_t* table = (uint32_t*)S.table.p; uint32_t* dfs = (uint32_t*)S.dfs.p;
     for (int attempt = 0; attempt < 2; attempt++)
     {
         if (det->big_records.ensure(cluster_record_bytes() * reccap)) return -1;
         CUDA_TRY(cudaMemcpyAsync(det->pts.p, xy_inout, sizeof(double) * 2 * Npoints, cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(det->lvls.p, levels, Npoints, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaMemsetAsync(det->counts.p, 0, sizeof(uint32_t), stream));
-        if (chess_sparse(det, fs, cand, (uint32_t*)det->counts.p, cap, stream)) return -1;
+        CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t), stream));
+        if (chess_sparse(det, fs, cand, (uint32_t*)S.counts.p, cap, stream)) return -1;
         ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = det->cfg.max_points; p.record_capacity = reccap; p.records = det->big_records.p;
-        CUDA_TRY(launch_cluster_refine(fs, p, cand, (uint32_t*)det->counts.p, table, dfs, (double*)det->pts.p, (signed char*)det->lvls.p,
-                                       Npoints, (int32_t*)det->outcounts.p, stream));
+        CUDA_TRY(launch_cluster_refine(fs, p, cand, (uint32_t*)S.counts.p, table, dfs, (double*)det->pts.p, (signed char*)det->lvls.p,
+                                       Npoints, (int32_t*)S.outcounts.p, stream));
         int32_t nref = 0;
-        CUDA_TRY(cudaMemcpyAsync(&nref, det->outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&nref, S.outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         if (nref >= 0)
         {

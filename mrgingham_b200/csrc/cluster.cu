@@ -222,7 +222,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
                     int32_t* xy_int, double* xy_dbl, int32_t* out_counts)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_nrec, s_nout;
+    __shared__ int s_nrec, s_nout, s_nstart;
     const int f = blockIdx.x, tid = threadIdx.x;
     FrameWork fw;
     if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 2))
@@ -262,62 +262,59 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
     if (fw.in_smem)
     {
         // The reference's scan is sequential only WITHIN a 4-connected region of the candidate set
-        // (nothing a component does reaches outside its region). So: label the regions in parallel
-        // (label = smallest raster key in the region), let the thread that owns a region's first
-        // pixel collect the region, put it in raster order and replay it.
-        uint32_t* label = fw.dfs;     // grow_component() only needs dfs[] once a region is collected
+        // (nothing a component does reaches outside its region), so regions are replayed in
+        // parallel, one thread each. A region is found from its raster-first pixel: every candidate
+        // with no candidate above it and none to its left ("starter") floods its region through the
+        // hash table and gives up as soon as it meets a pixel that precedes it in raster order, so
+        // exactly one starter per region -- its first pixel -- survives with the full member list.
+        uint16_t* starters = (uint16_t*)(smem + (sizeof(cand_t) + 3*sizeof(uint32_t)) * kClusterSmemCands);
         const int n = fw.n;
-        for (int i = tid; i < n; i += kClusterThreads) label[i] = cand_key(fw.cand[i]);
+        if (tid == 0) s_nstart = 0;
         __syncthreads();
-        for (;;)
-        {
-            bool changed = false;
-            for (int i = tid; i < n; i += kClusterThreads)
-            {
-                const uint32_t key = cand_key(fw.cand[i]);
-                uint32_t l = label[i];
-                const uint32_t nk[4] = { key - 0x10000u, key + 0x10000u, key - 1u, key + 1u };
-#pragma unroll
-                for (int d = 0; d < 4; d++)
-                {
-                    const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
-                    if (q >= 0) l = min(l, label[q]);
-                }
-                if (l < label[i]) { label[i] = l; changed = true; }
-            }
-            if (!__syncthreads_or(changed)) break;
-        }
-
-        constexpr int kRegionMax = 64;
-        constexpr uint32_t kCollected = 0xFFFFFFFFu;
-        for (int i = tid; i < n && !sequential; i += kClusterThreads)
+        for (int i = tid; i < n; i += kClusterThreads)
         {
             const uint32_t key = cand_key(fw.cand[i]);
-            if (label[i] != key) continue;              // not the first pixel of its region
-            // collect the region (breadth first through the hash table), marking what was taken
+            if (table_lookup(fw.cand, fw.table, fw.bits, key - 0x10000u) < 0 &&
+                table_lookup(fw.cand, fw.table, fw.bits, key - 1u) < 0)
+                starters[atomicAdd(&s_nstart, 1)] = (uint16_t)i;
+        }
+        __syncthreads();
+        const int nstart = s_nstart;
+        constexpr int kRegionMax = 64;
+        for (int k = tid; k < nstart && !sequential; k += kClusterThreads)
+        {
+            const int i = starters[k];
+            const uint32_t key = cand_key(fw.cand[i]);
             int members[kRegionMax], count = 1;
-            members[0] = i; label[i] = kCollected;
-            for (int head = 0; head < count && !sequential; head++)
+            uint32_t mkeys[kRegionMax];
+            members[0] = i; mkeys[0] = key;
+            bool first = true;
+            for (int head = 0; head < count && first && !sequential; head++)
             {
-                const uint32_t mk = cand_key(fw.cand[members[head]]);
+                const uint32_t mk = mkeys[head];
                 const uint32_t nk[4] = { mk - 0x10000u, mk + 0x10000u, mk - 1u, mk + 1u };
 #pragma unroll
                 for (int d = 0; d < 4; d++)
                 {
+                    if (nk[d] < key) { if (table_lookup(fw.cand, fw.table, fw.bits, nk[d]) >= 0) first = false; continue; }
+                    bool seen = false;
+                    for (int e = 0; e < count; e++) seen |= mkeys[e] == nk[d];
+                    if (seen) continue;
                     const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
-                    if (q < 0 || label[q] != key) continue;
+                    if (q < 0) continue;
                     if (count == kRegionMax) { sequential = true; break; }
-                    label[q] = kCollected; members[count++] = q;
+                    members[count] = q; mkeys[count] = nk[d]; count++;
                 }
             }
             if (sequential) break;
+            if (!first) continue;
             // raster order (insertion sort on the keys; regions are a dozen pixels)
             for (int a = 1; a < count; a++)
             {
-                const int m = members[a]; const uint32_t mk = cand_key(fw.cand[m]);
+                const int m = members[a]; const uint32_t mk = mkeys[a];
                 int b = a - 1;
-                while (b >= 0 && cand_key(fw.cand[members[b]]) > mk) { members[b + 1] = members[b]; b--; }
-                members[b + 1] = m;
+                while (b >= 0 && mkeys[b] > mk) { members[b + 1] = members[b]; mkeys[b + 1] = mkeys[b]; b--; }
+                members[b + 1] = m; mkeys[b + 1] = mk;
             }
             for (int a = 0; a < count; a++) try_seed(members[a]);
         }
@@ -353,6 +350,11 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
     // Output order = raster order of the seeds (find_chessboard_corners.cc:332-351): rank the
     // surviving records by seed index.
     if (tid == 0) s_nout = 0;
+    // (the hash table is no longer needed: reuse its shared memory for the tags when they fit)
+    const bool tags_in_smem = nrec <= 2 * kClusterSmemCands;
+    int32_t* tags = (int32_t*)(smem + sizeof(cand_t) * kClusterSmemCands);
+    if (tags_in_smem)
+        for (int k = tid; k < nrec; k += kClusterThreads) tags[k] = rec[k].tag;
     __syncthreads();
     const double scale = (double)(1 << p.level);
     for (int k = tid; k < nrec; k += kClusterThreads)
@@ -360,11 +362,10 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         const int tag = rec[k].tag;
         if (tag < 0) continue;
         int rank = 0;
-        for (int j = 0; j < nrec; j++)
-        {
-            const int tj = rec[j].tag;
-            rank += (tj >= 0 && tj < tag) ? 1 : 0;
-        }
+        if (tags_in_smem)
+            for (int j = 0; j < nrec; j++) { const int tj = tags[j]; rank += (tj >= 0 && tj < tag) ? 1 : 0; }
+        else
+            for (int j = 0; j < nrec; j++) { const int tj = rec[j].tag; rank += (tj >= 0 && tj < tag) ? 1 : 0; }
         atomicAdd(&s_nout, 1);
         if (rank < p.max_points)
         {
@@ -465,7 +466,7 @@ cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint
     if (tid == 0) out_refined[f] = s_nrefined;
 }
 
-static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 3*sizeof(uint32_t)) * (size_t)kClusterSmemCands; }
+static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 3*sizeof(uint32_t) + sizeof(uint16_t)) * (size_t)kClusterSmemCands; }
 
 size_t cluster_record_bytes() { return sizeof(ComponentRecord); }
 
