@@ -1,0 +1,107 @@
+// C++ spellings of the reference's API for the hot path, as inline adapters over the C ABI in
+// <mrgingham_b200.h>. Mirrors find_chessboard_corners.hh:12-72 of the reference: same namespace,
+// names, argument order, defaults, return conventions and "append to the vector" semantics
+// (find_chessboard_corners.cc:350 push_back()s; the vector is never cleared).
+//
+// The reference takes cv::Mat. Where OpenCV's C++ headers exist the cv::Mat overloads below are
+// compiled; everywhere (this image has no OpenCV C++ headers) the same functions are available on
+// mrgingham::ImageView, a 4-field view with the only members the reference reads from the Mat
+// (rows, cols, step, data; type() and isContinuous() are expressed by construction).
+#pragma once
+
+#include <vector>
+#include <stdio.h>
+#include "../mrgingham_b200.h"
+
+#if defined(__has_include)
+#  if __has_include(<opencv2/core/core.hpp>)
+#    include <opencv2/core/core.hpp>
+#    define MRGINGHAM_B200_HAVE_OPENCV 1
+#  endif
+#endif
+
+namespace mrgingham
+{
+#ifndef MRGINGHAM_B200_POINT_TYPES
+#define MRGINGHAM_B200_POINT_TYPES
+    // point.hh:5-15 of the reference (layout relied on by the bridge: 2 ints / 2 doubles)
+    struct PointInt    { int x, y;    PointInt(int _x = 0, int _y = 0) : x(_x), y(_y) {} };
+    struct PointDouble { double x, y; PointDouble(double _x = 0, double _y = 0) : x(_x), y(_y) {} };
+#endif
+
+    struct ImageView
+    {
+        int rows, cols;
+        size_t step;                 // bytes between rows
+        const unsigned char* data;   // 8-bit, single channel
+    };
+
+    // find_chessboard_corners.cc:568-587. Appends to *points_scaled_out (scaled by 1000);
+    // returns true iff at least one point is in the vector afterwards (the reference returns
+    // points_scaled_out->size() > 0).
+    inline bool find_chessboard_corners_from_image_array(std::vector<PointInt>* points_scaled_out,
+                                                         const ImageView& image_input,
+                                                         int image_pyramid_level,
+                                                         bool debug = false,
+                                                         const char* debug_image_filename = NULL)
+    {
+        (void)debug; (void)debug_image_filename;
+        int cap = 4096;
+        std::vector<int> xy((size_t)2 * cap);
+        int n = mrg_b200_find_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
+                                                 image_pyramid_level, xy.data(), cap);
+        if (n > cap)
+        {
+            cap = n; xy.resize((size_t)2 * cap);
+            n = mrg_b200_find_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
+                                                 image_pyramid_level, xy.data(), cap);
+        }
+        for (int i = 0; i < n; i++) points_scaled_out->push_back(PointInt(xy[2*i], xy[2*i + 1]));
+        return points_scaled_out->size() > 0;
+    }
+
+    // find_chessboard_corners.cc:591-619. Returns how many points were refined.
+    inline int refine_chessboard_corners_from_image_array(std::vector<PointDouble>* points,
+                                                          signed char* level,
+                                                          const ImageView& image_input,
+                                                          int image_pyramid_level,
+                                                          bool debug = false,
+                                                          const char* debug_image_filename = NULL)
+    {
+        (void)debug; (void)debug_image_filename;
+        static_assert(sizeof(PointDouble) == 2 * sizeof(double), "PointDouble must be 2 doubles");
+        if (points->empty()) return 0;
+        return mrg_b200_refine_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
+                                                  image_pyramid_level, &(*points)[0].x, level, (int)points->size());
+    }
+
+#ifdef MRGINGHAM_B200_HAVE_OPENCV
+    inline bool mat_to_view(ImageView* v, const cv::Mat& m, const char* who)
+    {
+        if (m.type() != CV_8U)
+        {
+            // same diagnostic as find_chessboard_corners.cc:468-473
+            fprintf(stderr, "%s:%d in %s(): I can only handle CV_8U arrays currently. Sorry.\n", __FILE__, __LINE__, who);
+            return false;
+        }
+        v->rows = m.rows; v->cols = m.cols; v->step = m.step; v->data = m.data;
+        return true;
+    }
+    inline bool find_chessboard_corners_from_image_array(std::vector<PointInt>* points_scaled_out, const cv::Mat& image_input,
+                                                         int image_pyramid_level, bool debug = false,
+                                                         const char* debug_image_filename = NULL)
+    {
+        ImageView v;
+        if (!mat_to_view(&v, image_input, __func__)) return points_scaled_out->size() > 0;
+        return find_chessboard_corners_from_image_array(points_scaled_out, v, image_pyramid_level, debug, debug_image_filename);
+    }
+    inline int refine_chessboard_corners_from_image_array(std::vector<PointDouble>* points, signed char* level,
+                                                          const cv::Mat& image_input, int image_pyramid_level,
+                                                          bool debug = false, const char* debug_image_filename = NULL)
+    {
+        ImageView v;
+        if (!mat_to_view(&v, image_input, __func__)) return 0;
+        return refine_chessboard_corners_from_image_array(points, level, v, image_pyramid_level, debug, debug_image_filename);
+    }
+#endif
+}
