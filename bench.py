@@ -188,8 +188,8 @@ def run_ours(a):
 
     W, H = a.width, a.height
     # contiguous shard of the batch for this rank: frame i -> rank floor(i*world/frames)
-    lo = (a.frames * rank) // world
-    hi = (a.frames * (rank + 1)) // world
+    from mrgingham_b200.sharding import shard_range
+    lo, hi = shard_range(a.frames, rank, world)
     nloc = hi - lo
 
     # synthetic data: K distinct frames, tiled; frame i of the batch is base[i % K]
