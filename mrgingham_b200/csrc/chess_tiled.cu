@@ -24,9 +24,11 @@
 //   * each thread walks down its column keeping the unpacked ring samples of the last 11 rows in
 //     registers (rows y-5..y+5 are needed per output row, but only row y+5 is new), the row loop
 //     is unrolled x11 so the window is addressed statically;
-//   * exact early-outs: response = sum - diff - |mean - local_mean| <= sum - diff <= sum, so a
-//     warp first forms only `sum` (always), then `diff` if some lane has sum > 15, then the rest if
-//     some lane has sum - diff > 15. Whenever a response can exceed 15 it is computed exactly.
+//   * exact early-out: response = sum - diff - |mean - local_mean| <= sum - diff, so the hot loop
+//     forms only `sum` and `diff` (branch-free) and flags the rows where some lane has
+//     sum - diff > 15 (~1 % of warp-rows on board frames); after each 11-row block the flagged rows
+//     are recomputed exactly from the staged bytes by an out-of-line scalar routine that appends
+//     the candidates. Whenever a response can exceed 15 it is computed exactly.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
@@ -260,6 +262,7 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
 #pragma unroll
     for (int j = 0; j < kStageRows; j++) { Um2[j] = U0[j] = Up2[j] = U4m[j] = U4p[j] = U5m[j] = U5p[j] = 0; }
 
+#pragma unroll 1
     for (int it = 0; it < nit; it++)
     {
         const int s = it % kStages;
@@ -279,7 +282,7 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
         }
         const uint8_t* stage = ring + s * kStageBytes + lane_off;
         const int ybase = rbase + it * kStageRows - 5;   // output row of step 0 (its +5 row is staged row 0)
-        uint32_t pending = 0;                            // warp-uniform: steps whose row may hold candidates
+        uint32_t pending = 0;                            // steps whose row may hold candidates (per lane until the block ends)
 
 #pragma unroll
         for (int j = 0; j < kStageRows; j++)
@@ -304,19 +307,21 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
                 const uint32_t w0 = h2sub(p0, p4), w1 = h2sub(p1, p5), w2 = h2sub(p2, p6), w3 = h2sub(p3, p7);
                 const uint32_t s01 = h2absadd(w0, w1), s23 = h2absadd(w2, w3);
                 const uint32_t sumr = h2absadd(s01, s23);
-                if (__any_sync(kFull, (sumr & 0xFFF0FFF0u) != 0))
-                {
-                    // diff_response = sum_k |s_k - s_k+8|  (byte abs-diff on the zero-extended lanes)
-                    const uint32_t diff = (__vabsdiffu4(a0, b0) + __vabsdiffu4(a1, b1)) + (__vabsdiffu4(a2, b2) + __vabsdiffu4(a3, b3)) +
-                                          (__vabsdiffu4(a4, b4) + __vabsdiffu4(a5, b5)) + (__vabsdiffu4(a6, b6) + __vabsdiffu4(a7, b7));
-                    // lanes of (sumr - diff + 2048 + 0x77F0) reach 0x8000 iff sumr - diff >= 16
-                    const uint32_t t = sumr - diff + 0x7FF07FF0u;
-                    if (__any_sync(kFull, (t & 0x80008000u) != 0)) pending |= 1u << j;   // settled after the block
-                }
+                // diff_response = sum_k |s_k - s_k+8|  (byte abs-diff on the zero-extended lanes).
+                // Branch-free on purpose: a per-row early-out on `sumr` alone fired on ~40 % of the
+                // warp-rows of board frames and its vote + branch cost more than it saved.
+                const uint32_t diff = (__vabsdiffu4(a0, b0) + __vabsdiffu4(a1, b1)) + (__vabsdiffu4(a2, b2) + __vabsdiffu4(a3, b3)) +
+                                      (__vabsdiffu4(a4, b4) + __vabsdiffu4(a5, b5)) + (__vabsdiffu4(a6, b6) + __vabsdiffu4(a7, b7));
+                // lanes of (sumr - diff + 2048 + 0x77F0) reach 0x8000 iff sumr - diff >= 16, and
+                // response = sumr - diff - |mean - local_mean| <= sumr - diff: only such rows can
+                // hold a candidate; they are settled exactly after the block.
+                const uint32_t t = sumr - diff + 0x7FF07FF0u;
+                if (t & 0x80008000u) pending |= 1u << j;
             }
             Um2[j] = n.m2; U0[j] = n.c0; Up2[j] = n.p2; U4m[j] = n.m4; U4p[j] = n.p4; U5m[j] = n.m5; U5p[j] = n.p5;
         }
 
+        pending = __reduce_or_sync(kFull, pending);
         while (pending)
         {
             const int j = __ffs(pending) - 1;
