@@ -310,7 +310,10 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
                 // diff_response = sum_k |s_k - s_k+8|  (byte abs-diff on the zero-extended lanes).
                 // Branch-free on purpose: a per-row early-out on `sumr` alone fired on ~40 % of the
                 // warp-rows of board frames and its vote + branch cost more than it saved.
-                const uint32_t diff = (__vabsdiffu4(a0, b0) + __vabsdiffu4(a1, b1)) + (__vabsdiffu4(a2, b2) + __vabsdiffu4(a3, b3)) +
+                // (three of the eight terms go through half2 instead of VABSDIFF4: the ALU pipe is
+                // the busier one -- PRMT, VABSDIFF4, IADD3 -- so this evens out the two issue pipes)
+                const uint32_t diff_h = h2absadd(h2absadd(h2sub(a0, b0), h2sub(a1, b1)), h2sub(a2, b2));
+                const uint32_t diff = diff_h + __vabsdiffu4(a3, b3) +
                                       (__vabsdiffu4(a4, b4) + __vabsdiffu4(a5, b5)) + (__vabsdiffu4(a6, b6) + __vabsdiffu4(a7, b7));
                 // lanes of (sumr - diff + 2048 + 0x77F0) reach 0x8000 iff sumr - diff >= 16, and
                 // response = sumr - diff - |mean - local_mean| <= sumr - diff: only such rows can
