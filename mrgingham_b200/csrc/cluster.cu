@@ -114,6 +114,57 @@ __device__ void grow_component(Component& c, cand_t* cand, const uint32_t* table
     }
 }
 
+// The same traversal as grow_component(), for a region that has been collected into a thread-local
+// graph: node i has raster key lkey[i] (y<<16|x), live response lr[i] (0 once visited) and the local
+// indices of its -y,+y,-x,+x neighbours in nb[i][0..3] (-1 = no candidate there). No hash lookups.
+constexpr int kRegionMax = 48;
+struct LocalRegion
+{
+    uint32_t lkey[kRegionMax];
+    uint16_t lr[kRegionMax];
+    int8_t   nb[kRegionMax][4];
+    int8_t   dfs_parent[kRegionMax];
+    uint8_t  dfs_dir[kRegionMax];
+};
+
+__device__ void grow_component_local(Component& c, LocalRegion& g, int seed, int w, int h)
+{
+    c.swx = c.swy = c.sw = 0; c.n = 0; c.peak = 0; c.peak_x = c.peak_y = 0; c.poisoned = false;
+    int cur = seed, parent = -1;
+    for (;;)
+    {
+        const int r = g.lr[cur];
+        const bool member = r != 0 && r > (c.peak >> 4);
+        g.lr[cur] = 0;
+        if (member)
+        {
+            const int x = (int)(g.lkey[cur] & 0xFFFF), y = (int)(g.lkey[cur] >> 16);
+            if (r > c.peak) { c.peak = r; c.peak_x = x; c.peak_y = y; }
+            c.swx += (unsigned long long)(r * x);
+            c.swy += (unsigned long long)(r * y);
+            c.sw  += (unsigned long long)r;
+            c.n++;
+            if (x + 1 >= w - kMargin || x - 1 < kMargin || y + 1 >= h - kMargin || y - 1 < kMargin)
+                c.poisoned = true;
+            g.dfs_parent[cur] = (int8_t)parent; g.dfs_dir[cur] = 0;
+        }
+        else
+            cur = parent;
+        bool found = false;
+        while (cur >= 0)
+        {
+            const int d = g.dfs_dir[cur];
+            if (d == 4) { cur = g.dfs_parent[cur]; continue; }
+            g.dfs_dir[cur] = (uint8_t)(d + 1);
+            const int q = g.nb[cur][d];
+            if (q < 0 || g.lr[q] == 0) continue;
+            parent = cur; cur = q; found = true;
+            break;
+        }
+        if (!found) break;
+    }
+}
+
 // 21x21 variance gate around (x,y) of the level image, one warp (find_chessboard_corners.cc:50-88)
 __device__ bool variance_gate_warp(const uint8_t* img, int pitch, int w, int h, int x, int y, int lane)
 {
@@ -280,43 +331,69 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         }
         __syncthreads();
         const int nstart = s_nstart;
-        constexpr int kRegionMax = 64;
         for (int k = tid; k < nstart && !sequential; k += kClusterThreads)
         {
-            const int i = starters[k];
-            const uint32_t key = cand_key(fw.cand[i]);
-            int members[kRegionMax], count = 1;
-            uint32_t mkeys[kRegionMax];
-            members[0] = i; mkeys[0] = key;
+            const int i0 = starters[k];
+            const uint32_t key = cand_key(fw.cand[i0]);
+            LocalRegion g;
+            int gidx[kRegionMax];     // local index -> candidate index
+            int count = 1;
+            gidx[0] = i0; g.lkey[0] = key;
             bool first = true;
             for (int head = 0; head < count && first && !sequential; head++)
             {
-                const uint32_t mk = mkeys[head];
+                const uint32_t mk = g.lkey[head];
                 const uint32_t nk[4] = { mk - 0x10000u, mk + 0x10000u, mk - 1u, mk + 1u };
 #pragma unroll
                 for (int d = 0; d < 4; d++)
                 {
-                    if (nk[d] < key) { if (table_lookup(fw.cand, fw.table, fw.bits, nk[d]) >= 0) first = false; continue; }
-                    bool seen = false;
-                    for (int e = 0; e < count; e++) seen |= mkeys[e] == nk[d];
-                    if (seen) continue;
-                    const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
-                    if (q < 0) continue;
-                    if (count == kRegionMax) { sequential = true; break; }
-                    members[count] = q; mkeys[count] = nk[d]; count++;
+                    g.nb[head][d] = -1;
+                    if (!first || sequential) continue;
+                    // already collected? (several starters of one region flood it concurrently, so
+                    // the "seen" state has to be private: scan the short local list)
+                    int li = -1;
+                    for (int e = 0; e < count; e++) if (g.lkey[e] == nk[d]) li = e;
+                    if (li < 0)
+                    {
+                        const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
+                        if (q < 0) continue;
+                        if (nk[d] < key) { first = false; continue; }     // someone precedes this starter
+                        if (count == kRegionMax) { sequential = true; continue; }
+                        li = count++; gidx[li] = q; g.lkey[li] = nk[d];
+                    }
+                    g.nb[head][d] = (int8_t)li;
                 }
             }
             if (sequential) break;
-            if (!first) continue;
-            // raster order (insertion sort on the keys; regions are a dozen pixels)
-            for (int a = 1; a < count; a++)
+            if (!first) continue;     // not this region's first pixel: its owner does the work
+            for (int a = 0; a < count; a++) g.lr[a] = (uint16_t)cand_r(fw.cand[gidx[a]]);
+            // seeds in raster order (insertion sort of the local indices by key)
+            int8_t order[kRegionMax];
+            for (int a = 0; a < count; a++)
             {
-                const int m = members[a]; const uint32_t mk = mkeys[a];
                 int b = a - 1;
-                while (b >= 0 && mkeys[b] > mk) { members[b + 1] = members[b]; mkeys[b + 1] = mkeys[b]; b--; }
-                members[b + 1] = m; mkeys[b + 1] = mk;
+                while (b >= 0 && g.lkey[order[b]] > g.lkey[a]) { order[b + 1] = order[b]; b--; }
+                order[b + 1] = (int8_t)a;
             }
-            for (int a = 0; a < count; a++) try_seed(members[a]);
+            for (int a = 0; a < count; a++)
+            {
+                const int sd = order[a];
+                if (g.lr[sd] == 0) continue;
+                const int x = (int)(g.lkey[sd] & 0xFFFF), y = (int)(g.lkey[sd] >> 16);
+                if (x < kMargin + 1 || x >= w - kMargin - 1 || y < kMargin + 1 || y >= h - kMargin - 1) continue;
+                Component c;
+                grow_component_local(c, g, sd, w, h);
+                if (c.poisoned || c.n < kComponentMinN || c.peak <= kPeakMin) continue;
+                const int slot = atomicAdd(&s_nrec, 1);
+                if (slot < record_cap)
+                {
+                    ComponentRecord r;
+                    r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
+                    r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x;
+                    r.tag = (int32_t)g.lkey[sd];
+                    rec[slot] = r;
+                }
+            }
         }
         // a region too large for one thread's scratch: redo the whole frame the sequential way
         sequential = __syncthreads_or(sequential) != 0;
