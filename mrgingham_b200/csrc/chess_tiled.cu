@@ -51,7 +51,7 @@ constexpr int kLookahead  = 2;                   // stages requested ahead of th
                                                  // deeper than that so the warp that issues never has to wait
                                                  // for a slower warp to hand a stage back.
 constexpr int kStageBytes = 3200;                // 11*288 = 3168 rounded up to 128
-constexpr int kTileThreads = 128;
+constexpr int kTileThreads = 64;                // 2 warps x 32 lanes x 4 pixels = the 256-pixel strip
 constexpr uint32_t kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
@@ -104,39 +104,30 @@ __device__ __forceinline__ uint32_t h2absadd(uint32_t a, uint32_t b)   // |a| + 
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-// The seven column offsets a pixel pair needs from one staged row, as [b0,0,b1,0] lanes.
-struct RowSamples { uint32_t m5, m4, m2, c0, p2, p4, p5; };
+// The ten pixel pairs a thread needs from one staged row, as [b0,0,b1,0] lanes. A thread owns the
+// four pixels X..X+3 of one staged 32-bit word: pair "0" = (X, X+1), pair "2" = (X+2, X+3).
+// q_o is the pair (X+o, X+o+1). Pair 0 samples the ring at column offsets {-5,-4,-2,0,+2,+4,+5}
+// -> q_-5, q_-4, q_-2, q_0, q_2, q_4, q_5; pair 2 at the same offsets from X+2
+// -> q_-3, q_-2, q_0, q_2, q_4, q_6, q_7: four of the fourteen are shared.
+struct RowPairs { uint32_t m5, m4, m3, m2, c0, p2, p4, p5, p6, p7; };
 
-// CLS = 0: pair at x = X (X = 0 mod 4); CLS = 2: pair at x = X+2. `row` points at the staged word
-// holding bytes X-8..X-5 of this thread.
-template<int CLS>
-__device__ __forceinline__ RowSamples unpack_row(const uint8_t* row)
+// `row` points at the staged word holding bytes X-8..X-5 of this thread.
+__device__ __forceinline__ RowPairs unpack_row(const uint8_t* row)
 {
-    RowSamples s;
+    RowPairs q;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(row);
-    if (CLS == 0)
-    {
-        const uint32_t A = wp[0], B = wp[1], C = wp[2], D = wp[3];     // X-8, X-4, X, X+4
-        s.m5 = __byte_perm(__byte_perm(A, B, 0x0043), 0, 0x4140);      // X-5 | X-4 straddles two words
-        s.m4 = __byte_perm(B, 0, 0x4140);
-        s.m2 = __byte_perm(B, 0, 0x4342);
-        s.c0 = __byte_perm(C, 0, 0x4140);
-        s.p2 = __byte_perm(C, 0, 0x4342);
-        s.p4 = __byte_perm(D, 0, 0x4140);
-        s.p5 = __byte_perm(D, 0, 0x4241);
-    }
-    else
-    {
-        const uint32_t B = wp[1], C = wp[2], D = wp[3], E = wp[4];     // X-4, X, X+4, X+8
-        s.m5 = __byte_perm(B, 0, 0x4241);                              // X-3 | X-2
-        s.m4 = __byte_perm(B, 0, 0x4342);
-        s.m2 = __byte_perm(C, 0, 0x4140);
-        s.c0 = __byte_perm(C, 0, 0x4342);
-        s.p2 = __byte_perm(D, 0, 0x4140);
-        s.p4 = __byte_perm(D, 0, 0x4342);
-        s.p5 = __byte_perm(__byte_perm(D, E, 0x0043), 0, 0x4140);      // X+7 | X+8 straddles two words
-    }
-    return s;
+    const uint32_t A = wp[0], B = wp[1], C = wp[2], D = wp[3], E = wp[4];   // X-8, X-4, X, X+4, X+8
+    q.m5 = __byte_perm(__byte_perm(A, B, 0x0043), 0, 0x4140);              // X-5 | X-4 straddles two words
+    q.m4 = __byte_perm(B, 0, 0x4140);
+    q.m3 = __byte_perm(B, 0, 0x4241);
+    q.m2 = __byte_perm(B, 0, 0x4342);
+    q.c0 = __byte_perm(C, 0, 0x4140);
+    q.p2 = __byte_perm(C, 0, 0x4342);
+    q.p4 = __byte_perm(D, 0, 0x4140);
+    q.p5 = __byte_perm(D, 0, 0x4241);
+    q.p6 = __byte_perm(D, 0, 0x4342);
+    q.p7 = __byte_perm(__byte_perm(D, E, 0x0043), 0, 0x4140);              // X+7 | X+8 straddles two words
+    return q;
 }
 
 // Rare path (entered warp-uniformly, after the 11-row block that flagged it): some pixel of this
@@ -168,28 +159,26 @@ __device__ __noinline__ void emit_row(const uint8_t* cur_stage, const uint8_t* p
         const int r = j - behind[k];
         rows[k] = (r >= 0 ? cur_stage + r * kRowBytes : prev_stage + (r + kStageRows) * kRowBytes) + col;
     }
-    const int r0 = chess_from_rows(rows);
-#pragma unroll
-    for (int k = 0; k < 7; k++) rows[k] += 1;
-    const int r1 = chess_from_rows(rows);
-    const bool hit0 = r0 > kRespMin && x     >= kMargin && x     < w - kMargin;
-    const bool hit1 = r1 > kRespMin && x + 1 >= kMargin && x + 1 < w - kMargin;
-    const uint32_t b0 = __ballot_sync(kFull, hit0), b1 = __ballot_sync(kFull, hit1);
-    if ((b0 | b1) == 0) return;
     const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(count, (uint32_t)(__popc(b0) + __popc(b1)));
-    base = __shfl_sync(kFull, base, 0);
     const uint32_t below = (1u << lane) - 1;
-    if (hit0)
+    // the thread's four pixels x .. x+3, one ballot each
+#pragma unroll 1
+    for (int i = 0; i < 4; i++)
     {
-        const uint32_t i = base + __popc(b0 & below);
-        if (i < (uint32_t)cap) out[i] = cand_pack(x, y, r0);
-    }
-    if (hit1)
-    {
-        const uint32_t i = base + __popc(b0) + __popc(b1 & below);
-        if (i < (uint32_t)cap) out[i] = cand_pack(x + 1, y, r1);
+        const int r = chess_from_rows(rows);
+#pragma unroll
+        for (int k = 0; k < 7; k++) rows[k] += 1;
+        const bool hit = r > kRespMin && x + i >= kMargin && x + i < w - kMargin;
+        const uint32_t b = __ballot_sync(kFull, hit);
+        if (b == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(b));
+        base = __shfl_sync(kFull, base, 0);
+        if (hit)
+        {
+            const uint32_t idx = base + __popc(b & below);
+            if (idx < (uint32_t)cap) out[idx] = cand_pack(x + i, y, r);
+        }
     }
 }
 
@@ -200,12 +189,31 @@ struct TileParams
     int lookahead;                  // stages kept in flight ahead of the consumers (<= kStages-2)
 };
 
-template<int CLS, bool USE_TMA>
+// sum_i |p_i - p_i+4| and sum_k |a_k - b_k| for one pixel pair; returns the word whose lanes reach
+// 0x8000 iff sum - diff >= 16 (a necessary condition for response > 15)
+__device__ __forceinline__ uint32_t pair_test(uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2,
+                                              uint32_t a3, uint32_t b3, uint32_t a4, uint32_t b4, uint32_t a5, uint32_t b5,
+                                              uint32_t a6, uint32_t b6, uint32_t a7, uint32_t b7)
+{
+    const uint32_t p0 = a0 + b0, p1 = a1 + b1, p2 = a2 + b2, p3 = a3 + b3;
+    const uint32_t p4 = a4 + b4, p5 = a5 + b5, p6 = a6 + b6, p7 = a7 + b7;
+    // sum_response = sum_i |p_i - p_i+4|   (half2 lanes, exact: |values| <= 2040)
+    const uint32_t sumr = h2absadd(h2absadd(h2sub(p0, p4), h2sub(p1, p5)), h2absadd(h2sub(p2, p6), h2sub(p3, p7)));
+    // diff_response = sum_k |a_k - b_k|: three terms through half2, five through VABSDIFF4, which
+    // evens out the ALU pipe (PRMT, VABSDIFF4, IADD3) and the FMA pipe (IMAD.IADD, HADD2/HFMA2)
+    const uint32_t diff_h = h2absadd(h2absadd(h2sub(a0, b0), h2sub(a1, b1)), h2sub(a2, b2));
+    const uint32_t diff = diff_h + __vabsdiffu4(a3, b3) +
+                          (__vabsdiffu4(a4, b4) + __vabsdiffu4(a5, b5)) + (__vabsdiffu4(a6, b6) + __vabsdiffu4(a7, b7));
+    // lanes of (sumr - diff + 2048 + 0x77F0) reach 0x8000 iff sumr - diff >= 16
+    return sumr - diff + 0x7FF07FF0u;
+}
+
+template<bool USE_TMA>
 __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameSet& fs, const TileParams& tp,
                                            uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar, int* next_issue,
                                            cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
 {
-    const int tid = threadIdx.x, lane = tid & 31, span = tid >> 6;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int item = blockIdx.x;
     const int strip = item % tp.nstrips;
     const int seg   = (item / tp.nstrips) % tp.nsegs;
@@ -219,9 +227,8 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
     const int rbase = ys - 5;
     const int nit = (ye - ys + 10 + kStageRows - 1) / kStageRows;
 
-    const int X = xs + span * 128 + 4 * lane;            // this thread's word-aligned column
-    const int x = X + CLS;                               // its pixel pair is (x, x+1)
-    const int lane_off = span * 128 + 4 * lane + (kHalo - 8);   // byte offset of column X-8 in a staged row
+    const int x = xs + 4 * tid;                          // this thread's pixels are x .. x+3 (one staged word)
+    const int lane_off = 4 * tid + (kHalo - 8);          // byte offset of column x-8 in a staged row
     cand_t*   out   = cand + (size_t)f * tp.cap;
     uint32_t* count = counts + f;
 
@@ -235,7 +242,7 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
     };
     auto load_stage_cooperative = [&](int it)
     {
-        // no-TMA loader: all 128 threads copy the 10 x 272 bytes with bounds checks (zero fill)
+        // no-TMA loader: all threads copy the 11 x 288 bytes with bounds checks (zero fill)
         const int s = it % kStages;
         const uint8_t* img = fs.base + (size_t)f * fs.frame_stride;
         for (int i = tid; i < kStageRows * kRowBytes; i += kTileThreads)
@@ -256,11 +263,14 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
     // Whichever warp reaches an iteration first requests the stage `lookahead` iterations ahead
     // (claimed through *next_issue), so no warp ever waits on a slower warp's producer duty.
 
-    uint32_t Um2[kStageRows], U0[kStageRows], Up2[kStageRows];   // offsets -2, 0, +2 (needed at dy = +5 and -5)
-    uint32_t U4m[kStageRows], U4p[kStageRows];                   // offsets -4, +4   (dy = +4 and -4)
-    uint32_t U5m[kStageRows], U5p[kStageRows];                   // offsets -5, +5   (dy = +2, 0, -2)
+    // Register window: pair q_o of the last 11 staged rows, for the offsets that are needed again
+    // on later output rows. Ring row dy = +-5 uses q_{-2,0,2} (pair 0) / q_{0,2,4} (pair 2);
+    // dy = +-4 uses q_{-4,4} / q_{-2,6}; dy = 0,+-2 uses q_{-5,5} / q_{-3,7}.
+    uint32_t Wm5[kStageRows], Wm4[kStageRows], Wm3[kStageRows], Wm2[kStageRows], W0[kStageRows];
+    uint32_t Wp2[kStageRows], Wp4[kStageRows], Wp5[kStageRows], Wp6[kStageRows], Wp7[kStageRows];
 #pragma unroll
-    for (int j = 0; j < kStageRows; j++) { Um2[j] = U0[j] = Up2[j] = U4m[j] = U4p[j] = U5m[j] = U5p[j] = 0; }
+    for (int j = 0; j < kStageRows; j++)
+        Wm5[j] = Wm4[j] = Wm3[j] = Wm2[j] = W0[j] = Wp2[j] = Wp4[j] = Wp5[j] = Wp6[j] = Wp7[j] = 0;
 
 #pragma unroll 1
     for (int it = 0; it < nit; it++)
@@ -287,41 +297,24 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
 #pragma unroll
         for (int j = 0; j < kStageRows; j++)
         {
-            const RowSamples n = unpack_row<CLS>(stage + j * kRowBytes);
+            const RowPairs n = unpack_row(stage + j * kRowBytes);
             // Rows outside [ys,ye) (window priming, segment tail) are computed like any other and
             // dropped below: cheaper than a test on the always-executed path.
-            {
-                // opposite ring samples (s_k, s_k+8), k = 0..7
-                // the window slot of row R-k is (j + 11 - k) % 11; the new row R goes to slot j
-                const uint32_t a0 = Up2[(j + 1) % 11],   b0 = n.m2;                    // (+2,-5) (-2,+5)
-                const uint32_t a1 = U0[(j + 1) % 11],    b1 = n.c0;                    // ( 0,-5) ( 0,+5)
-                const uint32_t a2 = Um2[(j + 1) % 11],   b2 = n.p2;                    // (-2,-5) (+2,+5)
-                const uint32_t a3 = U4m[(j + 2) % 11],   b3 = U4p[(j + 10) % 11];      // (-4,-4) (+4,+4)
-                const uint32_t a4 = U5m[(j + 4) % 11],   b4 = U5p[(j + 8) % 11];       // (-5,-2) (+5,+2)
-                const uint32_t a5 = U5m[(j + 6) % 11],   b5 = U5p[(j + 6) % 11];       // (-5, 0) (+5, 0)
-                const uint32_t a6 = U5m[(j + 8) % 11],   b6 = U5p[(j + 4) % 11];       // (-5,+2) (+5,-2)
-                const uint32_t a7 = U4m[(j + 10) % 11],  b7 = U4p[(j + 2) % 11];       // (-4,+4) (+4,-4)
-                const uint32_t p0 = a0 + b0, p1 = a1 + b1, p2 = a2 + b2, p3 = a3 + b3;
-                const uint32_t p4 = a4 + b4, p5 = a5 + b5, p6 = a6 + b6, p7 = a7 + b7;
-                // sum_response = sum_i |p_i - p_i+4|   (half2 lanes, exact: |values| <= 2040)
-                const uint32_t w0 = h2sub(p0, p4), w1 = h2sub(p1, p5), w2 = h2sub(p2, p6), w3 = h2sub(p3, p7);
-                const uint32_t s01 = h2absadd(w0, w1), s23 = h2absadd(w2, w3);
-                const uint32_t sumr = h2absadd(s01, s23);
-                // diff_response = sum_k |s_k - s_k+8|  (byte abs-diff on the zero-extended lanes).
-                // Branch-free on purpose: a per-row early-out on `sumr` alone fired on ~40 % of the
-                // warp-rows of board frames and its vote + branch cost more than it saved.
-                // (three of the eight terms go through half2 instead of VABSDIFF4: the ALU pipe is
-                // the busier one -- PRMT, VABSDIFF4, IADD3 -- so this evens out the two issue pipes)
-                const uint32_t diff_h = h2absadd(h2absadd(h2sub(a0, b0), h2sub(a1, b1)), h2sub(a2, b2));
-                const uint32_t diff = diff_h + __vabsdiffu4(a3, b3) +
-                                      (__vabsdiffu4(a4, b4) + __vabsdiffu4(a5, b5)) + (__vabsdiffu4(a6, b6) + __vabsdiffu4(a7, b7));
-                // lanes of (sumr - diff + 2048 + 0x77F0) reach 0x8000 iff sumr - diff >= 16, and
-                // response = sumr - diff - |mean - local_mean| <= sumr - diff: only such rows can
-                // hold a candidate; they are settled exactly after the block.
-                const uint32_t t = sumr - diff + 0x7FF07FF0u;
-                if (t & 0x80008000u) pending |= 1u << j;
-            }
-            Um2[j] = n.m2; U0[j] = n.c0; Up2[j] = n.p2; U4m[j] = n.m4; U4p[j] = n.p4; U5m[j] = n.m5; U5p[j] = n.p5;
+            // The window slot of row R-k is (j + 11 - k) % 11; the new row R goes to slot j.
+            constexpr int N = kStageRows;
+            const int r10 = (j + 1) % N, r9 = (j + 2) % N, r7 = (j + 4) % N, r5 = (j + 6) % N, r3 = (j + 8) % N, r1 = (j + 10) % N;
+            // opposite ring samples (s_k, s_k+8), k = 0..7:
+            //   (+2,-5)(-2,+5)  (0,-5)(0,+5)  (-2,-5)(+2,+5)  (-4,-4)(+4,+4)
+            //   (-5,-2)(+5,+2)  (-5,0)(+5,0)  (-5,+2)(+5,-2)  (-4,+4)(+4,-4)
+            const uint32_t t0 = pair_test(Wp2[r10], n.m2,  W0[r10],  n.c0,  Wm2[r10], n.p2,  Wm4[r9],  Wp4[r1],
+                                          Wm5[r7],  Wp5[r3], Wm5[r5], Wp5[r5], Wm5[r3], Wp5[r7], Wm4[r1], Wp4[r9]);
+            const uint32_t t2 = pair_test(Wp4[r10], n.c0,  Wp2[r10], n.p2,  W0[r10],  n.p4,  Wm2[r9],  Wp6[r1],
+                                          Wm3[r7],  Wp7[r3], Wm3[r5], Wp7[r5], Wm3[r3], Wp7[r7], Wm2[r1], Wp6[r9]);
+            // response <= sum - diff: only rows where some lane reaches the threshold can hold a
+            // candidate; they are settled exactly after the block.
+            if ((t0 | t2) & 0x80008000u) pending |= 1u << j;
+            Wm5[j] = n.m5; Wm4[j] = n.m4; Wm3[j] = n.m3; Wm2[j] = n.m2; W0[j] = n.c0;
+            Wp2[j] = n.p2; Wp4[j] = n.p4; Wp5[j] = n.p5; Wp6[j] = n.p6; Wp7[j] = n.p7;
         }
 
         pending = __reduce_or_sync(kFull, pending);
@@ -362,9 +355,7 @@ chess_tiled_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, TilePa
         }
         __syncthreads();
     }
-    // warps alternate between the two pixel-pair alignments of the same 128-pixel span
-    if (((threadIdx.x >> 5) & 1) == 0) strip_walk<0, USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, &next_issue, cand, counts);
-    else                               strip_walk<2, USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, &next_issue, cand, counts);
+    strip_walk<USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, &next_issue, cand, counts);
 }
 
 // ------------------------------------------------------------------------------------------------
