@@ -338,7 +338,7 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
 }
 
 template<bool USE_TMA>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 8)
 chess_tiled_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, TileParams tp,
                    cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
 {

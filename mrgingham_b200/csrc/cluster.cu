@@ -319,14 +319,18 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         // hash table and gives up as soon as it meets a pixel that precedes it in raster order, so
         // exactly one starter per region -- its first pixel -- survives with the full member list.
         uint16_t* starters = (uint16_t*)(smem + (sizeof(cand_t) + 3*sizeof(uint32_t)) * kClusterSmemCands);
+        // pointers derived straight from the shared array, so these accesses compile to LDS/STS
+        // (the FrameWork pointers are generic: they may also point at global scratch)
+        const cand_t*   scand  = (const cand_t*)smem;
+        const uint32_t* stable = (const uint32_t*)(smem + sizeof(cand_t) * kClusterSmemCands);
         const int n = fw.n;
         if (tid == 0) s_nstart = 0;
         __syncthreads();
         for (int i = tid; i < n; i += kClusterThreads)
         {
-            const uint32_t key = cand_key(fw.cand[i]);
-            if (table_lookup(fw.cand, fw.table, fw.bits, key - 0x10000u) < 0 &&
-                table_lookup(fw.cand, fw.table, fw.bits, key - 1u) < 0)
+            const uint32_t key = cand_key(scand[i]);
+            if (table_lookup(scand, stable, fw.bits, key - 0x10000u) < 0 &&
+                table_lookup(scand, stable, fw.bits, key - 1u) < 0)
                 starters[atomicAdd(&s_nstart, 1)] = (uint16_t)i;
         }
         __syncthreads();
@@ -334,7 +338,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         for (int k = tid; k < nstart && !sequential; k += kClusterThreads)
         {
             const int i0 = starters[k];
-            const uint32_t key = cand_key(fw.cand[i0]);
+            const uint32_t key = cand_key(scand[i0]);
             LocalRegion g;
             int gidx[kRegionMax];     // local index -> candidate index
             int count = 1;
@@ -355,7 +359,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
                     for (int e = 0; e < count; e++) if (g.lkey[e] == nk[d]) li = e;
                     if (li < 0)
                     {
-                        const int q = table_lookup(fw.cand, fw.table, fw.bits, nk[d]);
+                        const int q = table_lookup(scand, stable, fw.bits, nk[d]);
                         if (q < 0) continue;
                         if (nk[d] < key) { first = false; continue; }     // someone precedes this starter
                         if (count == kRegionMax) { sequential = true; continue; }
@@ -366,7 +370,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
             }
             if (sequential) break;
             if (!first) continue;     // not this region's first pixel: its owner does the work
-            for (int a = 0; a < count; a++) g.lr[a] = (uint16_t)cand_r(fw.cand[gidx[a]]);
+            for (int a = 0; a < count; a++) g.lr[a] = (uint16_t)cand_r(scand[gidx[a]]);
             // seeds in raster order (insertion sort of the local indices by key)
             int8_t order[kRegionMax];
             for (int a = 0; a < count; a++)

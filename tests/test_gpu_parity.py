@@ -255,3 +255,51 @@ def test_empty_batch_and_tiny_frames(api, oracle):
         xy, counts = det.find_corners(frames, 0)
         _check_batch(xy, counts, frames, oracle, 0)
     det.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# loader paths of the tiled kernel, randomised sizes
+# ---------------------------------------------------------------------------------------------
+def test_device_frames_that_defeat_tma(api, oracle):
+    """unaligned base address, odd width, pitch not a multiple of 16: the tiled kernel must take its
+    cooperative loader and still match"""
+    import torch
+    det = api.Detector(max_frames=4, max_points=4096)
+    base = np.stack([synth.board_frame(648, 488, 10, seed=120 + s) for s in range(3)])
+    big = torch.zeros((3, 488, 700), dtype=torch.uint8, device="cuda")
+    big[:, :, 1:649] = torch.from_numpy(base).cuda()
+    for (x0, wv) in ((1, 640), (1, 641), (3, 645), (16, 632)):
+        view = big[:, 4:484, x0:x0 + wv]                 # pitch 700, base offset 4*700 + x0
+        frames = base[:, 4:484, x0 - 1:x0 - 1 + wv]
+        xy, counts = det.find_corners(view, 0)
+        _check_batch(xy, counts, frames, oracle, 0)
+    det.close()
+
+
+def test_random_sizes_and_levels(api, oracle):
+    rng = np.random.default_rng(2024)
+    det = api.Detector(max_frames=2, max_points=8192)
+    for it in range(24):
+        w, h = int(rng.integers(20, 700)), int(rng.integers(20, 500))
+        kind = it % 4
+        if kind == 0:
+            img = synth.board_frame(w, h, 10, seed=300 + it) if min(w, h) > 120 else synth.noise_frame(w, h, seed=300 + it)
+        elif kind == 1:
+            img = synth.blurred_noise_frame(w, h, seed=300 + it, passes=1)
+        elif kind == 2:
+            img = synth.checker_frame(w, h, period=int(rng.integers(4, 14)), seed=300 + it, noise_sigma=float(rng.uniform(0, 6)))
+        else:
+            img = synth.blob_frame(w, h, seed=300 + it)
+        level = int(rng.integers(0, 3))
+        xy, counts = det.find_corners(img[None], level)
+        _check_batch(xy, counts, img[None], oracle, level)
+    det.close()
+
+
+def test_segmented_single_frame_matches(api, oracle):
+    """a single large frame is cut into row segments so the chip is filled: seams must not show"""
+    img = synth.board_frame(2560, 1440, 14, seed=77)
+    got, want = api.find_chessboard_corners_int(img, 0), oracle.find_corners(img, 0)
+    assert np.array_equal(got, want) and len(want) == 196
+    tex = synth.blurred_noise_frame(1600, 1200, seed=78, passes=1)
+    assert np.array_equal(api.find_chessboard_corners_int(tex, 0), oracle.find_corners(tex, 0))
