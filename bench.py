@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--gridn", type=int, default=10)
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--base-frames", type=int, default=8, help="distinct synthetic frames, tiled to --frames")
-    ap.add_argument("--chunk", type=int, default=256, help="frames per kernel launch")
+    ap.add_argument("--chunk", type=int, default=512, help="frames per kernel launch")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -55,18 +55,23 @@ def workload_name(a):
 # clocks sampling (the recipe's nvidia-smi line), during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load. Started before the
+    warm-up so that the sampler is already running when the (short) timed region begins; samples
+    are attributed to the timed region by timestamp, falling back to every sample taken under load
+    (utilization >= 50 %) if the region was shorter than the sampling period."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)],
+                                          "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -77,28 +82,45 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smmax, reasons = [], [], set()
+        rows = []
         for ln in self.lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
             try:
-                sm.append(float(p[1])); smmax.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(p[1]), float(p[2]), float(p[4]), [v.lower().startswith("active") for v in p[5:9]]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if v.lower().startswith("active"):
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
+        scope = "timed region"
+        if len(inside) < 3:
+            inside = [r for r in rows if r[3] >= 50.0]
+            scope = "warm-up + timed region (samples under load)"
+        reasons = set()
+        for r in inside:
+            for name, act in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if act:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -215,6 +237,8 @@ def run_ours(a):
         det.enqueue(frames, a.level, stream=stream)
         return det.collect()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(a.warmup, 0)):
         xy, counts = step()
 
@@ -233,9 +257,8 @@ def run_ours(a):
 
     # ---- timed region: device-resident inputs
     det.set_profiling(True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1_ms = k1_n = k2_ms = k2_n = 0
     e0.record()
@@ -246,6 +269,7 @@ def run_ours(a):
         ms, n = det.last_kernel_ms(2); k2_n += n
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     det.set_profiling(False)
     elapsed_ms = e0.elapsed_time(e1)

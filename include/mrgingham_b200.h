@@ -125,6 +125,19 @@ int mrg_b200_find_corners_batch_enqueue(mrg_b200_detector* det,
 int mrg_b200_find_corners_batch_collect(mrg_b200_detector* det,
                                         int32_t* xy_out, int32_t* counts_out);
 
+/* Batched form of mrg_b200_refine_chessboard_corners(): frame i refines its own npoints points.
+     xy_inout     HOST double [nframes][npoints][2], full-resolution pixels (in/out)
+     levels       HOST int8   [nframes][npoints] (in/out)
+     nrefined_out HOST int32  [nframes]
+   Synchronous. Returns 0 or <0. */
+int mrg_b200_refine_corners_batch(mrg_b200_detector* det,
+                                  const uint8_t* images, int images_on_device,
+                                  int nframes, int rows, int cols,
+                                  size_t row_pitch, size_t frame_stride,
+                                  int image_pyramid_level,
+                                  double* xy_inout, signed char* levels, int npoints,
+                                  int32_t* nrefined_out, void* stream);
+
 /* Dense ChESS response over a batch (the batched form of section A's function).
    response: int16 [nframes][rows][cols]; elements outside the 7-pixel interior are not written. */
 int mrg_b200_chess_response_batch(mrg_b200_detector* det,

@@ -20,6 +20,7 @@ EXPORTS = (
     "mrg_b200_find_chessboard_corners", "mrg_b200_refine_chessboard_corners",
     "mrg_b200_detector_create", "mrg_b200_detector_destroy",
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
+    "mrg_b200_refine_corners_batch",
     "mrg_b200_chess_response_batch", "mrg_b200_pyramid_level",
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
     "mrg_b200_device_count",
@@ -68,6 +69,8 @@ def lib():
     L.mrg_b200_find_corners_batch_enqueue.argtypes = batch_args + [ctypes.c_void_p]
     L.mrg_b200_find_corners_batch_collect.restype = ctypes.c_int
     L.mrg_b200_find_corners_batch_collect.argtypes = [ctypes.c_void_p, _i32p, _i32p]
+    L.mrg_b200_refine_corners_batch.restype = ctypes.c_int
+    L.mrg_b200_refine_corners_batch.argtypes = batch_args + [_f64p, _i8p, ctypes.c_int, _i32p, ctypes.c_void_p]
     L.mrg_b200_chess_response_batch.restype = ctypes.c_int
     L.mrg_b200_chess_response_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
@@ -256,6 +259,21 @@ class Detector:
         """returns (xy int32 [n, max_points, 2] scaled by 1000, counts int32 [n])"""
         self.enqueue(images, level, stream)
         return self.collect()
+
+    def refine_corners(self, images, level, xy, levels, stream=None):
+        """batched refinement: xy float64 [n, npoints, 2], levels int8 [n, npoints];
+        returns (nrefined int32 [n], xy', levels')"""
+        ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
+        xy = np.ascontiguousarray(xy, dtype=np.float64).copy().reshape(n, -1, 2)
+        levels = np.ascontiguousarray(levels, dtype=np.int8).copy().reshape(n, -1)
+        npoints = levels.shape[1]
+        nref = np.zeros(n, dtype=np.int32)
+        rc = lib().mrg_b200_refine_corners_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(level),
+                                                 _ptr(xy, _f64p), _ptr(levels, _i8p), npoints, _ptr(nref, _i32p),
+                                                 ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_refine_corners_batch() failed")
+        return nref, xy, levels
 
     def chess_response(self, images):
         """dense int16 response of host images [n, rows, cols] (border elements are 0)"""

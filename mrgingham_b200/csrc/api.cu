@@ -592,6 +592,98 @@ API void mrgingham_ChESS_response_5(int16_t* response, const uint8_t* image, int
     { MSG("ChESS response failed on the GPU."); abort(); }
 }
 
+// Refinement of `n` frames (n <= max_frames, or n == 1 with big == true for a frame whose candidate
+// list overflowed the chunk scratch). xy/levels/nref are HOST arrays [n][npoints][2], [n][npoints], [n].
+static int refine_frames(mrg_b200_detector* det, cudaStream_t stream, const uint8_t* images, int on_device, int n,
+                         int rows, int cols, size_t pitch, size_t fstride, int level,
+                         double* xy, signed char* levels, int npoints, int32_t* nref, bool big)
+{
+    mrg_b200_detector::Slot& S = det->slot[0];
+    FrameSet fs;
+    if (stage_frames(det, S, images, on_device, n, rows, cols, pitch, fstride, level, stream, stream, &fs)) return -1;
+    if (det->pts.ensure(sizeof(double) * 2 * npoints * n)) return -1;
+    if (det->lvls.ensure((size_t)npoints * n)) return -1;
+    if (ensure_chunk_scratch(det, S, n)) return -1;
+    if (det->big_records.ensure(cluster_record_bytes() * (size_t)npoints * n)) return -1;
+    int cap = det->cfg.candidate_capacity;
+    cand_t* cand = (cand_t*)S.cand.p; uint32_t* table = (uint32_t*)S.table.p; uint32_t* dfs = (uint32_t*)S.dfs.p;
+    if (big)
+    {
+        cap = next_pow2((long long)fs.w * fs.h);
+        if (det->big_cand.ensure(sizeof(cand_t) * cap)) return -1;
+        if (det->big_table.ensure(sizeof(uint32_t) * 2 * cap)) return -1;
+        if (det->big_dfs.ensure(sizeof(uint32_t) * cap)) return -1;
+        cand = (cand_t*)det->big_cand.p; table = (uint32_t*)det->big_table.p; dfs = (uint32_t*)det->big_dfs.p;
+    }
+    CUDA_TRY(cudaMemcpyAsync(det->pts.p, xy, sizeof(double) * 2 * npoints * n, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(det->lvls.p, levels, (size_t)npoints * n, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t) * n, stream));
+    if (chess_sparse(det, fs, cand, (uint32_t*)S.counts.p, cap, stream)) return -1;
+    ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = det->cfg.max_points;
+    p.record_capacity = npoints; p.records = det->big_records.p;
+    {
+        Launch l(det, 1, stream);
+        CUDA_TRY(launch_cluster_refine(fs, p, cand, (uint32_t*)S.counts.p, table, dfs, (double*)det->pts.p, (signed char*)det->lvls.p,
+                                       npoints, (int32_t*)S.outcounts.p, stream));
+    }
+    std::vector<int32_t> got(n);
+    CUDA_TRY(cudaMemcpyAsync(got.data(), S.outcounts.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    bool any_overflow = false;
+    for (int i = 0; i < n; i++) any_overflow |= got[i] < 0;
+    if (!any_overflow)
+    {
+        CUDA_TRY(cudaMemcpy(xy, det->pts.p, sizeof(double) * 2 * npoints * n, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(levels, det->lvls.p, (size_t)npoints * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) nref[i] = got[i];
+        return 0;
+    }
+    if (big) { MSG("Frame still overflows at worst-case capacity; this is a bug."); return -1; }
+    // some candidate list overflowed: frames that did not are final, the others are re-run one by
+    // one on the GPU with worst-case capacity (the kernel leaves an overflowed frame's points untouched)
+    std::vector<double> hxy((size_t)2 * npoints * n); std::vector<signed char> hl((size_t)npoints * n);
+    CUDA_TRY(cudaMemcpy(hxy.data(), det->pts.p, sizeof(double) * 2 * npoints * n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hl.data(), det->lvls.p, (size_t)npoints * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++)
+    {
+        double* xi = xy + (size_t)2 * npoints * i; signed char* li = levels + (size_t)npoints * i;
+        if (got[i] >= 0)
+        {
+            memcpy(xi, hxy.data() + (size_t)2 * npoints * i, sizeof(double) * 2 * npoints);
+            memcpy(li, hl.data() + (size_t)npoints * i, npoints);
+            nref[i] = got[i];
+        }
+        else if (refine_frames(det, stream, images + (size_t)i * fstride, on_device, 1, rows, cols, pitch, pitch * rows, level,
+                               xi, li, npoints, nref + i, true)) return -1;
+    }
+    return 0;
+}
+
+API int mrg_b200_refine_corners_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                      int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                      int level, double* xy_inout, signed char* levels, int npoints,
+                                      int32_t* nrefined_out, void* stream_)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    if (level < 0 || level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); return -1; }
+    if (nframes < 0 || rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767 || row_pitch < (size_t)cols || npoints < 0)
+    { MSG("Bad batch geometry."); return -1; }
+    for (int i = 0; i < nframes; i++) nrefined_out[i] = 0;
+    if (npoints == 0 || nframes == 0) return 0;
+    CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+    const int chunk = det->cfg.max_frames;
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        if (refine_frames(det, stream, images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride, level,
+                          xy_inout + (size_t)2 * npoints * f0, levels + (size_t)npoints * f0, npoints, nrefined_out + f0, false)) return -1;
+    }
+    return 0;
+}
+
 API int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride, int level,
                                            double* xy_inout, signed char* levels, int Npoints)
 {
@@ -601,44 +693,8 @@ API int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int 
     std::lock_guard<std::mutex> g(g_default_mtx);
     mrg_b200_detector* det = default_detector();
     if (!det) return -1;
-    std::lock_guard<std::mutex> g2(det->mtx);
-    CUDA_TRY(cudaSetDevice(det->device));
-    cudaStream_t stream = det->own_stream;
-    mrg_b200_detector::Slot& S = det->slot[0];
-    if (det->pending.active) { MSG("A batch is in flight on the default detector."); return -1; }
-    FrameSet fs;
-    if (stage_frames(det, S, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, stream, stream, &fs)) return -1;
-    if (det->pts.ensure(sizeof(double) * 2 * Npoints)) return -1;
-    if (det->lvls.ensure(Npoints)) return -1;
-    if (ensure_chunk_scratch(det, S, 1)) return -1;
-    int cap = det->cfg.candidate_capacity, reccap = std::max(Npoints, 1);
-    cand_t* cand = (cand_t*)S.cand.p; uint32_t* table = (uint32_t*)S.table.p; uint32_t* dfs = (uint32_t*)S.dfs.p;
-    for (int attempt = 0; attempt < 2; attempt++)
-    {
-        if (det->big_records.ensure(cluster_record_bytes() * reccap)) return -1;
-        CUDA_TRY(cudaMemcpyAsync(det->pts.p, xy_inout, sizeof(double) * 2 * Npoints, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(det->lvls.p, levels, Npoints, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t), stream));
-        if (chess_sparse(det, fs, cand, (uint32_t*)S.counts.p, cap, stream)) return -1;
-        ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = det->cfg.max_points; p.record_capacity = reccap; p.records = det->big_records.p;
-        CUDA_TRY(launch_cluster_refine(fs, p, cand, (uint32_t*)S.counts.p, table, dfs, (double*)det->pts.p, (signed char*)det->lvls.p,
-                                       Npoints, (int32_t*)S.outcounts.p, stream));
-        int32_t nref = 0;
-        CUDA_TRY(cudaMemcpyAsync(&nref, S.outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        if (nref >= 0)
-        {
-            CUDA_TRY(cudaMemcpy(xy_inout, det->pts.p, sizeof(double) * 2 * Npoints, cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(levels, det->lvls.p, Npoints, cudaMemcpyDeviceToHost));
-            return nref;
-        }
-        // candidate list overflowed: once more with worst-case capacity
-        cap = next_pow2((long long)fs.w * fs.h);
-        if (det->big_cand.ensure(sizeof(cand_t) * cap)) return -1;
-        if (det->big_table.ensure(sizeof(uint32_t) * 2 * cap)) return -1;
-        if (det->big_dfs.ensure(sizeof(uint32_t) * cap)) return -1;
-        cand = (cand_t*)det->big_cand.p; table = (uint32_t*)det->big_table.p; dfs = (uint32_t*)det->big_dfs.p;
-    }
-    MSG("Frame still overflows at worst-case capacity; this is a bug.");
-    return -1;
+    int32_t nref = 0;
+    if (mrg_b200_refine_corners_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level,
+                                      xy_inout, levels, Npoints, &nref, nullptr)) return -1;
+    return nref;
 }

@@ -303,3 +303,32 @@ def test_segmented_single_frame_matches(api, oracle):
     assert np.array_equal(got, want) and len(want) == 196
     tex = synth.blurred_noise_frame(1600, 1200, seed=78, passes=1)
     assert np.array_equal(api.find_chessboard_corners_int(tex, 0), oracle.find_corners(tex, 0))
+
+
+def test_refine_batch_matches_oracle(api, oracle):
+    frames = np.stack([synth.board_frame(800, 600, 10, seed=130 + s) for s in range(5)] +
+                      [synth.checker_frame(800, 600, 9, seed=140)])
+    det = api.Detector(max_frames=4, max_points=8192)
+    # points found at level 2, padded to a common count with dummies that must stay untouched
+    found = [oracle.find_corners(f, 2).astype(np.float64) / 1000.0 for f in frames]
+    npts = max(len(p) for p in found) + 3
+    xy = np.full((len(frames), npts, 2), -100.0)
+    lv = np.full((len(frames), npts), 7, dtype=np.int8)
+    for i, p in enumerate(found):
+        xy[i, :len(p)] = p
+        lv[i, :len(p)] = 2
+    for level in (1, 0):
+        nref, xy2, lv2 = det.refine_corners(frames, level, xy, lv)
+        for i, f in enumerate(frames):
+            n0, x0, l0 = oracle.refine_corners(f, level, xy[i], lv[i])
+            assert nref[i] == n0 and np.array_equal(lv2[i], l0), (level, i)
+            assert np.array_equal(xy2[i].view(np.uint64), x0.view(np.uint64)), (level, i)
+        xy, lv = xy2, lv2
+    # tiny candidate capacity: every frame overflows and is re-run one by one
+    det2 = api.Detector(max_frames=8, candidate_capacity=128)
+    xy = np.stack([np.pad(p, ((0, npts - len(p)), (0, 0))) for p in found]); lv = np.full((len(frames), npts), 2, dtype=np.int8)
+    nref, xy2, lv2 = det2.refine_corners(frames, 1, xy, lv)
+    for i, f in enumerate(frames):
+        n0, x0, l0 = oracle.refine_corners(f, 1, xy[i], lv[i])
+        assert nref[i] == n0 and np.array_equal(lv2[i], l0) and np.array_equal(xy2[i].view(np.uint64), x0.view(np.uint64)), i
+    det.close(); det2.close()
