@@ -91,7 +91,7 @@ typedef struct
                                  to a power of two; 0 = default. Frames that overflow it are
                                  re-run on the GPU with a capacity of rows*cols.                 */
     int max_points;           /* per-frame output capacity (corners); 0 = default 1024           */
-    int kernel_variant;       /* 0 = default; 1 = the simple one-thread-per-pixel ChESS kernel   */
+    int kernel_variant;       /* 0 = default (cascade); 1 = simple one-thread-per-pixel; 2 = tiled  */
 } mrg_b200_detector_config;
 
 /* returns 0 and a detector, or <0 */

@@ -143,8 +143,14 @@ struct Launch
 int chess_sparse(mrg_b200_detector* det, const FrameSet& fs, cand_t* cand, uint32_t* counts, int cap, cudaStream_t stream)
 {
     Launch l(det, 0, stream);
-    if (det->cfg.kernel_variant == 1) CUDA_TRY(launch_chess_sparse_simple(fs, cand, counts, cap, stream));
-    else                              CUDA_TRY(launch_chess_sparse_tiled (fs, cand, counts, cap, stream));
+    if (det->cfg.kernel_variant == 1) { CUDA_TRY(launch_chess_sparse_simple(fs, cand, counts, cap, stream)); return 0; }
+    if (det->cfg.kernel_variant != 2)
+    {
+        bool launched = false;
+        CUDA_TRY(launch_chess_sparse_cascade(fs, cand, counts, cap, stream, &launched));
+        if (launched) return 0;
+    }
+    CUDA_TRY(launch_chess_sparse_tiled(fs, cand, counts, cap, stream));
     return 0;
 }
 

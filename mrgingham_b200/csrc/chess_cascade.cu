@@ -1,0 +1,501 @@
+// K1, cascade variant: the production ChESS + candidate-emission kernel for sm_100a.
+//
+// Replaces, fused into one pass over the uint8 frame (1 byte/pixel of HBM traffic):
+//   ChESS.c:62-105 (response), find_chessboard_corners.cc:506 (zeroed response), :527-529 (clamp),
+//   and the r > 15 seed/member test of :159-171 -- only pixels with response > 15 are written out.
+//
+// The kernel is bound by instruction issue, not by HBM, so it is organised as a cascade of EXACT
+// necessary conditions for `response > 15`, each cheaper and applied to more pixels than the next:
+//
+//   With a,b,c,d = s_i, s_i+4, s_i+8, s_i+12 (ChESS.c:93-102), term_i = |a+c-b-d| - |a-c| - |b-d|
+//   and response = sum_i term_i - |mean - local_mean| <= sum_i term_i. For every i
+//       term_i = 2*max( min(a,c) - max(b,d), min(b,d) - max(a,c) )                       (identity)
+//   hence  term_i <= 2*|p - q|  for ANY p in {a,c}, q in {b,d},                           (L1)
+//   and    term_i <= |a-b| + |c-d| - |a-c| - |b-d|  (triangle inequality on |a+c-b-d|).   (L2)
+//
+//   L1 (every pixel; 4 pixels per instruction in byte lanes): one chord |p-q| per i, chosen so
+//      that three of the eight samples are aligned 32-bit words of the staged rows and the other
+//      five come from two PRMT'd words per row. response > 15 needs sum_i |p_i-q_i| >= 8. The four
+//      VABSDIFF4 results are added as packed bytes; a lane whose sum could wrap has some chord >= 8
+//      and is caught by OR-ing the chords, so the packed test never misses. ~5 % of the pixels
+//      of a board frame (the neighbourhood of edges) pass.
+//   L2 (8-pixel row cells flagged by L1, compacted so that all 32 lanes work): all sixteen
+//      VABSDIFF4 chords/diameters in byte lanes, widened into 16-bit lanes and summed exactly;
+//      needs sum >= 16. ~0.05 % of the pixels pass.
+//   L3 (those pixels, compacted again): the exact scalar response as ChESS.c:62-105 computes it;
+//      pixels with response > 15 inside [7,w-7) x [7,h-7) are appended to the frame's candidate list.
+//
+// Whatever L1/L2 let through is only ever MORE than needed; the candidate set equals the
+// reference's on any input (tests/test_gpu_parity.py compares it with the oracle on noise, textures
+// and dense checkers, where nearly everything reaches L2).
+//
+// Data movement: a CTA of NW warps owns a (256*NW)-pixel-wide column strip of one frame segment
+// and walks down it; rows arrive through a shared-memory ring filled by TMA
+// (cp.async.bulk.tensor.3d, one (256*NW+32)-byte x 11-row box per stage), completion on mbarriers,
+// stages handed back through a second set of mbarriers. A lane owns 8 adjacent pixels (two 32-bit
+// words) and keeps the PRMT'd words of the last 11 rows in registers (row loop unrolled x11).
+// L2/L3 re-read their few cells from global memory (L2-cache hits: the strip was just streamed).
+#include <cuda.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace mrgb200
+{
+namespace
+{
+constexpr int kLanePx   = 8;                   // pixels per lane
+constexpr int kWarpPx   = 32 * kLanePx;        // 256
+constexpr int kCHalo    = 16;                  // staged bytes left/right of the strip (ring needs 8; TMA boxes start 16-aligned)
+constexpr int kBlkRows  = 11;                  // rows per TMA stage == unroll of the row loop == register window
+constexpr int kL2QCap   = 128;                 // per-warp queue of flagged cells (power of two)
+constexpr int kL3QCap   = 512;                 // per-warp queue of pixels for the exact test (power of two)
+
+template<int NW> struct Geo
+{
+    static constexpr int kStripW   = kWarpPx * NW;
+    static constexpr int kRowBytes = kStripW + 2 * kCHalo;
+    static constexpr int kStageBytes = ((kRowBytes * kBlkRows + 127) / 128) * 128;
+};
+
+struct CascadeParams
+{
+    int nstrips, nsegs, seg_rows;   // work decomposition: item = (frame, segment, strip)
+    int cap;
+    int stages, lookahead;
+};
+
+struct WarpQueues
+{
+    uint32_t l2q[kL2QCap];
+    uint32_t l3q[kL3QCap];
+    uint32_t l3_tail;
+    uint32_t pad[3];
+};
+
+// mbarrier wait as a plain C loop around try_wait, executed by whole warps: no branch hidden from
+// the compiler, so no lane is ever left diverged from its warp across the unrolled row loop
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ uint32_t vabs4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+__device__ __forceinline__ uint32_t ev(uint32_t d) { return d & 0x00FF00FFu; }                 // [d0,0,d2,0]
+__device__ __forceinline__ uint32_t od(uint32_t d) { return __byte_perm(d, 0, 0x4341); }       // [d1,0,d3,0]
+
+// exact response of the pixel at c (ChESS.c:62-105), read straight from global memory
+__device__ __forceinline__ int chess_exact(const uint8_t* __restrict__ c, int pitch)
+{
+    const int p2 = 2*pitch, p4 = 4*pitch, p5 = 5*pitch;
+    const int s0  = c[ 2 - p5], s1  = c[   - p5], s2  = c[-2 - p5], s3  = c[-4 - p4];
+    const int s4  = c[-5 - p2], s5  = c[-5     ], s6  = c[-5 + p2], s7  = c[-4 + p4];
+    const int s8  = c[-2 + p5], s9  = c[     p5], s10 = c[ 2 + p5], s11 = c[ 4 + p4];
+    const int s12 = c[ 5 + p2], s13 = c[ 5     ], s14 = c[ 5 - p2], s15 = c[ 4 - p4];
+    const int q0 = s0 + s8, q1 = s1 + s9, q2 = s2 + s10, q3 = s3 + s11;
+    const int q4 = s4 + s12, q5 = s5 + s13, q6 = s6 + s14, q7 = s7 + s15;
+    const int sum  = abs(q0 - q4) + abs(q1 - q5) + abs(q2 - q6) + abs(q3 - q7);
+    const int diff = abs(s0 - s8) + abs(s1 - s9) + abs(s2 - s10) + abs(s3 - s11) +
+                     abs(s4 - s12) + abs(s5 - s13) + abs(s6 - s14) + abs(s7 - s15);
+    const int mean = (q0 + q1 + q2 + q3) + (q4 + q5 + q6 + q7);
+    const int local_mean = (c[-1] + c[0] + c[1]) * 16 / 3;
+    return sum - diff - abs(mean - local_mean);
+}
+
+// L2 arithmetic for four pixels held in byte lanes: s[k] = ring sample k of the four pixels.
+// Returns 16-bit lanes T + 0x7FF0 (bit 15 set iff T >= 16), T = sum of chords - sum of diameters;
+// e = pixels 0 and 2, o = pixels 1 and 3. |T| <= 2040, so the lanes never interact.
+__device__ __forceinline__ void l2_word(const uint32_t (&s)[16], uint32_t& e, uint32_t& o)
+{
+    e = 0x7FF07FF0u; o = 0x7FF07FF0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const uint32_t u0 = vabs4(s[i], s[i + 4]),  u1 = vabs4(s[i + 8], s[i + 12]);
+        const uint32_t v0 = vabs4(s[i], s[i + 8]),  v1 = vabs4(s[i + 4], s[i + 12]);
+        e = e + ev(u0) + ev(u1); e = e - ev(v0) - ev(v1);
+        o = o + od(u0) + od(u1); o = o - od(v0) - od(v1);
+    }
+}
+
+struct StripCtx
+{
+    const uint8_t* img;     // the frame
+    int pitch, w;
+    int x0;                 // first pixel of this warp's 256-pixel sub-strip
+    int ys, ye;             // output rows of the segment
+    cand_t* out; uint32_t* count; int cap;
+};
+
+// L3: exact test of queued pixels, 32 at a time (all of them when `final`).
+__device__ __forceinline__ void l3_phase(const StripCtx& c, WarpQueues* q, uint32_t& l3_head, bool final, int lane)
+{
+    __syncwarp();
+    const uint32_t tail = *(volatile uint32_t*)&q->l3_tail;
+    while (tail - l3_head >= 32u || (final && tail != l3_head))
+    {
+        const uint32_t n = min(32u, tail - l3_head);
+        int r = 0, x = 0, y = 0;
+        if ((uint32_t)lane < n)
+        {
+            const uint32_t ent = q->l3q[(l3_head + lane) & (kL3QCap - 1)];
+            x = ent & 0xFFFF; y = ent >> 16;
+            r = chess_exact(c.img + (size_t)y * c.pitch + x, c.pitch);
+        }
+        l3_head += n;
+        const bool hit = r > kRespMin;
+        const uint32_t b = __ballot_sync(kFull, hit);
+        if (b)
+        {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(c.count, (uint32_t)__popc(b));
+            base = __shfl_sync(kFull, base, 0);
+            if (hit)
+            {
+                const uint32_t idx = base + __popc(b & ((1u << lane) - 1));
+                if (idx < (uint32_t)c.cap) c.out[idx] = cand_pack(x, y, r);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// L2 on one 8-pixel cell: pixels X..X+7 of row y. Pushes pixels with T >= 16 to the L3 queue.
+__device__ __forceinline__ void l2_cell(const StripCtx& c, WarpQueues* q, int X, int y)
+{
+    // three 8-byte loads per row: bytes [cA,cA+8) ~ X-8.., [X,X+8), [cC,cC+8) ~ X+8..; clamped at the
+    // frame's first/last cell, where the displaced bytes only feed pixels outside [7,w-7)
+    const int cA = max(X - 8, 0), cC = min(X + 8, c.pitch - 8);
+    const uint8_t* base = c.img + (size_t)y * c.pitch;
+    uint2 A[7], B[7], C[7];
+    const int dys[7] = { -5, -4, -2, 0, 2, 4, 5 };
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+    {
+        const uint8_t* r = base + dys[k] * c.pitch;
+        A[k] = __ldg(reinterpret_cast<const uint2*>(r + cA));
+        B[k] = __ldg(reinterpret_cast<const uint2*>(r + X));
+        C[k] = __ldg(reinterpret_cast<const uint2*>(r + cC));
+    }
+    // words: Wm2 = A.x (X-8), Wm1 = A.y (X-4), W0 = B.x, W1 = B.y, W2 = C.x (X+8), W3 = C.y (X+12)
+    uint32_t s[16], e0, o0, e1, o1;
+    // pixels X..X+3
+    s[0]  = __byte_perm(B[0].x, B[0].y, 0x5432); s[1]  = B[0].x; s[2]  = __byte_perm(A[0].y, B[0].x, 0x5432);
+    s[3]  = A[1].y;                              s[15] = B[1].y;
+    s[4]  = __byte_perm(A[2].x, A[2].y, 0x6543); s[14] = __byte_perm(B[2].y, C[2].x, 0x4321);
+    s[5]  = __byte_perm(A[3].x, A[3].y, 0x6543); s[13] = __byte_perm(B[3].y, C[3].x, 0x4321);
+    s[6]  = __byte_perm(A[4].x, A[4].y, 0x6543); s[12] = __byte_perm(B[4].y, C[4].x, 0x4321);
+    s[7]  = A[5].y;                              s[11] = B[5].y;
+    s[8]  = __byte_perm(A[6].y, B[6].x, 0x5432); s[9]  = B[6].x; s[10] = __byte_perm(B[6].x, B[6].y, 0x5432);
+    l2_word(s, e0, o0);
+    // pixels X+4..X+7: everything one word to the right
+    s[0]  = __byte_perm(B[0].y, C[0].x, 0x5432); s[1]  = B[0].y; s[2]  = __byte_perm(B[0].x, B[0].y, 0x5432);
+    s[3]  = B[1].x;                              s[15] = C[1].x;
+    s[4]  = __byte_perm(A[2].y, B[2].x, 0x6543); s[14] = __byte_perm(C[2].x, C[2].y, 0x4321);
+    s[5]  = __byte_perm(A[3].y, B[3].x, 0x6543); s[13] = __byte_perm(C[3].x, C[3].y, 0x4321);
+    s[6]  = __byte_perm(A[4].y, B[4].x, 0x6543); s[12] = __byte_perm(C[4].x, C[4].y, 0x4321);
+    s[7]  = B[5].x;                              s[11] = C[5].x;
+    s[8]  = __byte_perm(B[6].x, B[6].y, 0x5432); s[9]  = B[6].y; s[10] = __byte_perm(B[6].y, C[6].x, 0x5432);
+    l2_word(s, e1, o1);
+
+    if ((e0 | o0 | e1 | o1) & 0x80008000u)
+    {
+        // rare: some of the eight pixels go on to the exact test. bit p of `hits` = pixel X+p
+        uint32_t hits = ((e0 >> 15) & 1) | ((o0 >> 14) & 2) | ((e0 >> 29) & 4) | ((o0 >> 28) & 8) |
+                        ((e1 >> 11) & 16) | ((o1 >> 10) & 32) | ((e1 >> 25) & 64) | ((o1 >> 24) & 128);
+        while (hits)
+        {
+            const int p = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int x = X + p;
+            if (x >= kMargin && x < c.w - kMargin)
+            {
+                const uint32_t pos = atomicAdd(&q->l3_tail, 1u);
+                q->l3q[pos & (kL3QCap - 1)] = ((uint32_t)y << 16) | (uint32_t)x;
+            }
+        }
+    }
+}
+
+// L2 phase: every lane repeatedly takes a flagged cell (a column of up to 11 row bits) from the
+// warp's queue and tests its rows one per iteration, so lanes stay busy however the flags are
+// spread. Unless `final`, the phase stops when fewer than 24 lanes have work left; their partial
+// cells stay in (cur_rows, cur_meta) for the next phase.
+__device__ __forceinline__ void l2_phase(const StripCtx& c, WarpQueues* q, uint32_t& q_head, uint32_t q_tail,
+                                         uint32_t& cur_rows, uint32_t& cur_meta, uint32_t& l3_head, bool final, int lane)
+{
+    const uint32_t lt = (1u << lane) - 1;
+    __syncwarp();
+    for (;;)
+    {
+        const bool need = cur_rows == 0;
+        const uint32_t nm = __ballot_sync(kFull, need);
+        const uint32_t avail = q_tail - q_head;
+        if (nm && avail)
+        {
+            const uint32_t rank = __popc(nm & lt);
+            if (need && rank < avail)
+            {
+                const uint32_t ent = q->l2q[(q_head + rank) & (kL2QCap - 1)];
+                cur_rows = ent & 0x7FFu; cur_meta = ent >> 11;
+            }
+            q_head += min((uint32_t)__popc(nm), avail);
+        }
+        const uint32_t act = __ballot_sync(kFull, cur_rows != 0);
+        if (final ? act == 0 : __popc(act) < 24) break;
+        if (cur_rows)
+        {
+            const int j = __ffs(cur_rows) - 1;
+            cur_rows &= cur_rows - 1;
+            // meta = lane column (5 bits) | (first output row of the block + 16) << 5
+            l2_cell(c, q, c.x0 + kLanePx * (int)(cur_meta & 31u), (int)(cur_meta >> 5) - 16 + j);
+        }
+        l3_phase(c, q, l3_head, false, lane);
+    }
+}
+
+template<int NW>
+__global__ void __launch_bounds__(NW * 32)
+chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, CascadeParams tp,
+                     cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
+{
+    using G = Geo<NW>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: ring[stages][kStageBytes] | full_bar[stages] | empty_bar[stages] | next_issue | queues[NW]
+    uint8_t*  ring      = smem;
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + (size_t)tp.stages * G::kStageBytes);
+    uint64_t* empty_bar = full_bar + tp.stages;
+    int*      next_issue = reinterpret_cast<int*>(empty_bar + tp.stages);
+    WarpQueues* queues  = reinterpret_cast<WarpQueues*>(next_issue + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+    const int nst = tp.stages;
+    if (tid == 0)
+    {
+        *next_issue = tp.lookahead;
+        for (int s = 0; s < nst; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    WarpQueues* q = &queues[wi];
+    if (lane == 0) q->l3_tail = 0;
+    __syncthreads();
+
+    const int item  = blockIdx.x;
+    const int strip = item % tp.nstrips;
+    const int seg   = (item / tp.nstrips) % tp.nsegs;
+    const int f     = item / (tp.nstrips * tp.nsegs);
+    const int xs = strip * G::kStripW;                   // first pixel of the strip
+    const int ys = kMargin + seg * tp.seg_rows;          // first output row of the segment
+    const int ye = min(ys + tp.seg_rows, fs.h - kMargin);
+    // Step j of block `it` stages frame row rbase + it*11 + j: the "+5" row of output row y = that - 5.
+    // The first ten staged rows (ys-5 .. ys+4) only prime the register window.
+    const int rbase = ys - 5;
+    const int nit = (ye - ys + 10 + kBlkRows - 1) / kBlkRows;
+
+    StripCtx c;
+    c.img = fs.base + (size_t)f * fs.frame_stride; c.pitch = fs.pitch; c.w = fs.w;
+    c.x0 = xs + wi * kWarpPx; c.ys = ys; c.ye = ye;
+    c.out = cand + (size_t)f * tp.cap; c.count = counts + f; c.cap = tp.cap;
+
+    // request the stage of block `it`: the whole warp waits for the slot, one lane issues the copy
+    auto issue = [&](int it)
+    {
+        const int s = it % nst;
+        if (it >= nst) mbar_wait_warp(&empty_bar[s], ((it / nst) - 1) & 1);
+        if (lane == 0)
+        {
+            mbar_arrive_expect_tx(&full_bar[s], G::kRowBytes * kBlkRows);
+            tma_load_3d(ring + (size_t)s * G::kStageBytes, &tmap, (xs - kCHalo) / 4, rbase + it * kBlkRows, f, &full_bar[s]);
+        }
+        __syncwarp();
+    };
+    if (wi == 0)
+        for (int it = 0; it < tp.lookahead && it < nit; it++) issue(it);
+
+    // byte offset, in a staged row, of this lane's byte X-8 (X = c.x0 + 8*lane)
+    const int lane_off = wi * kWarpPx + kLanePx * lane + (kCHalo - 8);
+
+    // Register window (slot = step at which the row was staged):
+    //   PP2 = bytes X+2.., X+6..  (ring dx = +2 of rows y-5 and y+5)    live 11 rows
+    //   PM5 = bytes X-5.., X-1..  (ring dx = -5 of rows y-2, y, y+2)    live 8 rows
+    //   the previous row's aligned words Wm1, W0, W1, W2 (ring dx = -4/+4 of row y+4)
+    uint32_t PP2a[kBlkRows], PP2b[kBlkRows], PM5a[kBlkRows], PM5b[kBlkRows];
+#pragma unroll
+    for (int j = 0; j < kBlkRows; j++) PP2a[j] = PP2b[j] = PM5a[j] = PM5b[j] = 0;
+    uint32_t pWm1 = 0, pW0 = 0, pW1 = 0, pW2 = 0;
+
+    uint32_t q_head = 0, q_tail = 0, cur_rows = 0, cur_meta = 0, l3_head = 0;
+    // cells without a pixel in [7,w-7) are never tested (their row bytes may lie beyond the pitch)
+    const bool lane_valid = c.x0 + kLanePx * lane < fs.w - kMargin;
+    const uint32_t lt = (1u << lane) - 1;
+
+#pragma unroll 1
+    for (int it = 0; it < nit; it++)
+    {
+        const int s = it % nst;
+        // whichever warp gets here first requests the stage `lookahead` blocks ahead
+        if (it + tp.lookahead < nit)
+        {
+            int won = 0;
+            if (lane == 0) won = atomicCAS(next_issue, it + tp.lookahead, it + tp.lookahead + 1) == it + tp.lookahead;
+            if (__shfl_sync(kFull, won, 0)) issue(it + tp.lookahead);
+        }
+        mbar_wait_warp(&full_bar[s], (it / nst) & 1);
+        __syncwarp();
+
+        const uint8_t* stage = ring + (size_t)s * G::kStageBytes + lane_off;
+        uint32_t flagbits = 0;
+#pragma unroll
+        for (int j = 0; j < kBlkRows; j++)
+        {
+            constexpr int N = kBlkRows;
+            const uint2 A = *reinterpret_cast<const uint2*>(stage + j * G::kRowBytes);        // X-8, X-4
+            const uint2 B = *reinterpret_cast<const uint2*>(stage + j * G::kRowBytes + 8);    // X,   X+4
+            const uint2 C = *reinterpret_cast<const uint2*>(stage + j * G::kRowBytes + 16);   // X+8, (X+12)
+            const uint32_t pm5a = __byte_perm(A.x, A.y, 0x6543), pm5b = __byte_perm(A.y, B.x, 0x6543);
+            const uint32_t pp2a = __byte_perm(B.x, B.y, 0x5432), pp2b = __byte_perm(B.y, C.x, 0x5432);
+            // slots of the rows staged k steps ago
+            const int r10 = (j + 1) % N, r7 = (j + 4) % N, r5 = (j + 6) % N, r3 = (j + 8) % N;
+            // chords, output row y = (row staged now) - 5:
+            //   i=0: s0 (+2,-5) vs s4 (-5,-2)      i=1: s9 (0,+5) vs s5 (-5,0)
+            //   i=2: s10 (+2,+5) vs s6 (-5,+2)     i=3: s7 (-4,+4) vs s11 (+4,+4)
+            const uint32_t u0a = vabs4(PP2a[r10], PM5a[r7]), u0b = vabs4(PP2b[r10], PM5b[r7]);
+            const uint32_t u1a = vabs4(B.x, PM5a[r5]),       u1b = vabs4(B.y, PM5b[r5]);
+            const uint32_t u2a = vabs4(pp2a, PM5a[r3]),      u2b = vabs4(pp2b, PM5b[r3]);
+            const uint32_t u3a = vabs4(pWm1, pW1),           u3b = vabs4(pW0, pW2);
+            const uint32_t sa = u0a + u1a + u2a + u3a + 0x78787878u;    // bit 7 of a lane: sum >= 8 (if no chord >= 8 ...)
+            const uint32_t sb = u0b + u1b + u2b + u3b + 0x78787878u;
+            const uint32_t big = (u0a | u1a | u2a | u3a | u0b | u1b | u2b | u3b) & 0xF8F8F8F8u;   // ... else caught here
+            if ((((sa | sb) & 0x80808080u) | big) != 0) flagbits |= 1u << j;
+            PP2a[j] = pp2a; PP2b[j] = pp2b; PM5a[j] = pm5a; PM5b[j] = pm5b;
+            pWm1 = A.y; pW0 = B.x; pW1 = B.y; pW2 = C.x;
+        }
+
+        // hand the stage back (L2/L3 read global memory, not the ring)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+        // rows of this block that belong to the segment: output row of step j is ybase + j
+        const int ybase = rbase + it * kBlkRows - 5;
+        const int lo = max(ys - ybase, 0), hi = min(ye - ybase, kBlkRows);
+        flagbits &= hi > lo && lane_valid ? ((1u << hi) - (1u << lo)) : 0u;
+
+        const uint32_t m = __ballot_sync(kFull, flagbits != 0);
+        if (m)
+        {
+            if (flagbits)
+                q->l2q[(q_tail + __popc(m & lt)) & (kL2QCap - 1)] = flagbits | ((uint32_t)lane << 11) | ((uint32_t)(ybase + 16) << 16);
+            q_tail += __popc(m);
+            if (q_tail - q_head >= 32u)
+                l2_phase(c, q, q_head, q_tail, cur_rows, cur_meta, l3_head, false, lane);
+        }
+    }
+    l2_phase(c, q, q_head, q_tail, cur_rows, cur_meta, l3_head, true, lane);
+    l3_phase(c, q, l3_head, true, lane);
+}
+
+bool make_cascade_map(CUtensorMap* map, const FrameSet& fs, int row_bytes)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    if (((uintptr_t)fs.base & 15) || (fs.pitch & 15)) return false;
+    size_t fstride = fs.frame_stride;
+    if (fs.nframes == 1) fstride = ((size_t)fs.pitch * fs.h + 15) & ~(size_t)15;
+    if (fstride & 15) return false;
+    // the row is declared `pitch` bytes wide: padding bytes beyond w only ever feed pixels outside [7,w-7)
+    const cuuint64_t dims[3]    = { (cuuint64_t)(fs.pitch / 4), (cuuint64_t)fs.h, (cuuint64_t)fs.nframes };
+    const cuuint64_t strides[2] = { (cuuint64_t)fs.pitch, (cuuint64_t)fstride };
+    const cuuint32_t box[3]     = { (cuuint32_t)(row_bytes / 4), kBlkRows, 1 };
+    const cuuint32_t estr[3]    = { 1, 1, 1 };
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)fs.base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template<int NW>
+cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32_t* counts, cudaStream_t stream, bool* ok)
+{
+    using G = Geo<NW>;
+    CUtensorMap map;
+    *ok = make_cascade_map(&map, fs, G::kRowBytes);
+    if (!*ok) return cudaSuccess;
+    const size_t smem = (size_t)tp.stages * G::kStageBytes + 2 * tp.stages * sizeof(uint64_t) + 16 + NW * sizeof(WarpQueues);
+    if (smem > 48 * 1024)
+    {
+        // per device, idempotent and cheap: set on every launch rather than tracking devices
+        cudaError_t e = cudaFuncSetAttribute(chess_cascade_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const long long items = (long long)fs.nframes * tp.nstrips * tp.nsegs;
+    if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
+    chess_cascade_kernel<NW><<<(unsigned)items, NW * 32, smem, stream>>>(map, fs, tp, cand, counts);
+    return cudaGetLastError();
+}
+
+int env_int(const char* name, int dflt, int lo, int hi)
+{
+    if (const char* e = getenv(name)) { const int v = atoi(e); if (v >= lo && v <= hi) return v; }
+    return dflt;
+}
+}   // namespace
+
+// Returns cudaSuccess with *launched = false when the frames do not meet TMA's alignment rules
+// (the caller then uses the tiled kernel's cooperative loader).
+cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32_t* counts,
+                                        int cand_capacity, cudaStream_t stream, bool* launched)
+{
+    *launched = true;
+    if (fs.w <= 2*kMargin || fs.h <= 2*kMargin || fs.nframes <= 0) return cudaSuccess;
+    if (fs.h > 32767 || fs.w > 32767) { *launched = false; return cudaSuccess; }
+
+    // strip width: the one that stages the fewest bytes (ties -> wider)
+    int nw = env_int("MRG_B200_K1_NW", 0, 1, 3);
+    if (nw == 0)
+    {
+        long long best = -1;
+        for (int k = 3; k >= 1; k--)
+        {
+            const int sw = kWarpPx * k;
+            const long long cost = (long long)((fs.w - kMargin + sw - 1) / sw) * (sw + 2 * kCHalo);
+            if (best < 0 || cost < best) { best = cost; nw = k; }
+        }
+    }
+    CascadeParams tp;
+    tp.cap = cand_capacity;
+    tp.stages = env_int("MRG_B200_K1_STAGES", 3, 3, 12);
+    tp.lookahead = env_int("MRG_B200_K1_LOOKAHEAD", 1, 1, tp.stages - 2);
+    const int sw = kWarpPx * nw;
+    tp.nstrips = (fs.w - kMargin + sw - 1) / sw;
+    const int out_rows = fs.h - 2*kMargin;
+    // enough work items to fill the chip a few times over, but segments no shorter than 44 rows
+    const long long want_items = 148LL * 4 * 4;
+    const long long per_seg = (long long)fs.nframes * tp.nstrips;
+    long long nsegs = (want_items + per_seg - 1) / per_seg;
+    int seg_rows = (int)((out_rows + nsegs - 1) / nsegs);
+    seg_rows = ((seg_rows + kBlkRows - 1) / kBlkRows) * kBlkRows;
+    if (seg_rows < 44) seg_rows = 44;
+    tp.seg_rows = seg_rows;
+    tp.nsegs = (out_rows + seg_rows - 1) / seg_rows;
+
+    switch (nw)
+    {
+    case 1:  return launch_nw<1>(fs, tp, cand, counts, stream, launched);
+    case 2:  return launch_nw<2>(fs, tp, cand, counts, stream, launched);
+    default: return launch_nw<3>(fs, tp, cand, counts, stream, launched);
+    }
+}
+
+}

@@ -60,6 +60,10 @@ cudaError_t launch_chess_sparse_simple(const FrameSet& fs, cand_t* cand, uint32_
 // K1 (tiled variant): TMA/shared-memory staged, packed-lane arithmetic
 cudaError_t launch_chess_sparse_tiled(const FrameSet& fs, cand_t* cand, uint32_t* counts,
                                       int cand_capacity, cudaStream_t stream);
+// K1 (cascade variant, production): TMA-staged, byte-lane filter cascade. *launched = false (and
+// nothing enqueued) when the frames do not meet TMA's alignment rules.
+cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32_t* counts,
+                                        int cand_capacity, cudaStream_t stream, bool* launched);
 // dense int16 response (interior only), for the ChESS_response_5 API
 cudaError_t launch_chess_dense(const FrameSet& fs, int16_t* response, size_t response_frame_stride_elems,
                                cudaStream_t stream);

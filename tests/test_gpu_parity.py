@@ -234,16 +234,18 @@ def test_large_candidate_lists_use_global_scratch(api, oracle):
 
 
 def test_kernel_variants_agree(api, oracle):
+    # 0 = cascade (production), 1 = one thread per pixel, 2 = tiled: identical candidate sets and corners
     frames = np.stack([synth.board_frame(800, 608, 10, seed=90), synth.blurred_noise_frame(800, 608, seed=91)])
-    a = api.Detector(max_frames=2, max_points=4096, kernel_variant=0)
-    b = api.Detector(max_frames=2, max_points=4096, kernel_variant=1)
-    xa, ca = a.find_corners(frames, 0)
-    xb, cb = b.find_corners(frames, 0)
-    assert np.array_equal(ca, cb) and np.array_equal(a.last_candidate_counts(2), b.last_candidate_counts(2))
-    for i in range(2):
-        assert np.array_equal(xa[i, :ca[i]], xb[i, :cb[i]])
-    _check_batch(xa, ca, frames, oracle, 0)
-    a.close(); b.close()
+    dets = [api.Detector(max_frames=2, max_points=4096, kernel_variant=v) for v in (0, 1, 2)]
+    res = [d.find_corners(frames, 0) for d in dets]
+    cands = [d.last_candidate_counts(2) for d in dets]
+    for v in (1, 2):
+        assert np.array_equal(res[0][1], res[v][1]) and np.array_equal(cands[0], cands[v]), (v, cands)
+        for i in range(2):
+            assert np.array_equal(res[0][0][i, :res[0][1][i]], res[v][0][i, :res[v][1][i]])
+    _check_batch(res[0][0], res[0][1], frames, oracle, 0)
+    for d in dets:
+        d.close()
 
 
 def test_empty_batch_and_tiny_frames(api, oracle):
