@@ -34,7 +34,8 @@
 // (cp.async.bulk.tensor.3d, one (256*NW+32)-byte x 11-row box per stage), completion on mbarriers,
 // stages handed back through a second set of mbarriers. A lane owns 8 adjacent pixels (two 32-bit
 // words) and keeps the PRMT'd words of the last 11 rows in registers (row loop unrolled x11).
-// L2/L3 re-read their few cells from global memory (L2-cache hits: the strip was just streamed).
+// L2 reads its cells from the two staged blocks still resident in shared memory (a stage is handed
+// back two blocks late for that); L3 re-reads its few pixels from global memory.
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
@@ -51,8 +52,8 @@ constexpr int kLanePx   = 8;                   // pixels per lane
 constexpr int kWarpPx   = 32 * kLanePx;        // 256
 constexpr int kCHalo    = 16;                  // staged bytes left/right of the strip (ring needs 8; TMA boxes start 16-aligned)
 constexpr int kBlkRows  = 11;                  // rows per TMA stage == unroll of the row loop == register window
-constexpr int kL2QCap   = 128;                 // per-warp queue of flagged cells (power of two)
-constexpr int kL3QCap   = 512;                 // per-warp queue of pixels for the exact test (power of two)
+constexpr int kL2QCap   = 512;                 // per-warp queue of flagged 8-pixel row cells (power of two, >= 31 + 352)
+constexpr int kL3QCap   = 512;                 // per-warp queue of pixels for the exact test (power of two, >= 31 + 256)
 
 template<int NW> struct Geo
 {
@@ -70,10 +71,10 @@ struct CascadeParams
 
 struct WarpQueues
 {
-    uint32_t l2q[kL2QCap];
     uint32_t l3q[kL3QCap];
-    uint32_t l3_tail;
-    uint32_t pad[3];
+    uint16_t l2q[kL2QCap];
+    uint32_t l2_tail, l3_tail;
+    uint32_t pad[2];
 };
 
 // mbarrier wait as a plain C loop around try_wait, executed by whole warps: no branch hidden from
@@ -172,98 +173,80 @@ __device__ __forceinline__ void l3_phase(const StripCtx& c, WarpQueues* q, uint3
     __syncwarp();
 }
 
-// L2 on one 8-pixel cell: pixels X..X+7 of row y. Pushes pixels with T >= 16 to the L3 queue.
-__device__ __forceinline__ void l2_cell(const StripCtx& c, WarpQueues* q, int X, int y)
+// One L2 batch: lane k < n takes unit head+k of the warp's queue, an 8-pixel row cell flagged by
+// L1, and reads its 7 ring rows from the staged blocks still resident in shared memory (a cell of
+// block B needs rows of blocks B and B-1). unit = one-hot step bit << 5 | lane column; units before
+// queue position `mark` belong to block it-1, the others to block it.
+// Pixels with T >= 16 go to the L3 queue.
+struct L2Ctx
 {
-    // three 8-byte loads per row: bytes [cA,cA+8) ~ X-8.., [X,X+8), [cC,cC+8) ~ X+8..; clamped at the
-    // frame's first/last cell, where the displaced bytes only feed pixels outside [7,w-7)
-    const int cA = max(X - 8, 0), cC = min(X + 8, c.pitch - 8);
-    const uint8_t* base = c.img + (size_t)y * c.pitch;
-    uint2 A[7], B[7], C[7];
-    const int dys[7] = { -5, -4, -2, 0, 2, 4, 5 };
+    const uint8_t* ring;
+    uint32_t off0, off1, off2;   // byte offsets of the stages of blocks it, it-1, it-2 (+ the warp's column base)
+    int ybase;                   // first output row of block it
+    uint32_t mark;               // queue position of the first unit of block it
+    int row_bytes;
+};
+
+__device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, WarpQueues* q, uint32_t head, uint32_t n, int lane)
+{
+    if ((uint32_t)lane < n)
+    {
+        const uint32_t u = q->l2q[(head + lane) & (kL2QCap - 1)];
+        const int col = u & 31, j = 31 - __clz(u >> 5);
+        const bool cur = (int)(head + lane - L.mark) >= 0;
+        const uint32_t sA = (cur ? L.off0 : L.off1) + kLanePx * col, sB = (cur ? L.off1 : L.off2) + kLanePx * col;
+        const int y = (cur ? L.ybase : L.ybase - kBlkRows) + j, X = c.x0 + kLanePx * col;
+        // ring row y+dy was staged (5 - dy) steps before step j: in block B if j >= 5 - dy, else in B-1
+        uint2 A[7], B[7], C[7];
+        const int behind[7] = { 10, 9, 7, 5, 3, 1, 0 };
 #pragma unroll
-    for (int k = 0; k < 7; k++)
-    {
-        const uint8_t* r = base + dys[k] * c.pitch;
-        A[k] = __ldg(reinterpret_cast<const uint2*>(r + cA));
-        B[k] = __ldg(reinterpret_cast<const uint2*>(r + X));
-        C[k] = __ldg(reinterpret_cast<const uint2*>(r + cC));
-    }
-    // words: Wm2 = A.x (X-8), Wm1 = A.y (X-4), W0 = B.x, W1 = B.y, W2 = C.x (X+8), W3 = C.y (X+12)
-    uint32_t s[16], e0, o0, e1, o1;
-    // pixels X..X+3
-    s[0]  = __byte_perm(B[0].x, B[0].y, 0x5432); s[1]  = B[0].x; s[2]  = __byte_perm(A[0].y, B[0].x, 0x5432);
-    s[3]  = A[1].y;                              s[15] = B[1].y;
-    s[4]  = __byte_perm(A[2].x, A[2].y, 0x6543); s[14] = __byte_perm(B[2].y, C[2].x, 0x4321);
-    s[5]  = __byte_perm(A[3].x, A[3].y, 0x6543); s[13] = __byte_perm(B[3].y, C[3].x, 0x4321);
-    s[6]  = __byte_perm(A[4].x, A[4].y, 0x6543); s[12] = __byte_perm(B[4].y, C[4].x, 0x4321);
-    s[7]  = A[5].y;                              s[11] = B[5].y;
-    s[8]  = __byte_perm(A[6].y, B[6].x, 0x5432); s[9]  = B[6].x; s[10] = __byte_perm(B[6].x, B[6].y, 0x5432);
-    l2_word(s, e0, o0);
-    // pixels X+4..X+7: everything one word to the right
-    s[0]  = __byte_perm(B[0].y, C[0].x, 0x5432); s[1]  = B[0].y; s[2]  = __byte_perm(B[0].x, B[0].y, 0x5432);
-    s[3]  = B[1].x;                              s[15] = C[1].x;
-    s[4]  = __byte_perm(A[2].y, B[2].x, 0x6543); s[14] = __byte_perm(C[2].x, C[2].y, 0x4321);
-    s[5]  = __byte_perm(A[3].y, B[3].x, 0x6543); s[13] = __byte_perm(C[3].x, C[3].y, 0x4321);
-    s[6]  = __byte_perm(A[4].y, B[4].x, 0x6543); s[12] = __byte_perm(C[4].x, C[4].y, 0x4321);
-    s[7]  = B[5].x;                              s[11] = C[5].x;
-    s[8]  = __byte_perm(B[6].x, B[6].y, 0x5432); s[9]  = B[6].y; s[10] = __byte_perm(B[6].y, C[6].x, 0x5432);
-    l2_word(s, e1, o1);
-
-    if ((e0 | o0 | e1 | o1) & 0x80008000u)
-    {
-        // rare: some of the eight pixels go on to the exact test. bit p of `hits` = pixel X+p
-        uint32_t hits = ((e0 >> 15) & 1) | ((o0 >> 14) & 2) | ((e0 >> 29) & 4) | ((o0 >> 28) & 8) |
-                        ((e1 >> 11) & 16) | ((o1 >> 10) & 32) | ((e1 >> 25) & 64) | ((o1 >> 24) & 128);
-        while (hits)
+        for (int k = 0; k < 7; k++)
         {
-            const int p = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const int x = X + p;
-            if (x >= kMargin && x < c.w - kMargin)
+            const int r = j - behind[k];
+            const uint8_t* p = L.ring + (r >= 0 ? sA + r * L.row_bytes : sB + (r + kBlkRows) * L.row_bytes);
+            A[k] = *reinterpret_cast<const uint2*>(p);        // X-8, X-4
+            B[k] = *reinterpret_cast<const uint2*>(p + 8);    // X,   X+4
+            C[k] = *reinterpret_cast<const uint2*>(p + 16);   // X+8, X+12
+        }
+        uint32_t s[16], e0, o0, e1, o1;
+        // pixels X..X+3
+        s[0]  = __byte_perm(B[0].x, B[0].y, 0x5432); s[1]  = B[0].x; s[2]  = __byte_perm(A[0].y, B[0].x, 0x5432);
+        s[3]  = A[1].y;                              s[15] = B[1].y;
+        s[4]  = __byte_perm(A[2].x, A[2].y, 0x6543); s[14] = __byte_perm(B[2].y, C[2].x, 0x4321);
+        s[5]  = __byte_perm(A[3].x, A[3].y, 0x6543); s[13] = __byte_perm(B[3].y, C[3].x, 0x4321);
+        s[6]  = __byte_perm(A[4].x, A[4].y, 0x6543); s[12] = __byte_perm(B[4].y, C[4].x, 0x4321);
+        s[7]  = A[5].y;                              s[11] = B[5].y;
+        s[8]  = __byte_perm(A[6].y, B[6].x, 0x5432); s[9]  = B[6].x; s[10] = __byte_perm(B[6].x, B[6].y, 0x5432);
+        l2_word(s, e0, o0);
+        // pixels X+4..X+7: everything one word to the right
+        s[0]  = __byte_perm(B[0].y, C[0].x, 0x5432); s[1]  = B[0].y; s[2]  = __byte_perm(B[0].x, B[0].y, 0x5432);
+        s[3]  = B[1].x;                              s[15] = C[1].x;
+        s[4]  = __byte_perm(A[2].y, B[2].x, 0x6543); s[14] = __byte_perm(C[2].x, C[2].y, 0x4321);
+        s[5]  = __byte_perm(A[3].y, B[3].x, 0x6543); s[13] = __byte_perm(C[3].x, C[3].y, 0x4321);
+        s[6]  = __byte_perm(A[4].y, B[4].x, 0x6543); s[12] = __byte_perm(C[4].x, C[4].y, 0x4321);
+        s[7]  = B[5].x;                              s[11] = C[5].x;
+        s[8]  = __byte_perm(B[6].x, B[6].y, 0x5432); s[9]  = B[6].y; s[10] = __byte_perm(B[6].y, C[6].x, 0x5432);
+        l2_word(s, e1, o1);
+
+        if ((e0 | o0 | e1 | o1) & 0x80008000u)
+        {
+            // rare: some of the eight pixels go on to the exact test. bit p of `hits` = pixel X+p
+            uint32_t hits = ((e0 >> 15) & 1) | ((o0 >> 14) & 2) | ((e0 >> 29) & 4) | ((o0 >> 28) & 8) |
+                            ((e1 >> 11) & 16) | ((o1 >> 10) & 32) | ((e1 >> 25) & 64) | ((o1 >> 24) & 128);
+            while (hits)
             {
-                const uint32_t pos = atomicAdd(&q->l3_tail, 1u);
-                q->l3q[pos & (kL3QCap - 1)] = ((uint32_t)y << 16) | (uint32_t)x;
+                const int pp = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int x = X + pp;
+                if (x >= kMargin && x < c.w - kMargin)
+                {
+                    const uint32_t pos = atomicAdd(&q->l3_tail, 1u);
+                    q->l3q[pos & (kL3QCap - 1)] = ((uint32_t)y << 16) | (uint32_t)x;
+                }
             }
         }
     }
-}
-
-// L2 phase: every lane repeatedly takes a flagged cell (a column of up to 11 row bits) from the
-// warp's queue and tests its rows one per iteration, so lanes stay busy however the flags are
-// spread. Unless `final`, the phase stops when fewer than 24 lanes have work left; their partial
-// cells stay in (cur_rows, cur_meta) for the next phase.
-__device__ __forceinline__ void l2_phase(const StripCtx& c, WarpQueues* q, uint32_t& q_head, uint32_t q_tail,
-                                         uint32_t& cur_rows, uint32_t& cur_meta, uint32_t& l3_head, bool final, int lane)
-{
-    const uint32_t lt = (1u << lane) - 1;
     __syncwarp();
-    for (;;)
-    {
-        const bool need = cur_rows == 0;
-        const uint32_t nm = __ballot_sync(kFull, need);
-        const uint32_t avail = q_tail - q_head;
-        if (nm && avail)
-        {
-            const uint32_t rank = __popc(nm & lt);
-            if (need && rank < avail)
-            {
-                const uint32_t ent = q->l2q[(q_head + rank) & (kL2QCap - 1)];
-                cur_rows = ent & 0x7FFu; cur_meta = ent >> 11;
-            }
-            q_head += min((uint32_t)__popc(nm), avail);
-        }
-        const uint32_t act = __ballot_sync(kFull, cur_rows != 0);
-        if (final ? act == 0 : __popc(act) < 24) break;
-        if (cur_rows)
-        {
-            const int j = __ffs(cur_rows) - 1;
-            cur_rows &= cur_rows - 1;
-            // meta = lane column (5 bits) | (first output row of the block + 16) << 5
-            l2_cell(c, q, c.x0 + kLanePx * (int)(cur_meta & 31u), (int)(cur_meta >> 5) - 16 + j);
-        }
-        l3_phase(c, q, l3_head, false, lane);
-    }
 }
 
 template<int NW>
@@ -273,23 +256,21 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
 {
     using G = Geo<NW>;
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: ring[stages][kStageBytes] | full_bar[stages] | empty_bar[stages] | next_issue | queues[NW]
+    // layout: ring[stages][kStageBytes] | full_bar[stages] | released[stages] | queues[NW]
     uint8_t*  ring      = smem;
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + (size_t)tp.stages * G::kStageBytes);
-    uint64_t* empty_bar = full_bar + tp.stages;
-    int*      next_issue = reinterpret_cast<int*>(empty_bar + tp.stages);
-    WarpQueues* queues  = reinterpret_cast<WarpQueues*>(next_issue + 4);
+    uint32_t* released  = reinterpret_cast<uint32_t*>(full_bar + tp.stages);     // warps done with the stage's current block
+    WarpQueues* queues  = reinterpret_cast<WarpQueues*>(released + ((tp.stages + 3) & ~3));
 
     const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
     const int nst = tp.stages;
     if (tid == 0)
     {
-        *next_issue = tp.lookahead;
-        for (int s = 0; s < nst; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        for (int s = 0; s < nst; s++) { mbar_init(&full_bar[s], 1); released[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     WarpQueues* q = &queues[wi];
-    if (lane == 0) q->l3_tail = 0;
+    if (lane == 0) { q->l2_tail = 0; q->l3_tail = 0; }
     __syncthreads();
 
     const int item  = blockIdx.x;
@@ -309,50 +290,62 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
     c.x0 = xs + wi * kWarpPx; c.ys = ys; c.ye = ye;
     c.out = cand + (size_t)f * tp.cap; c.count = counts + f; c.cap = tp.cap;
 
-    // request the stage of block `it`: the whole warp waits for the slot, one lane issues the copy
-    auto issue = [&](int it)
+    // One thread requests block `it` into its stage. The ring is filled once here; after that a
+    // stage is refilled by whichever warp is the LAST to be done with it (release() below), so no
+    // warp ever waits for a free slot and every copy is in flight as early as it can be.
+    auto issue = [&](int it, int s)
     {
-        const int s = it % nst;
-        if (it >= nst) mbar_wait_warp(&empty_bar[s], ((it / nst) - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[s], G::kRowBytes * kBlkRows);
+        tma_load_3d(ring + (size_t)s * G::kStageBytes, &tmap, (xs - kCHalo) / 4, rbase + it * kBlkRows, f, &full_bar[s]);
+    };
+    auto release = [&](int it, int s)    // this warp no longer reads stage s = block `it` (call with the warp converged)
+    {
+        __syncwarp();
         if (lane == 0)
         {
-            mbar_arrive_expect_tx(&full_bar[s], G::kRowBytes * kBlkRows);
-            tma_load_3d(ring + (size_t)s * G::kStageBytes, &tmap, (xs - kCHalo) / 4, rbase + it * kBlkRows, f, &full_bar[s]);
+            __threadfence_block();
+            if (atomicAdd(&released[s], 1u) == NW - 1)
+            {
+                released[s] = 0;
+                __threadfence_block();
+                if (it + nst < nit)
+                {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(it + nst, s);
+                }
+            }
         }
-        __syncwarp();
     };
-    if (wi == 0)
-        for (int it = 0; it < tp.lookahead && it < nit; it++) issue(it);
+    if (tid == 0)
+        for (int it = 0; it < nst && it < nit; it++) issue(it, it);
 
     // byte offset, in a staged row, of this lane's byte X-8 (X = c.x0 + 8*lane)
     const int lane_off = wi * kWarpPx + kLanePx * lane + (kCHalo - 8);
 
-    // Register window (slot = step at which the row was staged):
-    //   PP2 = bytes X+2.., X+6..  (ring dx = +2 of rows y-5 and y+5)    live 11 rows
-    //   PM5 = bytes X-5.., X-1..  (ring dx = -5 of rows y-2, y, y+2)    live 8 rows
+    // Register window (slot = step at which the row was staged). The two words of a lane use mirrored
+    // chords so that they share one PRMT'd word per row (bytes X+2..X+5 are dx = +2 for pixels X..X+3
+    // and dx = -2 for pixels X+4..X+7):
+    //   PP2  = bytes X+2..X+5    rows y-5 and y+5, both words                 live 11 rows
+    //   PM5a = bytes X-5..X-2    dx = -5 of rows y-2, y, y+2, pixels X..X+3    live 8 rows
+    //   PP5b = bytes X+9..X+12   dx = +5 of rows y-2, y, y+2, pixels X+4..X+7  live 8 rows
     //   the previous row's aligned words Wm1, W0, W1, W2 (ring dx = -4/+4 of row y+4)
-    uint32_t PP2a[kBlkRows], PP2b[kBlkRows], PM5a[kBlkRows], PM5b[kBlkRows];
+    uint32_t PP2[kBlkRows], PM5a[kBlkRows], PP5b[kBlkRows];
 #pragma unroll
-    for (int j = 0; j < kBlkRows; j++) PP2a[j] = PP2b[j] = PM5a[j] = PM5b[j] = 0;
+    for (int j = 0; j < kBlkRows; j++) PP2[j] = PM5a[j] = PP5b[j] = 0;
     uint32_t pWm1 = 0, pW0 = 0, pW1 = 0, pW2 = 0;
 
-    uint32_t q_head = 0, q_tail = 0, cur_rows = 0, cur_meta = 0, l3_head = 0;
+    uint32_t q_head = 0, prev_mark = 0, l3_head = 0;
+    L2Ctx L;
+    L.ring = ring; L.off0 = L.off1 = L.off2 = 0; L.row_bytes = G::kRowBytes;
     // cells without a pixel in [7,w-7) are never tested (their row bytes may lie beyond the pitch)
     const bool lane_valid = c.x0 + kLanePx * lane < fs.w - kMargin;
-    const uint32_t lt = (1u << lane) - 1;
 
+    int s = 0, s_rel = 0;          // stage of block it / of the block released next
+    uint32_t full_parity = 0;
 #pragma unroll 1
     for (int it = 0; it < nit; it++)
     {
-        const int s = it % nst;
-        // whichever warp gets here first requests the stage `lookahead` blocks ahead
-        if (it + tp.lookahead < nit)
-        {
-            int won = 0;
-            if (lane == 0) won = atomicCAS(next_issue, it + tp.lookahead, it + tp.lookahead + 1) == it + tp.lookahead;
-            if (__shfl_sync(kFull, won, 0)) issue(it + tp.lookahead);
-        }
-        mbar_wait_warp(&full_bar[s], (it / nst) & 1);
+        mbar_wait_warp(&full_bar[s], full_parity);
         __syncwarp();
 
         const uint8_t* stage = ring + (size_t)s * G::kStageBytes + lane_off;
@@ -363,46 +356,80 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
             constexpr int N = kBlkRows;
             const uint2 A = *reinterpret_cast<const uint2*>(stage + j * G::kRowBytes);        // X-8, X-4
             const uint2 B = *reinterpret_cast<const uint2*>(stage + j * G::kRowBytes + 8);    // X,   X+4
-            const uint2 C = *reinterpret_cast<const uint2*>(stage + j * G::kRowBytes + 16);   // X+8, (X+12)
-            const uint32_t pm5a = __byte_perm(A.x, A.y, 0x6543), pm5b = __byte_perm(A.y, B.x, 0x6543);
-            const uint32_t pp2a = __byte_perm(B.x, B.y, 0x5432), pp2b = __byte_perm(B.y, C.x, 0x5432);
+            const uint2 C = *reinterpret_cast<const uint2*>(stage + j * G::kRowBytes + 16);   // X+8, X+12
+            const uint32_t pm5a = __byte_perm(A.x, A.y, 0x6543);
+            const uint32_t pp2  = __byte_perm(B.x, B.y, 0x5432);
+            const uint32_t pp5b = __byte_perm(C.x, C.y, 0x4321);
             // slots of the rows staged k steps ago
             const int r10 = (j + 1) % N, r7 = (j + 4) % N, r5 = (j + 6) % N, r3 = (j + 8) % N;
-            // chords, output row y = (row staged now) - 5:
-            //   i=0: s0 (+2,-5) vs s4 (-5,-2)      i=1: s9 (0,+5) vs s5 (-5,0)
-            //   i=2: s10 (+2,+5) vs s6 (-5,+2)     i=3: s7 (-4,+4) vs s11 (+4,+4)
-            const uint32_t u0a = vabs4(PP2a[r10], PM5a[r7]), u0b = vabs4(PP2b[r10], PM5b[r7]);
-            const uint32_t u1a = vabs4(B.x, PM5a[r5]),       u1b = vabs4(B.y, PM5b[r5]);
-            const uint32_t u2a = vabs4(pp2a, PM5a[r3]),      u2b = vabs4(pp2b, PM5b[r3]);
+            // chords (p in {a,c}, q in {b,d}), output row y = (row staged now) - 5:
+            //   pixels X..X+3:    i=0: s0 (+2,-5) | s4 (-5,-2)    i=1: s9 (0,+5) | s5  (-5,0)    i=2: s10 (+2,+5) | s6  (-5,+2)
+            //   pixels X+4..X+7:  i=0: s8 (-2,+5) | s12 (+5,+2)   i=1: s9 (0,+5) | s13 (+5,0)    i=2: s2  (-2,-5) | s14 (+5,-2)
+            //   both:             i=3: s7 (-4,+4) | s11 (+4,+4)
+            const uint32_t u0a = vabs4(PP2[r10], PM5a[r7]),  u0b = vabs4(pp2, PP5b[r3]);
+            const uint32_t u1a = vabs4(B.x, PM5a[r5]),       u1b = vabs4(B.y, PP5b[r5]);
+            const uint32_t u2a = vabs4(pp2, PM5a[r3]),       u2b = vabs4(PP2[r10], PP5b[r7]);
             const uint32_t u3a = vabs4(pWm1, pW1),           u3b = vabs4(pW0, pW2);
             const uint32_t sa = u0a + u1a + u2a + u3a + 0x78787878u;    // bit 7 of a lane: sum >= 8 (if no chord >= 8 ...)
             const uint32_t sb = u0b + u1b + u2b + u3b + 0x78787878u;
             const uint32_t big = (u0a | u1a | u2a | u3a | u0b | u1b | u2b | u3b) & 0xF8F8F8F8u;   // ... else caught here
             if ((((sa | sb) & 0x80808080u) | big) != 0) flagbits |= 1u << j;
-            PP2a[j] = pp2a; PP2b[j] = pp2b; PM5a[j] = pm5a; PM5b[j] = pm5b;
+            PP2[j] = pp2; PM5a[j] = pm5a; PP5b[j] = pp5b;
             pWm1 = A.y; pW0 = B.x; pW1 = B.y; pW2 = C.x;
         }
-
-        // hand the stage back (L2/L3 read global memory, not the ring)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
 
         // rows of this block that belong to the segment: output row of step j is ybase + j
         const int ybase = rbase + it * kBlkRows - 5;
         const int lo = max(ys - ybase, 0), hi = min(ye - ybase, kBlkRows);
         flagbits &= hi > lo && lane_valid ? ((1u << hi) - (1u << lo)) : 0u;
 
-        const uint32_t m = __ballot_sync(kFull, flagbits != 0);
-        if (m)
+        // one L2 unit per flagged 8-pixel row cell
+        if (flagbits)
         {
-            if (flagbits)
-                q->l2q[(q_tail + __popc(m & lt)) & (kL2QCap - 1)] = flagbits | ((uint32_t)lane << 11) | ((uint32_t)(ybase + 16) << 16);
-            q_tail += __popc(m);
-            if (q_tail - q_head >= 32u)
-                l2_phase(c, q, q_head, q_tail, cur_rows, cur_meta, l3_head, false, lane);
+            // unit = one-hot row bit << 5 | lane column (the consumer finds the row; which block a unit
+            // belongs to follows from its position in the queue)
+            uint32_t pos = atomicAdd(&q->l2_tail, (uint32_t)__popc(flagbits));
+            do
+            {
+                const uint32_t low = flagbits & (0u - flagbits);
+                flagbits ^= low;
+                q->l2q[pos++ & (kL2QCap - 1)] = (uint16_t)(low * 32u + (uint32_t)lane);
+            } while (flagbits);
+        }
+        __syncwarp();
+        const uint32_t tail = *(volatile uint32_t*)&q->l2_tail;
+        L.off2 = L.off1; L.off1 = L.off0; L.off0 = (uint32_t)s * G::kStageBytes + wi * kWarpPx + (kCHalo - 8);
+        L.ybase = ybase; L.mark = prev_mark;
+        // full batches; then whatever is left of the PREVIOUS block (its older stage is about to be handed back)
+        while (tail - q_head >= 32u)
+        {
+            l2_batch(c, L, q, q_head, 32u, lane);
+            q_head += 32u;
+            l3_phase(c, q, l3_head, false, lane);
+        }
+        if ((int)(prev_mark - q_head) > 0 || (tp.lookahead && tail != q_head))   // lookahead != 0: never carry cells over
+        {
+            l2_batch(c, L, q, q_head, tail - q_head, lane);
+            q_head = tail;
+            l3_phase(c, q, l3_head, false, lane);
+        }
+        prev_mark = tail;
+        // every cell of block it-1 is settled: this warp is done with the stage of block it-2
+        // (of block it-1 when cells are never carried over)
+        const int hold = tp.lookahead ? 1 : 2;
+        if (it >= hold) { release(it - hold, s_rel); if (++s_rel == nst) s_rel = 0; }
+        if (++s == nst) { s = 0; full_parity ^= 1; }
+    }
+    {
+        const uint32_t tail = *(volatile uint32_t*)&q->l2_tail;
+        while (tail != q_head)
+        {
+            const uint32_t n = min(32u, tail - q_head);
+            l2_batch(c, L, q, q_head, n, lane);
+            q_head += n;
+            l3_phase(c, q, l3_head, false, lane);
         }
     }
-    l2_phase(c, q, q_head, q_tail, cur_rows, cur_meta, l3_head, true, lane);
     l3_phase(c, q, l3_head, true, lane);
 }
 
@@ -432,7 +459,8 @@ cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32
     CUtensorMap map;
     *ok = make_cascade_map(&map, fs, G::kRowBytes);
     if (!*ok) return cudaSuccess;
-    const size_t smem = (size_t)tp.stages * G::kStageBytes + 2 * tp.stages * sizeof(uint64_t) + 16 + NW * sizeof(WarpQueues);
+    const size_t smem = (size_t)tp.stages * G::kStageBytes + tp.stages * sizeof(uint64_t) + ((tp.stages + 3) & ~3) * sizeof(uint32_t) +
+                        NW * sizeof(WarpQueues);
     if (smem > 48 * 1024)
     {
         // per device, idempotent and cheap: set on every launch rather than tracking devices
@@ -475,8 +503,9 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     }
     CascadeParams tp;
     tp.cap = cand_capacity;
-    tp.stages = env_int("MRG_B200_K1_STAGES", 3, 3, 12);
-    tp.lookahead = env_int("MRG_B200_K1_LOOKAHEAD", 1, 1, tp.stages - 2);
+    // a stage is handed back two blocks after it was consumed (L2 reads it), so 3 stages are always held
+    tp.lookahead = env_int("MRG_B200_K1_NOCARRY", 0, 0, 1);     // experiment: settle every cell in its own block (2 stages held)
+    tp.stages = env_int("MRG_B200_K1_STAGES", 4, tp.lookahead ? 3 : 4, 12);
     const int sw = kWarpPx * nw;
     tp.nstrips = (fs.w - kMargin + sw - 1) / sw;
     const int out_rows = fs.h - 2*kMargin;

@@ -17,7 +17,7 @@ python bench.py --frames 512 --gridn 14 --level 3 --steps 3 --warmup 3 --no-cpu-
 # ncu: launch list of the bench command (shares, not absolutes), then full captures of K1 and K2
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${R}_launches.csv \
     python bench.py --frames 1024 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $O/${R}_launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:chess_tiled -s 2 -c 1 -f -o $O/${R}_k1 \
+ncu --set full --clock-control none --import-source on -k regex:chess_cascade -s 2 -c 1 -f -o $O/${R}_k1 \
     python bench.py --frames 512 --chunk 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/${R}_k1_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cluster_find -s 2 -c 1 -f -o $O/${R}_k2 \
     python bench.py --frames 512 --chunk 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/${R}_k2_ncu.log 2>&1
