@@ -138,3 +138,30 @@ def blob_frame(w, h, seed=0, nblobs=None):
         f[y0:y1, x0:x1][sub] = v
     f += rng.normal(0.0, 2.0, size=f.shape).astype(np.float32)
     return box_blur3(np.clip(np.rint(f), 0, 255).astype(np.uint8))
+
+
+def circle_grid_frame(w, h, n=10, seed=0, noise_sigma=2.0, blur=True):
+    """n x n grid of dark discs on a light board (the calibration target mrgingham's blob mode is
+    for: find_blobs.cc:22 'black-on-white dots'), mild rotation, noise, optional 3x3 box blur."""
+    rng = np.random.default_rng(seed)
+    side = 0.8 * min(w, h)
+    theta = rng.uniform(-0.3, 0.3)
+    c, s_ = np.cos(theta), np.sin(theta)
+    pitch = side / (n + 1)
+    r = pitch * rng.uniform(0.22, 0.32)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    u = c * (xx - w / 2.0) + s_ * (yy - h / 2.0)
+    v = -s_ * (xx - w / 2.0) + c * (yy - h / 2.0)
+    f = np.full((h, w), float(BACKGROUND), dtype=np.float32)
+    f[(np.abs(u) <= side / 2) & (np.abs(v) <= side / 2)] = float(WHITE)
+    gu = (u + side / 2) / pitch
+    gv = (v + side / 2) / pitch
+    iu, iv = np.rint(gu), np.rint(gv)
+    inside = (iu >= 1) & (iu <= n) & (iv >= 1) & (iv <= n)
+    d2 = ((gu - iu) ** 2 + (gv - iv) ** 2) * pitch * pitch
+    edge = np.clip(r + 0.5 - np.sqrt(d2), 0.0, 1.0)                     # one-pixel anti-aliased rim
+    f = np.where(inside, f * (1 - edge) + float(BLACK) * edge, f)
+    if noise_sigma > 0:
+        f = f + rng.normal(0.0, noise_sigma, size=f.shape).astype(np.float32)
+    img = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+    return box_blur3(img) if blur else img

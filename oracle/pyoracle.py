@@ -61,6 +61,9 @@ def oracle_lib():
         _oracle.oracle_find_corners.restype = ctypes.c_int
         _oracle.oracle_refine_corners.restype = ctypes.c_int
         _oracle.oracle_pyramid.restype = ctypes.c_int
+        _oracle.blob_oracle_find_contours.restype = ctypes.c_int
+        _oracle.blob_oracle_centers.restype = ctypes.c_int
+        _oracle.blob_oracle_find_blobs.restype = ctypes.c_int
     return _oracle
 
 
@@ -124,6 +127,42 @@ def refine_corners(image, level, xy, levels):
     n = oracle_lib().oracle_refine_corners(_ptr(image, _u8p), h, w, image.strides[0], level,
                                            _ptr(xy, _f64p), _ptr(levels, _i8p), len(levels))
     return n, xy, levels
+
+
+# ---------------------------------------------------------------------------------------------
+# blob path (oracle/blob_oracle.c)
+# ---------------------------------------------------------------------------------------------
+def blob_find_contours(binary):
+    """cv2.findContours(binary, RETR_LIST, CHAIN_APPROX_NONE): list of (n,2) int32 arrays (x,y)"""
+    binary = _check_image(binary)
+    h, w = binary.shape
+    xy = np.empty((4 * w * h + 16, 2), dtype=np.int32)
+    lens = np.empty(w * h + 16, dtype=np.int32)
+    n = oracle_lib().blob_oracle_find_contours(_ptr(binary, _u8p), w, h, binary.strides[0], _ptr(xy, _i32p), len(xy),
+                                               _ptr(lens, _i32p), len(lens))
+    assert n >= 0
+    ends = np.cumsum(lens[:n])
+    return [xy[e - l:e].copy() for e, l in zip(ends, lens[:n])]
+
+
+def blob_centers(image, thresh, cap=1 << 16):
+    """SimpleBlobDetector::findBlobs for one threshold: (n,4) float64 rows x, y, radius, confidence"""
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.empty((cap, 4), dtype=np.float64)
+    n = oracle_lib().blob_oracle_centers(_ptr(image, _u8p), w, h, image.strides[0], int(thresh), _ptr(out, _f64p), cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def find_blobs(image, cap=1 << 16):
+    """find_blobs_from_image_array: (N,2) int32 PointInt list (x,y scaled by 1000), reference order"""
+    image = _check_image(image)
+    h, w = image.shape
+    xy = np.empty((cap, 2), dtype=np.int32)
+    n = oracle_lib().blob_oracle_find_blobs(_ptr(image, _u8p), w, h, image.strides[0], _ptr(xy, _i32p), cap)
+    assert n >= 0
+    return xy[:n].copy()
 
 
 # ---------------------------------------------------------------------------------------------

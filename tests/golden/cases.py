@@ -41,3 +41,22 @@ def refine_chain(find_fn, refine_fn, image, start_level):
         if n <= 0:
             break
     return xy, levels, np.asarray(counts, dtype=np.int32)
+
+
+def blob_golden_images():
+    """name -> uint8 image for tests/golden/blobs_v1.npz (the blob path)."""
+    out = {}
+    out["circles_vga_n10"] = synth.circle_grid_frame(640, 480, 10, seed=1)
+    out["circles_small_n7"] = synth.circle_grid_frame(331, 257, 7, seed=2)
+    out["circles_noblur"] = synth.circle_grid_frame(400, 300, 8, seed=3, noise_sigma=5.0, blur=False)
+    out["board_vga_n10"] = synth.board_frame(640, 480, 10, seed=0)       # black squares qualify as blobs
+    out["board_n14"] = synth.board_frame(512, 512, 14, seed=7)
+    out["blobs"] = synth.blob_frame(300, 200, seed=19)
+    out["blobs_dense"] = synth.blob_frame(257, 193, seed=29, nblobs=120)
+    out["blurred_noise"] = synth.blurred_noise_frame(240, 200, seed=13)
+    out["noise"] = synth.noise_frame(120, 90, seed=11)
+    out["checker8"] = synth.checker_frame(256, 192, period=8, seed=15)
+    out["tiny_9x7"] = synth.noise_frame(9, 7, seed=31)
+    out["flat"] = np.full((64, 64), 128, dtype=np.uint8)
+    out["all_dark"] = np.full((40, 50), 10, dtype=np.uint8)
+    return out
