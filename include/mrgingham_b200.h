@@ -44,9 +44,9 @@ void mrgingham_ChESS_response_5(int16_t*       response,
 
 /* Replaces mrgingham_pywrap_cplusplus_bridge.cc:28-70 (declared in
    mrgingham_pywrap_cplusplus_bridge.h:10-23): the C bridge the reference's Python module binds.
-   Returns false when nothing was found, on error, or when doblobs is set (the blob detector is
-   not built yet: see DESIGN.md, scope); otherwise calls
-   add_points(xy, N, 1/1000., cookie) once and returns its result. */
+   Returns false when nothing was found or on error (doblobs with a level other than 0 is one:
+   ...bridge.cc:50-56); otherwise calls add_points(xy, N, 1/1000., cookie) once and returns its
+   result. doblobs selects the blob detector (find_blobs.cc:14-46) instead of the corner detector. */
 bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols,
                                                 int stride,
                                                 char* imagebuffer, /* const */
@@ -75,6 +75,14 @@ int mrg_b200_find_chessboard_corners(const uint8_t* image, int Nrows, int Ncols,
 int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride,
                                        int image_pyramid_level,
                                        double* xy_inout, signed char* level, int Npoints);
+
+/* mrgingham::find_blobs_from_image_array(), find_blobs.cc:14-46: cv::SimpleBlobDetector with
+   minArea=20, maxArea=80000, minDistBetweenBlobs=5, blobColor=0, OpenCV defaults otherwise
+   (behaviour pinned to OpenCV 4.13.0, which is what oracle/blob_oracle.c is checked against).
+   Returns the number of blobs (<0 on a CUDA failure); writes min(N, cap) points into xy_out as
+   (x,y) pairs scaled by 1000, in the reference's keypoint order. */
+int mrg_b200_find_blobs(const uint8_t* image, int Nrows, int Ncols, int stride,
+                        int* xy_out, int cap);
 
 /* ===========================================================================================
    C. Batched / device-resident entry points (additive)
@@ -138,6 +146,15 @@ int mrg_b200_refine_corners_batch(mrg_b200_detector* det,
                                   double* xy_inout, signed char* levels, int npoints,
                                   int32_t* nrefined_out, void* stream);
 
+/* Blob detection over a batch of equally-sized frames (the batched form of mrg_b200_find_blobs();
+   arguments as for mrg_b200_find_corners_batch()). Synchronous. Returns 0 or <0. */
+int mrg_b200_find_blobs_batch(mrg_b200_detector* det,
+                              const uint8_t* images, int images_on_device,
+                              int nframes, int rows, int cols,
+                              size_t row_pitch, size_t frame_stride,
+                              int32_t* xy_out, int32_t* counts_out,
+                              void* stream);
+
 /* Dense ChESS response over a batch (the batched form of section A's function).
    response: int16 [nframes][rows][cols]; elements outside the 7-pixel interior are not written. */
 int mrg_b200_chess_response_batch(mrg_b200_detector* det,
@@ -156,7 +173,7 @@ int mrg_b200_pyramid_level(mrg_b200_detector* det,
 
 /* Accumulated device time (CUDA events on the launching stream) of the kernels launched by the
    most recent batch call, and how many kernels that call launched. which: 0 = ChESS+candidate
-   kernel, 1 = clustering kernel, 2 = pyramid kernel. */
+   kernel, 1 = clustering kernel, 2 = pyramid kernel, 3 = the blob kernels (time only). */
 int mrg_b200_last_kernel_ms(mrg_b200_detector* det, int which, float* ms, int* launches);
 void mrg_b200_set_profiling(mrg_b200_detector* det, int enabled);
 

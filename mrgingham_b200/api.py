@@ -20,7 +20,7 @@ EXPORTS = (
     "mrg_b200_find_chessboard_corners", "mrg_b200_refine_chessboard_corners",
     "mrg_b200_detector_create", "mrg_b200_detector_destroy",
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
-    "mrg_b200_refine_corners_batch",
+    "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch",
     "mrg_b200_chess_response_batch", "mrg_b200_pyramid_level",
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
     "mrg_b200_device_count",
@@ -71,6 +71,11 @@ def lib():
     L.mrg_b200_find_corners_batch_collect.argtypes = [ctypes.c_void_p, _i32p, _i32p]
     L.mrg_b200_refine_corners_batch.restype = ctypes.c_int
     L.mrg_b200_refine_corners_batch.argtypes = batch_args + [_f64p, _i8p, ctypes.c_int, _i32p, ctypes.c_void_p]
+    L.mrg_b200_find_blobs.restype = ctypes.c_int
+    L.mrg_b200_find_blobs.argtypes = [_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, ctypes.c_int]
+    L.mrg_b200_find_blobs_batch.restype = ctypes.c_int
+    L.mrg_b200_find_blobs_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_size_t, ctypes.c_size_t, _i32p, _i32p, ctypes.c_void_p]
     L.mrg_b200_chess_response_batch.restype = ctypes.c_int
     L.mrg_b200_chess_response_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
@@ -187,6 +192,19 @@ def find_chessboard_corners_int(image, image_pyramid_level=0, cap=1 << 16):
     return xy[:n].copy()
 
 
+def find_blobs_int(image, cap=1 << 14):
+    """mrgingham::find_blobs_from_image_array (find_blobs.cc:14-46): (N,2) int32 PointInt list (x1000)"""
+    image = _check_image(image, ndim_exact=2)
+    _require_gpu()
+    xy = np.empty((cap, 2), dtype=np.int32)
+    n = lib().mrg_b200_find_blobs(_ptr(image, _u8p), image.shape[0], image.shape[1], image.strides[0], _ptr(xy, _i32p), cap)
+    if n < 0:
+        raise RuntimeError("mrg_b200_find_blobs() failed")
+    if n > cap:
+        return find_blobs_int(image, cap=n)
+    return xy[:n].copy()
+
+
 def refine_chessboard_corners(image, image_pyramid_level, xy, levels):
     """mrgingham::refine_chessboard_corners_from_image_array: returns (nrefined, xy', levels')"""
     image = _check_image(image, ndim_exact=2)
@@ -259,6 +277,17 @@ class Detector:
         """returns (xy int32 [n, max_points, 2] scaled by 1000, counts int32 [n])"""
         self.enqueue(images, level, stream)
         return self.collect()
+
+    def find_blobs(self, images, stream=None):
+        """batched blob detector: returns (xy int32 [n, max_points, 2] scaled by 1000, counts int32 [n])"""
+        ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
+        xy = np.empty((n, self.max_points, 2), dtype=np.int32)
+        counts = np.zeros(n, dtype=np.int32)
+        rc = lib().mrg_b200_find_blobs_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride,
+                                             _ptr(xy, _i32p), _ptr(counts, _i32p), ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_find_blobs_batch() failed")
+        return xy, counts
 
     def refine_corners(self, images, level, xy, levels, stream=None):
         """batched refinement: xy float64 [n, npoints, 2], levels int8 [n, npoints];

@@ -14,7 +14,7 @@ HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + \
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3,-ffp-contract=off",
     "-cudart", "static",
 ]
 

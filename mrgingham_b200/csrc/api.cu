@@ -115,6 +115,8 @@ struct mrg_b200_detector
 
     bool profiling = false;
     KernelTimer timers[3];
+    BlobWorkspace* blobs = nullptr;
+    float blob_ms = 0;
 
     struct Pending
     {
@@ -391,6 +393,7 @@ API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detecto
 
 API void mrg_b200_detector_destroy(mrg_b200_detector* det)
 {
+    if (det && det->blobs) { cudaSetDevice(det->device); blob_workspace_destroy(det->blobs); det->blobs = nullptr; }
     if (!det) return;
     cudaSetDevice(det->device);
     cudaDeviceSynchronize();
@@ -500,8 +503,9 @@ API int mrg_b200_pyramid_level(mrg_b200_detector* det, const uint8_t* image, int
 
 API int mrg_b200_last_kernel_ms(mrg_b200_detector* det, int which, float* ms, int* launches)
 {
-    if (!det || which < 0 || which > 2) return -1;
+    if (!det || which < 0 || which > 3) return -1;
     std::lock_guard<std::mutex> g(det->mtx);
+    if (which == 3) { if (ms) *ms = det->blob_ms; if (launches) *launches = 0; return 0; }
     if (ms) *ms = det->timers[which].ms;
     if (launches) *launches = det->timers[which].launches;
     return 0;
@@ -523,6 +527,35 @@ API int mrg_b200_device_count(void)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 0;
     return ndev;
+}
+
+API int mrg_b200_find_blobs_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                  int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                  int32_t* xy_out, int32_t* counts_out, void* stream_)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    if (nframes < 0 || rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767 || row_pitch < (size_t)cols)
+    { MSG("Bad batch geometry (nframes=%d rows=%d cols=%d pitch=%zu).", nframes, rows, cols, row_pitch); return -1; }
+    CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+    if (!det->blobs) det->blobs = blob_workspace_create();
+    det->blob_ms = 0;
+    // the blob scratch is ~70 MB per 4K frame: chunks of at most 16 frames
+    const int chunk = std::max(1, std::min(det->cfg.max_frames, 16));
+    const int mp = det->cfg.max_points;
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        FrameSet fs;
+        if (stage_frames(det, det->slot[0], images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride,
+                         0, stream, stream, &fs)) return -1;
+        float ms = 0;
+        if (blob_find_frames(det->blobs, fs, xy_out + (size_t)f0 * 2 * mp, counts_out + f0, mp, stream, det->profiling ? &ms : nullptr)) return -1;
+        det->blob_ms += ms;
+    }
+    return 0;
 }
 
 // =================================================================================================
@@ -565,6 +598,24 @@ API int mrg_b200_find_chessboard_corners(const uint8_t* image, int Nrows, int Nc
     return n;
 }
 
+API int mrg_b200_find_blobs(const uint8_t* image, int Nrows, int Ncols, int stride, int* xy_out, int cap)
+{
+    if (Nrows <= 0 || Ncols <= 0 || stride < Ncols) { MSG("Bad image geometry."); return 0; }
+    std::lock_guard<std::mutex> g(g_default_mtx);
+    mrg_b200_detector* det = default_detector();
+    if (!det) return -1;
+    for (;;)
+    {
+        const int mp = det->cfg.max_points;
+        std::vector<int32_t> xy((size_t)2 * mp);
+        int32_t n = 0;
+        if (mrg_b200_find_blobs_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, xy.data(), &n, nullptr)) return -1;
+        if (n > mp) { det->cfg.max_points = next_pow2(n); continue; }
+        for (int i = 0; i < n && i < cap; i++) { xy_out[2*i] = xy[2*i]; xy_out[2*i + 1] = xy[2*i + 1]; }
+        return n;
+    }
+}
+
 API bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols, int stride, char* imagebuffer,
                                                     int image_pyramid_level, bool doblobs, bool debug,
                                                     bool (*add_points)(int* xy, int N, double scale, void* cookie), void* cookie)
@@ -572,9 +623,18 @@ API bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols, int st
     (void)debug; // the reference's debug mode only writes /tmp dumps
     if (doblobs)
     {
+        // mrgingham_pywrap_cplusplus_bridge.cc:50-56: blobs only at level 0, via find_blobs_from_image_array()
         if (image_pyramid_level != 0) return false;
-        MSG("The blob detector is not part of this build (chessboard corners only).");
-        return false;
+        int bcap = 4096;
+        std::vector<int> bxy((size_t)2 * bcap);
+        int bn = mrg_b200_find_blobs((const uint8_t*)imagebuffer, Nrows, Ncols, stride, bxy.data(), bcap);
+        if (bn > bcap)
+        {
+            bcap = bn; bxy.resize((size_t)2 * bcap);
+            bn = mrg_b200_find_blobs((const uint8_t*)imagebuffer, Nrows, Ncols, stride, bxy.data(), bcap);
+        }
+        if (bn <= 0) return false;
+        return (*add_points)(bxy.data(), bn, 1.0 / kFindGridScale, cookie);
     }
     int cap = 4096;
     std::vector<int> xy((size_t)2 * cap);

@@ -91,6 +91,16 @@ cudaError_t launch_cluster_refine(const FrameSet& fs, const ClusterParams& p,
                                   double* points_xy, signed char* levels, int npoints,
                                   int32_t* out_refined, cudaStream_t stream);
 
+// Blob path (find_blobs.cc:14-46 = cv::SimpleBlobDetector): blobs.cu. The workspace owns the device
+// scratch (bit planes, mark planes, border points, records) and grows it on demand.
+struct BlobWorkspace;
+BlobWorkspace* blob_workspace_create();
+void           blob_workspace_destroy(BlobWorkspace* ws);
+// xy_out: HOST int32 [nframes][max_points][2] scaled by 1000, counts_out: HOST int32 [nframes].
+// Synchronous on `stream`. ms_out (optional): device time of the three kernels (CUDA events).
+int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
+                     cudaStream_t stream, float* ms_out);
+
 // shared-memory candidate capacity of the clustering kernel (lists up to this size never touch
 // the global scratch)
 constexpr int kClusterSmemCands = 4096;

@@ -1,0 +1,103 @@
+"""GPU parity tests of the blob path through the C ABI: the CUDA
+detector against the committed cv2.SimpleBlobDetector golden vectors and against the CPU oracle
+(oracle/blob_oracle.c) on seeded frames, single-image, batched, device-resident and strided."""
+import os
+
+import numpy as np
+import pytest
+
+from mrgingham_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "blobs_v1.npz"))
+NAMES = sorted(k[4:] for k in GOLD.files if k.startswith("img/"))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from mrgingham_b200 import api as a
+    a._require_gpu()
+    return a
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import pyoracle as po
+    return po
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_blobs_match_golden(api, name):
+    got = api.find_blobs_int(np.ascontiguousarray(GOLD["img/" + name]))
+    want = GOLD["pts/" + name]
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    assert np.array_equal(got, want), name
+
+
+def test_find_points_blobs_mirror(api):
+    img = np.ascontiguousarray(GOLD["img/circles_vga_n10"])
+    xy = api.find_points(img, blobs=True)
+    assert np.array_equal(xy, GOLD["pts/circles_vga_n10"].astype(np.float64) * (1.0 / 1000))
+    with pytest.raises(RuntimeError):
+        api.find_points(img, image_pyramid_level=1, blobs=True)
+
+
+def test_blobs_batch_matches_oracle(api, oracle):
+    frames = np.stack([synth.circle_grid_frame(800, 608, 10, seed=40), synth.board_frame(800, 608, 10, seed=41),
+                       synth.blob_frame(800, 608, seed=42), synth.blurred_noise_frame(800, 608, seed=43)])
+    det = api.Detector(max_frames=3, max_points=4096)      # 4 frames in chunks of 3
+    xy, counts = det.find_blobs(frames)
+    for i in range(len(frames)):
+        want = oracle.find_blobs(frames[i])
+        assert counts[i] == len(want), (i, counts[i], len(want))
+        assert np.array_equal(xy[i, :counts[i]], want), i
+    assert counts[0] == 100
+    det.close()
+
+
+def test_blobs_device_resident_and_strided(api, oracle):
+    import torch
+    base = np.stack([synth.circle_grid_frame(640, 480, 9, seed=50 + s) for s in range(2)])
+    wide = np.zeros((2, 480, 704), np.uint8)
+    wide[:, :, 3:643] = base
+    t = torch.from_numpy(wide).cuda()[:, :, 3:643]          # unaligned device view with a pitch
+    det = api.Detector(max_frames=2, max_points=2048)
+    xy, counts = det.find_blobs(t)
+    xy2, counts2 = det.find_blobs(wide[:, :, 3:643])         # same thing from the host
+    for i in range(2):
+        want = oracle.find_blobs(np.ascontiguousarray(base[i]))
+        assert counts[i] == len(want) and np.array_equal(xy[i, :counts[i]], want)
+        assert counts2[i] == len(want) and np.array_equal(xy2[i, :counts2[i]], want)
+    det.close()
+
+
+def test_blobs_noise_overflows_default_scratch(api, oracle):
+    # uniform noise: a huge number of tiny borders per threshold
+    frames = synth.noise_frame(640, 480, seed=60)[None]
+    det = api.Detector(max_frames=1, max_points=4096)
+    xy, counts = det.find_blobs(frames)
+    want = oracle.find_blobs(frames[0])
+    assert counts[0] == len(want) and np.array_equal(xy[0, :counts[0]], want)
+    det.close()
+
+
+def test_blobs_4k_board(api, oracle):
+    frame = synth.board_frame(3840, 2160, 14, seed=70)
+    got = api.find_blobs_int(frame)
+    want = oracle.find_blobs(frame)
+    assert len(want) > 50
+    assert np.array_equal(got, want)
+
+
+def test_blobs_tiny_and_empty(api, oracle):
+    det = api.Detector(max_frames=4)
+    for (w, h) in ((1, 1), (2, 3), (5, 5), (33, 7), (64, 1)):
+        frames = np.stack([synth.noise_frame(w, h, seed=s) for s in range(3)])
+        xy, counts = det.find_blobs(frames)
+        for i in range(3):
+            want = oracle.find_blobs(frames[i])
+            assert counts[i] == len(want) and np.array_equal(xy[i, :counts[i]], want)
+    xy, counts = det.find_blobs(np.zeros((0, 16, 16), np.uint8))
+    assert len(counts) == 0
+    det.close()
