@@ -94,9 +94,24 @@ struct Plane
 {
     const uint32_t* B; uint32_t* V; uint32_t* R;
     int w, h, wpr;
-    __device__ bool fg(int x, int y) const
+    // bits (x-1, x, x+1) of row y as bits 0..2; 0 outside the image
+    __device__ uint32_t row3(int x, int y) const
     {
-        return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h && ((B[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u);
+        if ((unsigned)y >= (unsigned)h) return 0;
+        const uint32_t* r = B + (size_t)y * wpr;
+        const int wd = x >> 5, b = x & 31;
+        const uint32_t c = r[wd];
+        uint32_t v = b ? (c >> (b - 1)) & 7u : (c << 1) & 6u;
+        if (b == 0 && wd > 0) v |= r[wd - 1] >> 31;
+        if (b == 31 && wd + 1 < wpr) v |= (r[wd + 1] & 1u) << 2;
+        return v;       // bits beyond w are zero in the plane already
+    }
+    // bit d = the neighbour of (x, y) in direction d (0 = E, 1 = NE, 2 = N, 3 = NW, 4 = W, 5 = SW, 6 = S, 7 = SE) is foreground
+    __device__ uint32_t nbr8(int x, int y) const
+    {
+        const uint32_t up = row3(x, y - 1), mid = row3(x, y), dn = row3(x, y + 1);
+        return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) |
+               ((mid & 1u) << 4) | ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
     }
     __device__ bool visited(int x, int y) const { return (V[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u; }
     __device__ bool rflag(int x, int y) const { return (R[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u; }
@@ -137,8 +152,19 @@ struct Tracer
             return true;
         };
 
-        int s_end = is_hole ? 0 : 4, s = s_end, x1, y1;
-        do { s = (s - 1) & 7; x1 = x0 + kDx[s]; y1 = y0 + kDy[s]; } while (!P.fg(x1, y1) && s != s_end);
+        // neighbour search on an 8-bit mask of the 3x3 neighbourhood (bit d = direction d is
+        // foreground): the three rows are fetched with independent loads, the rotation is bit math
+        int s_end = is_hole ? 0 : 4, s, x1, y1;
+        {
+            // first neighbour clockwise from s_end: directions s_end-1, s_end-2, ..., s_end (mod 8)
+            const uint32_t m = P.nbr8(x0, y0);
+            const uint32_t rot = ((m | (m << 8)) >> s_end) & 0xFFu;          // bit j = direction s_end + j
+            // clockwise order = j = 7, 6, ..., 1: the highest set bit (direction s_end itself, j = 0, is
+            // background at every start the scan can produce); none = isolated pixel
+            const int hb = rot ? 31 - __clz(rot) : 0;
+            s = (s_end + hb) & 7;
+            x1 = x0 + kDx[s]; y1 = y0 + kDy[s];
+        }
         if (s == s_end)
         {
             P.set_visited(x0, y0); P.set_rflag(x0, y0);          // isolated pixel
@@ -150,9 +176,13 @@ struct Tracer
             for (;;)
             {
                 s_end = s;
-                int x4, y4;
-                for (;;) { ++s; x4 = x3 + kDx[s & 7]; y4 = y3 + kDy[s & 7]; if (P.fg(x4, y4)) break; }
-                s &= 7;
+                // first neighbour counter-clockwise from s+1: directions s+1, s+2, ... (mod 8)
+                const uint32_t m = P.nbr8(x3, y3);
+                const uint32_t rot = ((m | (m << 8)) >> ((s + 1) & 7)) & 0xFFu;   // bit j = direction s + 1 + j
+                const int j = __ffs(rot) - 1;                                    // a neighbour always exists: we came from one
+                const int s_raw = s + 1 + j;                                     // what the original's ++s loop ends on (<= 15)
+                s = s_raw & 7;
+                const int x4 = x3 + kDx[s], y4 = y3 + kDy[s];
                 if ((unsigned)(s - 1) < (unsigned)s_end) { P.set_visited(x3, y3); P.set_rflag(x3, y3); }
                 else if (!P.visited(x3, y3)) P.set_visited(x3, y3);
                 if (!emit(x3, y3)) return false;
