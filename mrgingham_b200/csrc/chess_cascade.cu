@@ -135,7 +135,8 @@ struct StripCtx
 {
     const uint8_t* img;     // the frame
     int pitch, w;
-    int x0;                 // first pixel of this warp's 256-pixel sub-strip
+    int x0;                 // first pixel of this warp's first 8-pixel cell
+    int cell_pitch;         // pixels between the cells of consecutive lanes
     int ys, ye;             // output rows of the segment
     cand_t* out; uint32_t* count; int cap;
 };
@@ -194,8 +195,8 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
         const uint32_t u = q->l2q[(head + lane) & (kL2QCap - 1)];
         const int col = u & 31, j = 31 - __clz(u >> 5);
         const bool cur = (int)(head + lane - L.mark) >= 0;
-        const uint32_t sA = (cur ? L.off0 : L.off1) + kLanePx * col, sB = (cur ? L.off1 : L.off2) + kLanePx * col;
-        const int y = (cur ? L.ybase : L.ybase - kBlkRows) + j, X = c.x0 + kLanePx * col;
+        const uint32_t sA = (cur ? L.off0 : L.off1) + c.cell_pitch * col, sB = (cur ? L.off1 : L.off2) + c.cell_pitch * col;
+        const int y = (cur ? L.ybase : L.ybase - kBlkRows) + j, X = c.x0 + c.cell_pitch * col;
         // ring row y+dy was staged (5 - dy) steps before step j: in block B if j >= 5 - dy, else in B-1
         uint2 A[7], B[7], C[7];
         const int behind[7] = { 10, 9, 7, 5, 3, 1, 0 };
@@ -287,7 +288,11 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
 
     StripCtx c;
     c.img = fs.base + (size_t)f * fs.frame_stride; c.pitch = fs.pitch; c.w = fs.w;
-    c.x0 = xs + wi * kWarpPx; c.ys = ys; c.ye = ye;
+    // The 8-pixel cells of the strip are dealt to the warps round-robin (lane l of warp w owns cell
+    // NW*l + w): an edge that crosses the strip then loads every warp alike, which keeps the warps
+    // of a CTA, who share the staged rows, in step. 64-bit shared loads at this lane pitch are
+    // still bank-conflict free (16 lanes x 24 or 16 bytes cover the 32 banks once).
+    c.x0 = xs + wi * kLanePx; c.cell_pitch = NW * kLanePx; c.ys = ys; c.ye = ye;
     c.out = cand + (size_t)f * tp.cap; c.count = counts + f; c.cap = tp.cap;
 
     // One thread requests block `it` into its stage. The ring is filled once here; after that a
@@ -319,8 +324,8 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
     if (tid == 0)
         for (int it = 0; it < nst && it < nit; it++) issue(it, it);
 
-    // byte offset, in a staged row, of this lane's byte X-8 (X = c.x0 + 8*lane)
-    const int lane_off = wi * kWarpPx + kLanePx * lane + (kCHalo - 8);
+    // byte offset, in a staged row, of this lane's byte X-8 (X = c.x0 + cell_pitch*lane)
+    const int lane_off = wi * kLanePx + NW * kLanePx * lane + (kCHalo - 8);
 
     // Register window (slot = step at which the row was staged). The two words of a lane use mirrored
     // chords so that they share one PRMT'd word per row (bytes X+2..X+5 are dx = +2 for pixels X..X+3
@@ -338,7 +343,7 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
     L2Ctx L;
     L.ring = ring; L.off0 = L.off1 = L.off2 = 0; L.row_bytes = G::kRowBytes;
     // cells without a pixel in [7,w-7) are never tested (their row bytes may lie beyond the pitch)
-    const bool lane_valid = c.x0 + kLanePx * lane < fs.w - kMargin;
+    const bool lane_valid = c.x0 + c.cell_pitch * lane < fs.w - kMargin;
 
     int s = 0, s_rel = 0;          // stage of block it / of the block released next
     uint32_t full_parity = 0;
@@ -398,7 +403,7 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
         }
         __syncwarp();
         const uint32_t tail = *(volatile uint32_t*)&q->l2_tail;
-        L.off2 = L.off1; L.off1 = L.off0; L.off0 = (uint32_t)s * G::kStageBytes + wi * kWarpPx + (kCHalo - 8);
+        L.off2 = L.off1; L.off1 = L.off0; L.off0 = (uint32_t)s * G::kStageBytes + wi * kLanePx + (kCHalo - 8);
         L.ybase = ybase; L.mark = prev_mark;
         // full batches; then whatever is left of the PREVIOUS block (its older stage is about to be handed back)
         while (tail - q_head >= 32u)
