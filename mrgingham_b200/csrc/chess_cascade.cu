@@ -16,12 +16,12 @@
 //   L1 (every pixel; 4 pixels per instruction in byte lanes): one chord |p-q| per i, chosen so
 //      that three of the eight samples are aligned 32-bit words of the staged rows and the other
 //      five come from two PRMT'd words per row. response > 15 needs sum_i |p_i-q_i| >= 8. The four
-//      VABSDIFF4 results are added as packed bytes; a lane whose sum could wrap has some chord >= 8
-//      and is caught by OR-ing the chords, so the packed test never misses. ~5 % of the pixels
-//      of a board frame (the neighbourhood of edges) pass.
+//      VABSDIFF4 results are added as packed bytes; a lane can only wrap if some chord is large, and
+//      then the sum of all the word's chord bytes (IDP.4A, FMA pipe) is >= 32 and flags the word, so
+//      the packed test never misses. ~5 % of the pixels of a board frame (edge neighbourhoods) pass.
 //   L2 (8-pixel row cells flagged by L1, compacted so that all 32 lanes work): all sixteen
-//      VABSDIFF4 chords/diameters in byte lanes, widened into 16-bit lanes and summed exactly;
-//      needs sum >= 16. ~0.05 % of the pixels pass.
+//      VABSDIFF4 chords/diameters in byte lanes, summed exactly per pixel with IDP.4A dot products
+//      (FMA pipe); needs sum >= 16. ~0.05 % of the pixels pass.
 //   L3 (those pixels, compacted again): the exact scalar response as ChESS.c:62-105 computes it;
 //      pixels with response > 15 inside [7,w-7) x [7,h-7) are appended to the frame's candidate list.
 //
@@ -94,8 +94,6 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity)
 }
 
 __device__ __forceinline__ uint32_t vabs4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
-__device__ __forceinline__ uint32_t ev(uint32_t d) { return d & 0x00FF00FFu; }                 // [d0,0,d2,0]
-__device__ __forceinline__ uint32_t od(uint32_t d) { return __byte_perm(d, 0, 0x4341); }       // [d1,0,d3,0]
 
 // exact response of the pixel at c (ChESS.c:62-105), read straight from global memory
 __device__ __forceinline__ int chess_exact(const uint8_t* __restrict__ c, int pitch)
@@ -116,18 +114,29 @@ __device__ __forceinline__ int chess_exact(const uint8_t* __restrict__ c, int pi
 }
 
 // L2 arithmetic for four pixels held in byte lanes: s[k] = ring sample k of the four pixels.
-// Returns 16-bit lanes T + 0x7FF0 (bit 15 set iff T >= 16), T = sum of chords - sum of diameters;
-// e = pixels 0 and 2, o = pixels 1 and 3. |T| <= 2040, so the lanes never interact.
-__device__ __forceinline__ void l2_word(const uint32_t (&s)[16], uint32_t& e, uint32_t& o)
+// T[p] += sum of chords - sum of diameters of pixel p (|T| <= 2040). The sixteen VABSDIFF4 run on
+// the ALU pipe; the per-pixel sums are taken with IDP.4A (dot product with a one-hot +-1 byte
+// vector), which runs on the otherwise idle FMA pipe -- the kernel is ALU-pipe bound.
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, int b_s8x4, int c)
 {
-    e = 0x7FF07FF0u; o = 0x7FF07FF0u;
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void l2_word(const uint32_t (&s)[16], int (&T)[4])
+{
 #pragma unroll
     for (int i = 0; i < 4; i++)
     {
         const uint32_t u0 = vabs4(s[i], s[i + 4]),  u1 = vabs4(s[i + 8], s[i + 12]);
         const uint32_t v0 = vabs4(s[i], s[i + 8]),  v1 = vabs4(s[i + 4], s[i + 12]);
-        e = e + ev(u0) + ev(u1); e = e - ev(v0) - ev(v1);
-        o = o + od(u0) + od(u1); o = o - od(v0) - od(v1);
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+        {
+            const int plus = 1 << (8 * p), minus = (int)(0xFFu << (8 * p));
+            T[p] = dp4a_us(u0, plus, T[p]);  T[p] = dp4a_us(u1, plus, T[p]);
+            T[p] = dp4a_us(v0, minus, T[p]); T[p] = dp4a_us(v1, minus, T[p]);
+        }
     }
 }
 
@@ -209,7 +218,8 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
             B[k] = *reinterpret_cast<const uint2*>(p + 8);    // X,   X+4
             C[k] = *reinterpret_cast<const uint2*>(p + 16);   // X+8, X+12
         }
-        uint32_t s[16], e0, o0, e1, o1;
+        uint32_t s[16];
+        int T0[4] = { 0, 0, 0, 0 }, T1[4] = { 0, 0, 0, 0 };
         // pixels X..X+3
         s[0]  = __byte_perm(B[0].x, B[0].y, 0x5432); s[1]  = B[0].x; s[2]  = __byte_perm(A[0].y, B[0].x, 0x5432);
         s[3]  = A[1].y;                              s[15] = B[1].y;
@@ -218,7 +228,7 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
         s[6]  = __byte_perm(A[4].x, A[4].y, 0x6543); s[12] = __byte_perm(B[4].y, C[4].x, 0x4321);
         s[7]  = A[5].y;                              s[11] = B[5].y;
         s[8]  = __byte_perm(A[6].y, B[6].x, 0x5432); s[9]  = B[6].x; s[10] = __byte_perm(B[6].x, B[6].y, 0x5432);
-        l2_word(s, e0, o0);
+        l2_word(s, T0);
         // pixels X+4..X+7: everything one word to the right
         s[0]  = __byte_perm(B[0].y, C[0].x, 0x5432); s[1]  = B[0].y; s[2]  = __byte_perm(B[0].x, B[0].y, 0x5432);
         s[3]  = B[1].x;                              s[15] = C[1].x;
@@ -227,13 +237,14 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
         s[6]  = __byte_perm(A[4].y, B[4].x, 0x6543); s[12] = __byte_perm(C[4].x, C[4].y, 0x4321);
         s[7]  = B[5].x;                              s[11] = C[5].x;
         s[8]  = __byte_perm(B[6].x, B[6].y, 0x5432); s[9]  = B[6].y; s[10] = __byte_perm(B[6].y, C[6].x, 0x5432);
-        l2_word(s, e1, o1);
+        l2_word(s, T1);
 
-        if ((e0 | o0 | e1 | o1) & 0x80008000u)
+        if (max(max(max(T0[0], T0[1]), max(T0[2], T0[3])), max(max(T1[0], T1[1]), max(T1[2], T1[3]))) >= 16)
         {
             // rare: some of the eight pixels go on to the exact test. bit p of `hits` = pixel X+p
-            uint32_t hits = ((e0 >> 15) & 1) | ((o0 >> 14) & 2) | ((e0 >> 29) & 4) | ((o0 >> 28) & 8) |
-                            ((e1 >> 11) & 16) | ((o1 >> 10) & 32) | ((e1 >> 25) & 64) | ((o1 >> 24) & 128);
+            uint32_t hits = 0;
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) hits |= (uint32_t)(T0[pp] >= 16) << pp | (uint32_t)(T1[pp] >= 16) << (4 + pp);
             while (hits)
             {
                 const int pp = __ffs(hits) - 1;
@@ -375,10 +386,15 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
             const uint32_t u1a = vabs4(B.x, PM5a[r5]),       u1b = vabs4(B.y, PP5b[r5]);
             const uint32_t u2a = vabs4(pp2, PM5a[r3]),       u2b = vabs4(PP2[r10], PP5b[r7]);
             const uint32_t u3a = vabs4(pWm1, pW1),           u3b = vabs4(pW0, pW2);
-            const uint32_t sa = u0a + u1a + u2a + u3a + 0x78787878u;    // bit 7 of a lane: sum >= 8 (if no chord >= 8 ...)
+            // packed byte sums: bit 7 of a lane of sa/sb = that pixel's four chords sum to >= 8, PROVIDED no
+            // lane can wrap, i.e. every chord <= 31 (4*31 + 0x78 < 256). That is what ha/hb guarantee: the
+            // sum of all sixteen chord bytes of a word (IDP.4A against 1,1,1,1 -- FMA pipe, which idles
+            // otherwise) is < 32. A word with ha >= 32 holds a chord sum >= 8 anyway and is flagged.
+            const uint32_t sa = u0a + u1a + u2a + u3a + 0x78787878u;
             const uint32_t sb = u0b + u1b + u2b + u3b + 0x78787878u;
-            const uint32_t big = (u0a | u1a | u2a | u3a | u0b | u1b | u2b | u3b) & 0xF8F8F8F8u;   // ... else caught here
-            if ((((sa | sb) & 0x80808080u) | big) != 0) flagbits |= 1u << j;
+            const int ha = dp4a_us(u3a, 0x01010101, dp4a_us(u2a, 0x01010101, dp4a_us(u1a, 0x01010101, dp4a_us(u0a, 0x01010101, 0))));
+            const int hb = dp4a_us(u3b, 0x01010101, dp4a_us(u2b, 0x01010101, dp4a_us(u1b, 0x01010101, dp4a_us(u0b, 0x01010101, 0))));
+            if ((((sa | sb) & 0x80808080u) | ((uint32_t)(ha | hb) & ~31u)) != 0) flagbits |= 1u << j;
             PP2[j] = pp2; PM5a[j] = pm5a; PP5b[j] = pp5b;
             pWm1 = A.y; pW0 = B.x; pW1 = B.y; pW2 = C.x;
         }
