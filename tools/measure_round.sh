@@ -19,6 +19,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${
     python bench.py --frames 1024 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $O/${R}_launches_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:chess_cascade -s 2 -c 1 -f -o $O/${R}_k1 \
     python bench.py --frames 512 --chunk 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/${R}_k1_ncu.log 2>&1
+python tools/bench_blobs.py --frames 256 --steps 2 > $O/${R}_blobs_4k_n14.json 2>> $O/${R}_bench_n1.err
+python tools/bench_blobs.py --frames 256 --steps 2 --kind circles --gridn 10 > $O/${R}_blobs_4k_circles.json 2>> $O/${R}_bench_n1.err
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${R}_blob_launches.csv \
+    python tools/bench_blobs.py --frames 64 --chunk 64 --steps 1 --warmup 1 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cluster_find -s 2 -c 1 -f -o $O/${R}_k2 \
     python bench.py --frames 512 --chunk 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/${R}_k2_ncu.log 2>&1
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $O/${R}_gpu.txt
