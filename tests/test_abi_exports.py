@@ -58,3 +58,22 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "pyoracle" not in txt and "libmrg_oracle" not in txt and "oracle/" not in txt, fn
+
+
+def test_cxx_adapter_headers_compile(tmp_path):
+    # the C++ spellings of the reference API (find_chessboard_corners.hh:12-72, find_blobs.hh:15-20)
+    # must compile and link against the C ABI without OpenCV
+    import subprocess
+    src = tmp_path / "t.cc"
+    src.write_text('#include <mrgingham_b200/find_chessboard_corners.hh>\n#include <mrgingham_b200/find_blobs.hh>\n'
+                   'int main(int argc, char**) {\n'
+                   '  std::vector<mrgingham::PointInt> p; std::vector<mrgingham::PointDouble> q; signed char lv[1];\n'
+                   '  mrgingham::ImageView v = {0, 0, 0, nullptr};\n'
+                   '  if (argc > 100) { mrgingham::find_chessboard_corners_from_image_array(&p, v, 0);\n'
+                   '    mrgingham::refine_chessboard_corners_from_image_array(&q, lv, v, 0);\n'
+                   '    mrgingham::find_blobs_from_image_array(&p, v); }\n'
+                   '  return 0; }\n')
+    lib = os.path.join(ROOT, "mrgingham_b200")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "t"),
+                    "-L" + lib, "-lmrgingham_b200", "-Wl,-rpath," + lib], check=True)
+    subprocess.run([str(tmp_path / "t")], check=True)
