@@ -275,7 +275,10 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
     if (det->h_candcounts.ensure(sizeof(int32_t) * std::max(nframes, 1))) return -1;
 
     const int chunk = det->cfg.max_frames;
-    cudaStream_t aux = det->aux_stream, cpy = det->copy_stream;
+    // MRG_B200_K2_STREAM=main runs the clustering kernel on the ChESS kernel's stream (no overlap of
+    // K2(c) with K1(c+1)); default: its own high-priority stream
+    static const bool k2_on_main = [] { const char* e = getenv("MRG_B200_K2_STREAM"); return e && !strcmp(e, "main"); }();
+    cudaStream_t aux = k2_on_main ? stream : det->aux_stream, cpy = det->copy_stream;
     // size both slots before anything is in flight (growing a buffer frees it)
     for (int b = 0; b < 2 && b * chunk < nframes; b++)
     {

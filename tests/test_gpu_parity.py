@@ -334,3 +334,34 @@ def test_refine_batch_matches_oracle(api, oracle):
         n0, x0, l0 = oracle.refine_corners(f, 1, xy[i], lv[i])
         assert nref[i] == n0 and np.array_equal(lv2[i], l0) and np.array_equal(xy2[i].view(np.uint64), x0.view(np.uint64)), i
     det.close(); det2.close()
+
+
+def test_8k_frame(api, oracle):
+    # BASELINE.json configs[4] tops out at 7680x4320: ten strips of 768 pixels per frame
+    frame = synth.board_frame(7680, 4320, 10, seed=123)
+    got = api.find_chessboard_corners_int(frame, 0)
+    want = oracle.find_corners(frame, 0)
+    assert len(want) == 100 and np.array_equal(got, want)
+    got2 = api.find_chessboard_corners_int(frame, 2)
+    assert np.array_equal(got2, oracle.find_corners(frame, 2))
+
+
+def test_cascade_adversarial_frames(api, oracle):
+    # frames built to stress the cascade kernel's packed-byte tests: extreme contrasts (byte-lane wrap
+    # guards), one-pixel stripes and checkers (everything reaches L2), and widths that select every
+    # strip geometry (1, 2 and 3 warps per CTA, partial last strips, widths not multiples of 4)
+    rng = np.random.default_rng(7)
+    for (w, h) in ((250, 64), (301, 97), (530, 120), (799, 150), (1100, 90), (1537, 70)):
+        imgs = [
+            (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8),                                  # salt and pepper
+            np.where((np.arange(w)[None, :] + np.arange(h)[:, None]) % 2 == 0, 255, 0).astype(np.uint8) + np.zeros((h, w), np.uint8),
+            np.tile(np.where(np.arange(w) % 2 == 0, 255, 0).astype(np.uint8), (h, 1)),            # vertical stripes
+            np.tile(np.where(np.arange(h) % 3 == 0, 255, 0).astype(np.uint8)[:, None], (1, w)),   # horizontal stripes
+            np.clip(rng.normal(128, 60, (h, w)), 0, 255).astype(np.uint8),                        # wide noise
+            synth.checker_frame(w, h, period=6, seed=int(w)),
+        ]
+        frames = np.stack([np.ascontiguousarray(i) for i in imgs])
+        det = api.Detector(max_frames=len(frames), candidate_capacity=1 << 18, max_points=1 << 15)
+        xy, counts = det.find_corners(frames, 0)
+        _check_batch(xy, counts, frames, oracle, 0)
+        det.close()
