@@ -164,6 +164,18 @@ int mrg_b200_chess_response_batch(mrg_b200_detector* det,
                                   int16_t* response, int response_on_device,
                                   void* stream);
 
+/* The box blur the reference CLI applies before the detector by default (mrgingham-from-image.cc:
+   106-111, --blur R with R = 1): cv::blur(image, image, Size(1+2R, 1+2R)), BORDER_REFLECT_101.
+   out: uint8 [nframes][rows][cols] dense, HOST or DEVICE (out_on_device); it must not overlap the
+   input. blur_radius in [1,4]. Synchronous. Returns 0 or <0. */
+int mrg_b200_box_blur_batch(mrg_b200_detector* det,
+                            const uint8_t* images, int images_on_device,
+                            int nframes, int rows, int cols,
+                            size_t row_pitch, size_t frame_stride,
+                            int blur_radius,
+                            uint8_t* out, int out_on_device,
+                            void* stream);
+
 /* Pyramid level image (what the reference gets from cv::resize, find_chessboard_corners.cc:449-450).
    out: HOST uint8 [orows][ocols] dense; returns 0 and the size, or <0. */
 int mrg_b200_pyramid_level(mrg_b200_detector* det,

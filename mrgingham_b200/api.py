@@ -20,7 +20,7 @@ EXPORTS = (
     "mrg_b200_find_chessboard_corners", "mrg_b200_refine_chessboard_corners",
     "mrg_b200_detector_create", "mrg_b200_detector_destroy",
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
-    "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch",
+    "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch", "mrg_b200_box_blur_batch",
     "mrg_b200_chess_response_batch", "mrg_b200_pyramid_level",
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
     "mrg_b200_device_count",
@@ -76,6 +76,9 @@ def lib():
     L.mrg_b200_find_blobs_batch.restype = ctypes.c_int
     L.mrg_b200_find_blobs_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_size_t, ctypes.c_size_t, _i32p, _i32p, ctypes.c_void_p]
+    L.mrg_b200_box_blur_batch.restype = ctypes.c_int
+    L.mrg_b200_box_blur_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.mrg_b200_chess_response_batch.restype = ctypes.c_int
     L.mrg_b200_chess_response_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
@@ -288,6 +291,25 @@ class Detector:
         if rc != 0:
             raise RuntimeError("mrg_b200_find_blobs_batch() failed")
         return xy, counts
+
+    def box_blur(self, images, radius=1, out=None, stream=None):
+        """cv::blur(Size(1+2R,1+2R)) as the reference CLI applies it by default (mrgingham-from-image.cc:106-111).
+        Host images -> numpy result; a CUDA torch tensor -> a new CUDA tensor (or `out`), no host round trip."""
+        ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
+        if on_dev:
+            import torch
+            if out is None:
+                out = torch.empty((n, rows, cols), dtype=torch.uint8, device=keep.device)
+            assert out.is_contiguous() and out.shape == (n, rows, cols)
+            optr = out.data_ptr()
+        else:
+            out = np.empty((n, rows, cols), dtype=np.uint8)
+            optr = out.ctypes.data
+        rc = lib().mrg_b200_box_blur_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(radius), optr, on_dev,
+                                           ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_box_blur_batch() failed")
+        return out
 
     def refine_corners(self, images, level, xy, levels, stream=None):
         """batched refinement: xy float64 [n, npoints, 2], levels int8 [n, npoints];

@@ -486,6 +486,38 @@ API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* ima
     return 0;
 }
 
+API int mrg_b200_box_blur_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                int blur_radius, uint8_t* out, int out_on_device, void* stream_)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (nframes < 0 || rows <= 0 || cols <= 0 || row_pitch < (size_t)cols) { MSG("Bad batch geometry."); return -1; }
+    if (blur_radius < 1 || blur_radius > 4) { MSG("blur_radius must be in [1,4]; got %d.", blur_radius); return -1; }
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+    const size_t fe = (size_t)rows * cols;
+    const int chunk = out_on_device && images_on_device ? std::max(nframes, 1) : std::max(1, det->cfg.max_frames);
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        mrg_b200_detector::Slot& S = det->slot[0];
+        FrameSet fs;
+        if (stage_frames(det, S, images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride, 0, stream, stream, &fs)) return -1;
+        uint8_t* d = out + (size_t)f0 * fe;
+        if (!out_on_device)
+        {
+            if (S.level_img.ensure(fe * n)) return -1;
+            d = (uint8_t*)S.level_img.p;
+        }
+        CUDA_TRY(launch_box_blur(fs, blur_radius, d, cols, fe, stream));
+        if (!out_on_device) CUDA_TRY(cudaMemcpyAsync(out + (size_t)f0 * fe, d, fe * n, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
 API int mrg_b200_pyramid_level(mrg_b200_detector* det, const uint8_t* image, int rows, int cols, size_t row_pitch,
                                int level, uint8_t* out, int* orows, int* ocols)
 {

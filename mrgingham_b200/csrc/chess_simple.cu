@@ -141,6 +141,137 @@ pyramid_kernel(FrameSet src, int level, uint8_t* __restrict__ dst, int dst_pitch
     dst[(size_t)f * dst_frame_stride + (size_t)dy * dst_pitch + dx] = (uint8_t)v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Kpre: the box blur the reference CLI applies before the detector by default
+// (mrgingham-from-image.cc:106-111, --blur 1): cv::blur(Size(1+2R,1+2R)), BORDER_REFLECT_101,
+// = floor((sum + (k*k-1)/2) / (k*k)) for 8-bit data. A CTA blurs a 128 x 8 output tile from a
+// shared-memory tile with the halo; 2 bytes of HBM traffic per pixel (1 read + 1 written).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlurMaxR = 4, kBlurTW = 128, kBlurTH = 8;
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+__global__ void __launch_bounds__(256)
+box_blur_kernel(FrameSet fs, int radius, uint8_t* __restrict__ dst, int dst_pitch, size_t dst_frame_stride)
+{
+    __shared__ uint8_t tile[kBlurTH + 2 * kBlurMaxR][kBlurTW + 2 * kBlurMaxR + 8];
+    const int f = blockIdx.z, x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
+    const uint8_t* img = fs.base + (size_t)f * fs.frame_stride;
+    const int tw = kBlurTW + 2 * radius, th = kBlurTH + 2 * radius;
+    for (int i = threadIdx.x; i < tw * th; i += 256)
+    {
+        const int ty = i / tw, tx = i % tw;
+        tile[ty][tx] = img[(size_t)reflect101(y0 + ty - radius, fs.h) * fs.pitch + reflect101(x0 + tx - radius, fs.w)];
+    }
+    __syncthreads();
+    const int k = 2 * radius + 1, k2 = k * k, half = (k2 - 1) / 2;
+    // thread = 4 adjacent pixels of one row of the tile
+    const int ty = threadIdx.x / 32, tx = (threadIdx.x % 32) * 4;
+    const int y = y0 + ty;
+    if (y >= fs.h || x0 + tx >= fs.w) return;
+    int sum[4] = { 0, 0, 0, 0 };
+    for (int dy = 0; dy < k; dy++)
+        for (int dx = 0; dx < k + 3; dx++)
+        {
+            const int v = tile[ty + dy][tx + dx];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (dx - p >= 0 && dx - p < k) sum[p] += v;
+        }
+    uint8_t* o = dst + (size_t)f * dst_frame_stride + (size_t)y * dst_pitch + x0 + tx;
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+        if (x0 + tx + p < fs.w) o[p] = (uint8_t)((sum[p] + half) / k2);
+}
+
+// Fast path for the CLI's default R = 1 (3x3): HBM-bound, 1 byte read + 1 byte written per pixel.
+// A lane owns 16 adjacent pixels (one 128-bit load and one 128-bit store per row) and walks down a
+// row segment keeping the unpacked 16-bit lanes of the previous two rows in registers: vertical
+// 3-sums first (packed IADD3), then horizontal 3-sums with PRMT-shifted copies, neighbours across
+// lanes by shuffle. Lanes 0 and 31 of a warp are halo lanes (they load and sum but do not store), so
+// a warp emits 480 pixels per row and no lane ever needs data from another warp.
+// Needs 16-byte aligned rows on both sides and w % 16 == 0 (every BASELINE size); otherwise the
+// generic kernel above runs. floor((s + 4) / 9) = ((s + 4) * 7282) >> 16 for s <= 2295 (checked exhaustively).
+constexpr int kBlur3SegRows = 64;
+__global__ void __launch_bounds__(128)
+box_blur3_kernel(FrameSet fs, uint8_t* __restrict__ dst, int dst_pitch, size_t dst_frame_stride, int strips_per_row)
+{
+    const int lane = threadIdx.x & 31, wglobal = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int strip = wglobal % strips_per_row, seg = wglobal / strips_per_row, f = blockIdx.y;
+    const int w = fs.w, h = fs.h;
+    const int x0 = strip * 480 + 16 * (lane - 1);
+    const int ys = seg * kBlur3SegRows, ye = min(ys + kBlur3SegRows, h);
+    if (ys >= h) return;
+    const bool inside = x0 >= 0 && x0 < w;
+    const uint8_t* img = fs.base + (size_t)f * fs.frame_stride + (inside ? x0 : 0);
+    uint8_t* out = dst + (size_t)f * dst_frame_stride + (inside ? x0 : 0);
+    const bool store = inside && lane >= 1 && lane <= 30;
+
+    auto load_row = [&](int y, uint32_t (&u)[8])
+    {
+        // row y (reflected at the top/bottom edge) as eight words of two 16-bit lanes
+        const int yy = h == 1 ? 0 : (y < 0 ? -y : (y >= h ? 2 * (h - 1) - y : y));
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (inside) q = *reinterpret_cast<const uint4*>(img + (size_t)yy * fs.pitch);
+        u[0] = __byte_perm(q.x, 0, 0x4140); u[1] = __byte_perm(q.x, 0, 0x4342);
+        u[2] = __byte_perm(q.y, 0, 0x4140); u[3] = __byte_perm(q.y, 0, 0x4342);
+        u[4] = __byte_perm(q.z, 0, 0x4140); u[5] = __byte_perm(q.z, 0, 0x4342);
+        u[6] = __byte_perm(q.w, 0, 0x4140); u[7] = __byte_perm(q.w, 0, 0x4342);
+    };
+    uint32_t ra[8], rb[8], rc[8];
+    load_row(ys - 1, ra);
+    load_row(ys, rb);
+#pragma unroll 1
+    for (int y = ys; y < ye; y++)
+    {
+        load_row(y + 1, rc);
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = ra[k] + rb[k] + rc[k];           // vertical sums, <= 765 per lane
+        // neighbours: v[-1] from the lane on the left, v[16] from the lane on the right; at the image's
+        // left/right edge BORDER_REFLECT_101 takes v[1] / v[14]
+        uint32_t lv = __shfl_up_sync(0xffffffffu, v[7], 1) >> 16;
+        uint32_t rv = __shfl_down_sync(0xffffffffu, v[0], 1) & 0xFFFFu;
+        if (x0 == 0) lv = v[0] >> 16;
+        if (x0 + 16 == w) rv = v[7] & 0xFFFFu;
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            const uint32_t left  = k == 0 ? (lv | (v[0] << 16)) : __byte_perm(v[k - 1], v[k], 0x5432);     // [v(2k-1), v(2k)]
+            const uint32_t right = k == 7 ? ((v[7] >> 16) | (rv << 16)) : __byte_perm(v[k], v[k + 1], 0x5432); // [v(2k+1), v(2k+2)]
+            const uint32_t s = v[k] + left + right;                                                        // <= 2295 per lane
+            const uint32_t q0 = (((s & 0xFFFFu) + 4u) * 7282u) >> 16, q1 = (((s >> 16) + 4u) * 7282u) >> 16;
+            const uint32_t pair = q0 | (q1 << 8);
+            if (k & 1) o[k >> 1] |= pair << 16; else o[k >> 1] = pair;
+        }
+        if (store) *reinterpret_cast<uint4*>(out + (size_t)y * dst_pitch) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { ra[k] = rb[k]; rb[k] = rc[k]; }
+    }
+}
+
+cudaError_t launch_box_blur(const FrameSet& src, int radius, uint8_t* dst, int dst_pitch, size_t dst_frame_stride, cudaStream_t stream)
+{
+    if (src.w <= 0 || src.h <= 0 || src.nframes <= 0) return cudaSuccess;
+    if (radius < 1 || radius > kBlurMaxR) return cudaErrorInvalidValue;
+    const bool aligned = !((uintptr_t)src.base & 15) && !(src.pitch & 15) && !(src.frame_stride & 15) &&
+                         !((uintptr_t)dst & 15) && !(dst_pitch & 15) && !(dst_frame_stride & 15) && !(src.w & 15);
+    if (radius == 1 && aligned && src.nframes <= 65535)
+    {
+        const int strips = (src.w + 479) / 480, segs = (src.h + kBlur3SegRows - 1) / kBlur3SegRows;
+        dim3 grid((strips * segs + 3) / 4, src.nframes);
+        box_blur3_kernel<<<grid, 128, 0, stream>>>(src, dst, dst_pitch, dst_frame_stride, strips);
+        return cudaGetLastError();
+    }
+    dim3 grid((src.w + kBlurTW - 1) / kBlurTW, (src.h + kBlurTH - 1) / kBlurTH, src.nframes);
+    box_blur_kernel<<<grid, 256, 0, stream>>>(src, radius, dst, dst_pitch, dst_frame_stride);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pyramid(const FrameSet& src, int level, uint8_t* dst, int dst_pitch,
                            size_t dst_frame_stride, int ow, int oh, cudaStream_t stream)
 {

@@ -54,6 +54,10 @@ size_t cluster_record_bytes();
 cudaError_t launch_pyramid(const FrameSet& src, int level, uint8_t* dst, int dst_pitch,
                            size_t dst_frame_stride, int ow, int oh, cudaStream_t stream);
 
+// Kpre: cv::blur(Size(1+2R,1+2R)) of the reference CLI's default preprocessing (mrgingham-from-image.cc:106-111)
+cudaError_t launch_box_blur(const FrameSet& src, int radius, uint8_t* dst, int dst_pitch, size_t dst_frame_stride,
+                            cudaStream_t stream);
+
 // K1 (simple variant): ChESS response, one thread per pixel, emits candidates
 cudaError_t launch_chess_sparse_simple(const FrameSet& fs, cand_t* cand, uint32_t* counts,
                                        int cand_capacity, cudaStream_t stream);

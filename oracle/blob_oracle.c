@@ -327,3 +327,31 @@ EXPORT int blob_oracle_find_blobs(const uint8_t* gray, int w, int h, int stride,
     free(groups);
     return n <= max_points ? n : -1 - n;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Preprocessing the reference CLI applies before the detector by default:
+ * cv::blur(image, image, Size(1+2R, 1+2R)) with R = 1 (mrgingham-from-image.cc:106-111, default
+ * --blur 1 at :222). OpenCV's normalised box filter on 8-bit data with BORDER_REFLECT_101 is, for
+ * odd k*k, exactly out = floor((sum + (k*k-1)/2) / (k*k)) (no ties exist, so the float rounding
+ * inside OpenCV cannot matter). PINNED against cv2.blur 4.13.0 by tests/test_blur.py.
+ * ------------------------------------------------------------------------------------------------ */
+static int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) { if (i < 0) i = -i; else i = 2 * (n - 1) - i; }
+    return i;
+}
+EXPORT void blob_oracle_box_blur(const uint8_t* in, int w, int h, int stride, int radius, uint8_t* out /* dense [h][w] */)
+{
+    const int k2 = (2 * radius + 1) * (2 * radius + 1);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+        {
+            int sum = 0;
+            for (int dy = -radius; dy <= radius; dy++)
+                for (int dx = -radius; dx <= radius; dx++)
+                    sum += in[(size_t)reflect101(y + dy, h) * stride + reflect101(x + dx, w)];
+            out[(size_t)y * w + x] = (uint8_t)((sum + (k2 - 1) / 2) / k2);
+        }
+}

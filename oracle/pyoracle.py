@@ -165,6 +165,15 @@ def find_blobs(image, cap=1 << 16):
     return xy[:n].copy()
 
 
+def box_blur(image, radius=1):
+    """cv::blur(image, Size(1+2R,1+2R)) as the reference CLI applies it (mrgingham-from-image.cc:106-111)"""
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.empty((h, w), dtype=np.uint8)
+    oracle_lib().blob_oracle_box_blur(_ptr(image, _u8p), w, h, image.strides[0], int(radius), _ptr(out, _u8p))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference itself (oracle/_ref)
 # ---------------------------------------------------------------------------------------------
