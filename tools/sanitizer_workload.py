@@ -1,0 +1,17 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from mrgingham_b200 import api, synth
+from oracle import pyoracle as po
+frames = np.stack([synth.board_frame(1280, 720, 10, seed=1), synth.blurred_noise_frame(1280, 720, seed=2)])
+det = api.Detector(max_frames=2, candidate_capacity=1<<18, max_points=1<<14)
+xy, c = det.find_corners(frames, 0)
+for i in range(2):
+    w = po.find_corners(frames[i], 0)
+    assert c[i] == len(w) and np.array_equal(xy[i,:c[i]], w)
+small = np.stack([synth.circle_grid_frame(320, 240, 6, seed=3), synth.blob_frame(320, 240, seed=4)])
+bx, bc = det.find_blobs(small)
+for i in range(2):
+    w = po.find_blobs(small[i]); assert bc[i] == len(w) and np.array_equal(bx[i,:bc[i]], w)
+b = det.box_blur(small, 1); assert np.array_equal(b[0], po.box_blur(small[0], 1))
+print("sanitizer workload ok", c, bc)
