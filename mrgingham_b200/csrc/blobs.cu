@@ -90,33 +90,83 @@ blob_binarize_kernel(FrameSet fs, BlobGeom g, uint32_t* __restrict__ planes)
 __constant__ int kDx[8] = { 1, 1, 0, -1, -1, -1, 0, 1 };     // 0 = east, then counter-clockwise on the screen
 __constant__ int kDy[8] = { 0, -1, -1, -1, 0, 1, 1, 1 };
 
+// One thread's view of its bit planes. The thread keeps, in registers, the 3 x 3 words of B around
+// its position (rows cy-1..cy+1, words cwd-1..cwd+1) and the V/R words it is marking (written back
+// when it moves to another word): while a border is followed most steps need no load at all, a
+// vertical step needs one round of three independent loads.
 struct Plane
 {
     const uint32_t* B; uint32_t* V; uint32_t* R;
     int w, h, wpr;
-    // bits (x-1, x, x+1) of row y as bits 0..2; 0 outside the image
-    __device__ uint32_t row3(int x, int y) const
+    int cy, cwd; uint32_t b[3][3];
+    int my, mwd; uint32_t vword, rword; bool dirty;
+
+    __device__ __forceinline__ void init() { cy = -0x40000000; cwd = -2; my = -1; mwd = -1; vword = rword = 0; dirty = false; }
+    __device__ __forceinline__ void load_row(int slot, int y)
     {
-        if ((unsigned)y >= (unsigned)h) return 0;
-        const uint32_t* r = B + (size_t)y * wpr;
-        const int wd = x >> 5, b = x & 31;
-        const uint32_t c = r[wd];
-        uint32_t v = b ? (c >> (b - 1)) & 7u : (c << 1) & 6u;
-        if (b == 0 && wd > 0) v |= r[wd - 1] >> 31;
-        if (b == 31 && wd + 1 < wpr) v |= (r[wd + 1] & 1u) << 2;
-        return v;       // bits beyond w are zero in the plane already
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+        {
+            const int wc = cwd - 1 + c;
+            b[slot][c] = ((unsigned)y < (unsigned)h && (unsigned)wc < (unsigned)wpr) ? B[(size_t)y * wpr + wc] : 0u;
+        }
+    }
+    __device__ __forceinline__ void seek(int x, int y)
+    {
+        const int wd = x >> 5;
+        if (wd == cwd && y == cy) return;
+        if (wd == cwd && y == cy + 1)
+        {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { b[0][c] = b[1][c]; b[1][c] = b[2][c]; }
+            cy = y; load_row(2, y + 1);
+        }
+        else if (wd == cwd && y == cy - 1)
+        {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { b[2][c] = b[1][c]; b[1][c] = b[0][c]; }
+            cy = y; load_row(0, y - 1);
+        }
+        else
+        {
+            cwd = wd; cy = y;
+            load_row(0, y - 1); load_row(1, y); load_row(2, y + 1);
+        }
+    }
+    // bits (x-1, x, x+1) of a cached row as bits 0..2
+    __device__ __forceinline__ uint32_t row3(int slot, int bpos) const
+    {
+        const unsigned long long w64 = ((unsigned long long)b[slot][1] << 32) | b[slot][0];
+        uint32_t v = (uint32_t)(w64 >> (31 + bpos)) & 7u;
+        if (bpos == 31) v |= (b[slot][2] & 1u) << 2;
+        return v;
     }
     // bit d = the neighbour of (x, y) in direction d (0 = E, 1 = NE, 2 = N, 3 = NW, 4 = W, 5 = SW, 6 = S, 7 = SE) is foreground
-    __device__ uint32_t nbr8(int x, int y) const
+    __device__ __forceinline__ uint32_t nbr8(int x, int y)
     {
-        const uint32_t up = row3(x, y - 1), mid = row3(x, y), dn = row3(x, y + 1);
+        seek(x, y);
+        const int bpos = x & 31;
+        const uint32_t up = row3(0, bpos), mid = row3(1, bpos), dn = row3(2, bpos);
         return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) |
                ((mid & 1u) << 4) | ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
     }
-    __device__ bool visited(int x, int y) const { return (V[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u; }
-    __device__ bool rflag(int x, int y) const { return (R[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u; }
-    __device__ void set_visited(int x, int y) { V[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31); }
-    __device__ void set_rflag(int x, int y) { R[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31); }
+    // mark words: write-back cache of one V word and one R word
+    __device__ __forceinline__ void flush_marks()
+    {
+        if (dirty) { V[(size_t)my * wpr + mwd] = vword; R[(size_t)my * wpr + mwd] = rword; dirty = false; }
+    }
+    __device__ __forceinline__ void seek_marks(int x, int y)
+    {
+        const int wd = x >> 5;
+        if (wd == mwd && y == my) return;
+        flush_marks();
+        my = y; mwd = wd;
+        vword = V[(size_t)y * wpr + wd]; rword = R[(size_t)y * wpr + wd];
+    }
+    __device__ __forceinline__ bool visited(int x, int y) { seek_marks(x, y); return (vword >> (x & 31)) & 1u; }
+    __device__ __forceinline__ bool rflag(int x, int y)   { seek_marks(x, y); return (rword >> (x & 31)) & 1u; }
+    __device__ __forceinline__ void set_visited(int x, int y) { seek_marks(x, y); vword |= 1u << (x & 31); dirty = true; }
+    __device__ __forceinline__ void set_rflag(int x, int y)   { seek_marks(x, y); rword |= 1u << (x & 31); dirty = true; }
 };
 
 struct Tracer
@@ -128,26 +178,19 @@ struct Tracer
     int frame, thr, seq;
 
     // follow the border that starts at (x0, y0); false = out of space
-    __device__ bool trace(int x0, int y0, bool is_hole)
+    __device__ __forceinline__ bool trace(int x0, int y0, bool is_hole)
     {
         const unsigned start = npts;
-        long long a00 = 0, a10 = 0, a01 = 0, a20 = 0, a11 = 0, a02 = 0;
-        int xmin = x0, xmax = x0, ymin = y0, ymax = y0;
+        // Only the area term is accumulated here (it decides at once whether the border is kept); the
+        // other moments and the bounding box are summed over the stored points, in parallel, by B3.
+        long long a00 = 0;
         int fx = x0, fy = y0, px = x0, py = y0;          // first / previous emitted point
         int n = 0;
         auto emit = [&](int x, int y) -> bool
         {
             if (npts >= pts_cap) return false;
             pts[npts++] = (uint32_t)x | ((uint32_t)y << 16);
-            if (n > 0)
-            {
-                const long long dxy = (long long)px * y - (long long)x * py, xs = px + x, ys = py + y;
-                a00 += dxy; a10 += dxy * xs; a01 += dxy * ys;
-                a20 += dxy * ((long long)px * xs + (long long)x * x);
-                a11 += dxy * ((long long)px * (ys + py) + (long long)x * (ys + y));
-                a02 += dxy * ((long long)py * ys + (long long)y * y);
-            }
-            xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+            a00 += px * y - x * py;                      // coordinates < 2^15: the products fit 32 bits
             px = x; py = y; n++;
             return true;
         };
@@ -191,14 +234,7 @@ struct Tracer
                 s = (s + 4) & 7;
             }
         }
-        // closing edge: last point -> first point
-        {
-            const long long dxy = (long long)px * fy - (long long)fx * py, xs = px + fx, ys = py + fy;
-            a00 += dxy; a10 += dxy * xs; a01 += dxy * ys;
-            a20 += dxy * ((long long)px * xs + (long long)fx * fx);
-            a11 += dxy * ((long long)px * (ys + py) + (long long)fx * (ys + fy));
-            a02 += dxy * ((long long)py * ys + (long long)fy * fy);
-        }
+        a00 += px * fy - fx * py;                        // closing edge: last point -> first point
         // filterByArea: m00 = |a00| / 2 in [20, 80000) -- exact in integers. Everything else is dropped here.
         const long long aa = a00 < 0 ? -a00 : a00;
         if (aa < 40 || aa >= 160000) { npts = start; return true; }
@@ -206,8 +242,8 @@ struct Tracer
         if (idx >= rec_cap) return false;
         BlobRecord r;
         r.frame = frame; r.thr = thr; r.seq = seq++; r.n = n; r.pts_off = start;
-        r.xmin = xmin; r.xmax = xmax; r.ymin = ymin; r.ymax = ymax;
-        r.a00 = a00; r.a10 = a10; r.a01 = a01; r.a20 = a20; r.a11 = a11; r.a02 = a02;
+        r.xmin = r.xmax = r.ymin = r.ymax = 0;
+        r.a00 = a00; r.a10 = r.a01 = r.a20 = r.a11 = r.a02 = 0;
         r.hull2 = 0; r.cx = r.cy = r.radius = 0; r.colour_ok = 0; r.pad = 0;
         recs[idx] = r;
         return true;
@@ -223,39 +259,54 @@ blob_trace_kernel(BlobGeom g, const uint32_t* __restrict__ planes, uint32_t* mar
     const size_t poff = ((size_t)f * kNThr + k) * g.h * g.wpr;
     Tracer T;
     T.P.B = planes + poff; T.P.V = marksV + poff; T.P.R = marksR + poff;
-    T.P.w = g.w; T.P.h = g.h; T.P.wpr = g.wpr;
+    T.P.w = g.w; T.P.h = g.h; T.P.wpr = g.wpr; T.P.init();
     T.pts = pts + (size_t)job * g.pts_cap; T.npts = 0; T.pts_cap = g.pts_cap;
     T.recs = recs; T.rec_count = rec_count; T.rec_cap = g.rec_cap; T.status = status;
     T.frame = f; T.thr = k; T.seq = 0;
 
+    // The scan runs on one thread, so its cost is instructions per word: rows are read four words at
+    // a time (the next group is requested before the current one is examined; wpr is a multiple of 4
+    // and the planes are 16-byte aligned) and a group without any 0/1 transition costs ~16 instructions.
+    const int groups = g.wpr / 4;
     for (int y = 0; y < g.h; y++)
     {
-        const uint32_t* brow = T.P.B + (size_t)y * g.wpr;
+        const uint4* brow = reinterpret_cast<const uint4*>(T.P.B + (size_t)y * g.wpr);
         uint32_t prevbit = 0;
-        for (int wd = 0; wd < g.wpr; wd++)
+        uint4 nxt = brow[0];
+        for (int gi = 0; gi < groups; gi++)
         {
-            const uint32_t cur = brow[wd];
-            uint32_t ev = cur ^ ((cur << 1) | prevbit);        // pixels that differ from their left neighbour
-            prevbit = cur >> 31;
-            const int left = g.w - wd * 32;                    // only x < w is examined (the scan stops before the frame)
-            if (left < 32) ev &= (1u << left) - 1;
-            while (ev)
+            const uint4 q = nxt;
+            if (gi + 1 < groups) nxt = brow[gi + 1];
+            // pixels that differ from their left neighbour
+            uint32_t e0 = q.x ^ ((q.x << 1) | prevbit), e1 = q.y ^ ((q.y << 1) | (q.x >> 31));
+            uint32_t e2 = q.z ^ ((q.z << 1) | (q.y >> 31)), e3 = q.w ^ ((q.w << 1) | (q.z >> 31));
+            prevbit = q.w >> 31;
+            const int left = g.w - gi * 128;                     // only x < w is examined (the scan stops before the frame)
+            if (left < 128)
             {
-                const int b = __ffs(ev) - 1;
-                ev &= ev - 1;
-                const int x = wd * 32 + b;
-                bool ok = true;
-                if ((cur >> b) & 1u)
+                e0 &= left >= 32 ? ~0u : (left > 0 ? (1u << left) - 1 : 0u);
+                e1 &= left >= 64 ? ~0u : (left > 32 ? (1u << (left - 32)) - 1 : 0u);
+                e2 &= left >= 96 ? ~0u : (left > 64 ? (1u << (left - 64)) - 1 : 0u);
+                e3 &= left > 96 ? (1u << (left - 96)) - 1 : 0u;
+            }
+            if ((e0 | e1 | e2 | e3) == 0) continue;
+#pragma unroll 1
+            for (int k = 0; k < 4; k++)
+            {
+                uint32_t ev = k == 0 ? e0 : k == 1 ? e1 : k == 2 ? e2 : e3;
+                const uint32_t cur = k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w;
+                while (ev)
                 {
-                    // 0 -> 1: an outer border starts here unless the pixel was already visited
-                    if (!T.P.visited(x, y)) ok = T.trace(x, y, false);
-                }
-                else
-                {
+                    const int bb = __ffs(ev) - 1;
+                    ev &= ev - 1;
+                    const int x = (gi * 4 + k) * 32 + bb;
+                    // 0 -> 1: an outer border starts here unless the pixel was already visited;
                     // 1 -> 0: a hole border starts at x-1 unless that pixel carries the east flag
-                    if (!T.P.rflag(x - 1, y)) ok = T.trace(x - 1, y, true);
+                    const bool hole = !((cur >> bb) & 1u);
+                    const int sx = x - (hole ? 1 : 0);
+                    const bool start = hole ? !T.P.rflag(sx, y) : !T.P.visited(sx, y);
+                    if (start && !T.trace(sx, y, hole)) { atomicExch(status, 1); return; }
                 }
-                if (!ok) { atomicExch(status, 1); return; }
             }
         }
     }
@@ -274,6 +325,9 @@ blob_contour_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const uint3
     __shared__ unsigned long long sel_prefix;
     __shared__ unsigned sel_rank;
     __shared__ double s_cx, s_cy;
+    __shared__ long long red_ll[kB3Threads / 32][5];
+    __shared__ int red_i[kB3Threads / 32][4];
+    __shared__ int s_need_radius;
     const unsigned nrec = min(*rec_count, g.rec_cap);
     int* ylo = scratch + (size_t)blockIdx.x * scratch_stride;       // per column of the bounding box
     int* yhi = ylo + g.w;
@@ -282,7 +336,54 @@ blob_contour_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const uint3
     {
         BlobRecord& r = recs[ri];
         const uint32_t* p = pts + ((size_t)r.frame * kNThr + r.thr) * g.pts_cap + r.pts_off;
-        const int n = r.n, bw = r.xmax - r.xmin + 1;
+        const int n = r.n;
+        // Green's-theorem sums over the directed edges (point i-1 -> point i, cyclically) and the
+        // bounding box: exact integers, any order
+        {
+            long long t10 = 0, t01 = 0, t20 = 0, t11 = 0, t02 = 0;
+            int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
+            for (int i = threadIdx.x; i < n; i += kB3Threads)
+            {
+                const uint32_t q = p[i], qp = p[i == 0 ? n - 1 : i - 1];
+                const long long x = q & 0xFFFF, y = q >> 16, xp = qp & 0xFFFF, yp = qp >> 16;
+                const long long dxy = xp * y - x * yp, xs = xp + x, ys2 = yp + y;
+                t10 += dxy * xs; t01 += dxy * ys2;
+                t20 += dxy * (xp * xs + x * x);
+                t11 += dxy * (xp * (ys2 + yp) + x * (ys2 + y));
+                t02 += dxy * (yp * ys2 + y * y);
+                bx0 = min(bx0, (int)x); bx1 = max(bx1, (int)x); by0 = min(by0, (int)y); by1 = max(by1, (int)y);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                t10 += __shfl_down_sync(0xffffffffu, t10, o); t01 += __shfl_down_sync(0xffffffffu, t01, o);
+                t20 += __shfl_down_sync(0xffffffffu, t20, o); t11 += __shfl_down_sync(0xffffffffu, t11, o);
+                t02 += __shfl_down_sync(0xffffffffu, t02, o);
+                bx0 = min(bx0, __shfl_down_sync(0xffffffffu, bx0, o)); bx1 = max(bx1, __shfl_down_sync(0xffffffffu, bx1, o));
+                by0 = min(by0, __shfl_down_sync(0xffffffffu, by0, o)); by1 = max(by1, __shfl_down_sync(0xffffffffu, by1, o));
+            }
+            if ((threadIdx.x & 31) == 0)
+            {
+                const int wi = threadIdx.x >> 5;
+                red_ll[wi][0] = t10; red_ll[wi][1] = t01; red_ll[wi][2] = t20; red_ll[wi][3] = t11; red_ll[wi][4] = t02;
+                red_i[wi][0] = bx0; red_i[wi][1] = bx1; red_i[wi][2] = by0; red_i[wi][3] = by1;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                long long u[5] = { 0, 0, 0, 0, 0 };
+                int c0 = INT_MAX, c1 = INT_MIN, c2 = INT_MAX, c3 = INT_MIN;
+                for (int wq = 0; wq < kB3Threads / 32; wq++)
+                {
+                    for (int k = 0; k < 5; k++) u[k] += red_ll[wq][k];
+                    c0 = min(c0, red_i[wq][0]); c1 = max(c1, red_i[wq][1]); c2 = min(c2, red_i[wq][2]); c3 = max(c3, red_i[wq][3]);
+                }
+                r.a10 = u[0]; r.a01 = u[1]; r.a20 = u[2]; r.a11 = u[3]; r.a02 = u[4];
+                r.xmin = c0; r.xmax = c1; r.ymin = c2; r.ymax = c3;
+            }
+            __syncthreads();
+        }
+        const int bw = r.xmax - r.xmin + 1;
         for (int i = threadIdx.x; i < bw; i += kB3Threads) { ylo[i] = INT_MAX; yhi[i] = INT_MIN; }
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += kB3Threads)
@@ -337,8 +438,13 @@ blob_contour_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const uint3
                 ok = !((B[(size_t)ry * g.wpr + (rx >> 5)] >> (rx & 31)) & 1u);
             }
             r.colour_ok = ok;
+            // The host rejects the record if the colour test fails or area / hullArea < 0.95f. Where that is
+            // certain (colour, or a ratio below 0.94: far from any rounding question) the median is not needed.
+            const long long aa = r.a00 < 0 ? -r.a00 : r.a00;
+            s_need_radius = ok && aa * 100 >= r.hull2 * 94;
         }
         __syncthreads();
+        if (!s_need_radius) { __syncthreads(); continue; }
         // median of the point distances to the centre: order statistics (n-1)/2 and n/2 of
         // d2 = dx*dx + dy*dy, selected on the bit patterns (non-negative doubles order like integers)
         const double cx = s_cx, cy = s_cy;
@@ -514,7 +620,7 @@ int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int
     for (int i = 0; i < n; i++) counts_out[i] = 0;
     if (n <= 0 || fs.w <= 0 || fs.h <= 0) return 0;
     BlobGeom g;
-    g.w = fs.w; g.h = fs.h; g.wpr = (fs.w + 31) / 32; g.nframes = n;
+    g.w = fs.w; g.h = fs.h; g.wpr = ((fs.w + 31) / 32 + 3) & ~3; g.nframes = n;      // rows of the planes: multiples of 16 bytes
     const size_t plane_words = (size_t)n * kNThr * g.h * g.wpr;
     BLOB_TRY(grow(&ws->planes, &ws->planes_b, plane_words * 4));
     {
