@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-variant", type=int, default=0)
+    ap.add_argument("--max-points", type=int, default=256, help="per-frame output capacity (the boards have gridn^2 corners)")
     return ap.parse_args()
 
 
@@ -223,7 +224,7 @@ def run_ours(a):
         frames[i].copy_(base_t[(lo + i) % K])
     torch.cuda.synchronize()
 
-    det = api.Detector(max_frames=a.chunk, max_rows=H, max_cols=W, max_points=1024, device=local_rank,
+    det = api.Detector(max_frames=a.chunk, max_rows=H, max_cols=W, max_points=a.max_points, device=local_rank,
                        kernel_variant=a.kernel_variant)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -311,7 +312,7 @@ def run_ours(a):
             ems = float(t.item())
         e2e = {"value": a.frames * W * H / (ems / a.e2e_steps * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(a.frames) * W * H,
-               "d2h_bytes_per_step": int(a.frames) * (1024 * 2 * 4 + 8),
+               "d2h_bytes_per_step": int(a.frames) * (a.max_points * 2 * 4 + 8),
                "note": f"host-pinned frames via mrg_b200_find_corners_batch, {pool_n} frames per call"}
 
     if rank != 0:

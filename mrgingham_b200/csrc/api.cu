@@ -115,6 +115,7 @@ struct mrg_b200_detector
 
     bool profiling = false;
     KernelTimer timers[3];
+    int k2_smem_cands = kClusterSmemCands;   // adapted to the candidate counts of the previous batch (collect_locked)
     BlobWorkspace* blobs = nullptr;
     float blob_ms = 0;
 
@@ -242,7 +243,7 @@ int rerun_big(mrg_b200_detector* det, const uint8_t* image, int on_device, int r
     if (ensure_chunk_scratch(det, S, 1)) return -1;
     CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t), stream));
     if (chess_sparse(det, fs, (cand_t*)det->big_cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
-    ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = reccap; p.records = det->big_records.p;
+    ClusterParams p; p.smem_cands = det->k2_smem_cands; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = reccap; p.records = det->big_records.p;
     {
         Launch l(det, 1, stream);
         CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)det->big_cand.p, (uint32_t*)S.counts.p, (uint32_t*)det->big_table.p,
@@ -309,7 +310,7 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
         if (chess_sparse(det, fs, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
         CUDA_TRY(cudaEventRecord(S.k1done, stream));
         CUDA_TRY(cudaStreamWaitEvent(aux, S.k1done, 0));
-        ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = 2 * mp; p.records = S.records.p;
+        ClusterParams p; p.smem_cands = det->k2_smem_cands; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = 2 * mp; p.records = S.records.p;
         {
             Launch l(det, 1, aux);
             CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, (uint32_t*)S.table.p,
@@ -347,6 +348,16 @@ int collect_locked(mrg_b200_detector* det, int32_t* xy_out, int32_t* counts_out)
                           hxy + (size_t)f * 2 * mp, hc + f, hcc + f)) return -1;
     if (xy_out)     memcpy(xy_out, hxy, sizeof(int32_t) * 2 * mp * pd.nframes);
     if (counts_out) memcpy(counts_out, hc, sizeof(int32_t) * pd.nframes);
+    // Size the clustering kernel's shared memory for the next batch from this one's longest candidate
+    // list (with headroom): 22 KB for lists up to 1024 instead of 90 KB lets its CTAs run beside the
+    // ChESS kernel's. Lists that outgrow the choice still work (global scratch), only slower.
+    {
+        static const bool fixed = getenv("MRG_B200_K2_SMEM_FIXED") != nullptr;
+        int longest = 0;
+        for (int f = 0; f < pd.nframes; f++) longest = std::max(longest, hcc[f]);
+        const int want = longest + longest / 4;
+        if (pd.nframes > 0 && !fixed) det->k2_smem_cands = want <= 1024 ? 1024 : want <= 2048 ? 2048 : kClusterSmemCands;
+    }
     return 0;
 }
 }
@@ -721,7 +732,7 @@ static int refine_frames(mrg_b200_detector* det, cudaStream_t stream, const uint
     CUDA_TRY(cudaMemcpyAsync(det->lvls.p, levels, (size_t)npoints * n, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t) * n, stream));
     if (chess_sparse(det, fs, cand, (uint32_t*)S.counts.p, cap, stream)) return -1;
-    ClusterParams p; p.level = level; p.cand_capacity = cap; p.max_points = det->cfg.max_points;
+    ClusterParams p; p.smem_cands = det->k2_smem_cands; p.level = level; p.cand_capacity = cap; p.max_points = det->cfg.max_points;
     p.record_capacity = npoints; p.records = det->big_records.p;
     {
         Launch l(det, 1, stream);

@@ -214,7 +214,7 @@ struct FrameWork
 // sort_mode: 0 = never sort (caller orders what it needs itself; only valid for the shared-memory
 // path), 1 = always sort into raster order, 2 = sort only lists that live in global scratch
 __device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, const uint32_t* counts,
-                              uint32_t* scratch_table, uint32_t* scratch_dfs, uint8_t* smem, int sort_mode)
+                              uint32_t* scratch_table, uint32_t* scratch_dfs, uint8_t* smem, int sort_mode, int scap)
 {
     const int tid = threadIdx.x;
     const uint32_t total = counts[f];
@@ -223,10 +223,10 @@ __device__ bool prepare_frame(FrameWork& fw, int f, int cap, cand_t* cand_all, c
     int P = 1, lg = 0;
     while (P < n) { P <<= 1; lg++; }
     cand_t* gcand = cand_all + (size_t)f * cap;
-    const bool in_smem = P <= kClusterSmemCands;
+    const bool in_smem = P <= scap;          // scap = candidates the launch's shared memory holds (ClusterParams::smem_cands)
     cand_t*   cand  = in_smem ? (cand_t*)smem : gcand;
-    uint32_t* table = in_smem ? (uint32_t*)(smem + sizeof(cand_t) * kClusterSmemCands) : scratch_table + (size_t)f * 2 * cap;
-    uint32_t* dfs   = in_smem ? (uint32_t*)(smem + (sizeof(cand_t) + 2*sizeof(uint32_t)) * kClusterSmemCands) : scratch_dfs + (size_t)f * cap;
+    uint32_t* table = in_smem ? (uint32_t*)(smem + sizeof(cand_t) * scap) : scratch_table + (size_t)f * 2 * cap;
+    uint32_t* dfs   = in_smem ? (uint32_t*)(smem + (sizeof(cand_t) + 2*sizeof(uint32_t)) * scap) : scratch_dfs + (size_t)f * cap;
 
     for (int i = tid; i < P; i += kClusterThreads)
         cand[i] = i < n ? gcand[i] : ~0ull;
@@ -276,7 +276,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
     __shared__ int s_nrec, s_nout, s_nstart;
     const int f = blockIdx.x, tid = threadIdx.x;
     FrameWork fw;
-    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 2))
+    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 2, p.smem_cands))
     {
         if (tid == 0) out_counts[f] = -1;
         return;
@@ -318,11 +318,11 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         // with no candidate above it and none to its left ("starter") floods its region through the
         // hash table and gives up as soon as it meets a pixel that precedes it in raster order, so
         // exactly one starter per region -- its first pixel -- survives with the full member list.
-        uint16_t* starters = (uint16_t*)(smem + (sizeof(cand_t) + 3*sizeof(uint32_t)) * kClusterSmemCands);
+        uint16_t* starters = (uint16_t*)(smem + (sizeof(cand_t) + 3*sizeof(uint32_t)) * p.smem_cands);
         // pointers derived straight from the shared array, so these accesses compile to LDS/STS
         // (the FrameWork pointers are generic: they may also point at global scratch)
         const cand_t*   scand  = (const cand_t*)smem;
-        const uint32_t* stable = (const uint32_t*)(smem + sizeof(cand_t) * kClusterSmemCands);
+        const uint32_t* stable = (const uint32_t*)(smem + sizeof(cand_t) * p.smem_cands);
         const int n = fw.n;
         if (tid == 0) s_nstart = 0;
         __syncthreads();
@@ -403,7 +403,7 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         sequential = __syncthreads_or(sequential) != 0;
         if (sequential)
         {
-            if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 1)) return;
+            if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 1, p.smem_cands)) return;
             if (tid == 0) s_nrec = 0;
             __syncthreads();
         }
@@ -432,8 +432,8 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
     // surviving records by seed index.
     if (tid == 0) s_nout = 0;
     // (the hash table is no longer needed: reuse its shared memory for the tags when they fit)
-    const bool tags_in_smem = nrec <= 2 * kClusterSmemCands;
-    int32_t* tags = (int32_t*)(smem + sizeof(cand_t) * kClusterSmemCands);
+    const bool tags_in_smem = nrec <= 2 * p.smem_cands;
+    int32_t* tags = (int32_t*)(smem + sizeof(cand_t) * p.smem_cands);
     if (tags_in_smem)
         for (int k = tid; k < nrec; k += kClusterThreads) tags[k] = rec[k].tag;
     __syncthreads();
@@ -477,7 +477,7 @@ cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint
     const int f = blockIdx.x, tid = threadIdx.x;
     if (tid == 0) s_nrefined = 0;
     FrameWork fw;
-    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 1))
+    if (!prepare_frame(fw, f, p.cand_capacity, cand_all, counts, scratch_table, scratch_dfs, smem, 1, p.smem_cands))
     {
         if (tid == 0) out_refined[f] = -1;
         return;
@@ -547,44 +547,52 @@ cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint
     if (tid == 0) out_refined[f] = s_nrefined;
 }
 
-static size_t cluster_smem_bytes() { return (sizeof(cand_t) + 3*sizeof(uint32_t) + sizeof(uint16_t)) * (size_t)kClusterSmemCands; }
+static size_t cluster_smem_bytes(int scap) { return (sizeof(cand_t) + 3*sizeof(uint32_t) + sizeof(uint16_t)) * (size_t)scap; }
+static int checked_smem_cands(const ClusterParams& p)
+{
+    int c = p.smem_cands;
+    if (c != 1024 && c != 2048 && c != 4096) c = kClusterSmemCands;
+    return c;
+}
 
 size_t cluster_record_bytes() { return sizeof(ComponentRecord); }
 
-cudaError_t launch_cluster_find(const FrameSet& fs, const ClusterParams& p,
+cudaError_t launch_cluster_find(const FrameSet& fs, const ClusterParams& p_in,
                                 cand_t* cand, const uint32_t* counts,
                                 uint32_t* scratch_table, uint32_t* scratch_dfs,
                                 int32_t* xy_int, double* xy_dbl, int32_t* out_counts,
                                 cudaStream_t stream)
 {
     if (fs.nframes <= 0) return cudaSuccess;
-    static bool attr_done = false;
-    const size_t smem = cluster_smem_bytes();
-    if (!attr_done)
+    ClusterParams p = p_in;
+    p.smem_cands = checked_smem_cands(p_in);
+    const size_t smem = cluster_smem_bytes(p.smem_cands);
+    if (smem > 48 * 1024)
     {
+        // per device, idempotent and cheap: set on every launch rather than tracking devices
         cudaError_t e = cudaFuncSetAttribute(cluster_find_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     cluster_find_kernel<<<fs.nframes, kClusterThreads, smem, stream>>>(fs, p, cand, counts, scratch_table, scratch_dfs,
                                                                        xy_int, xy_dbl, out_counts);
     return cudaGetLastError();
 }
 
-cudaError_t launch_cluster_refine(const FrameSet& fs, const ClusterParams& p,
+cudaError_t launch_cluster_refine(const FrameSet& fs, const ClusterParams& p_in,
                                   cand_t* cand, const uint32_t* counts,
                                   uint32_t* scratch_table, uint32_t* scratch_dfs,
                                   double* points_xy, signed char* levels, int npoints,
                                   int32_t* out_refined, cudaStream_t stream)
 {
     if (fs.nframes <= 0) return cudaSuccess;
-    static bool attr_done = false;
-    const size_t smem = cluster_smem_bytes();
-    if (!attr_done)
+    ClusterParams p = p_in;
+    p.smem_cands = checked_smem_cands(p_in);
+    const size_t smem = cluster_smem_bytes(p.smem_cands);
+    if (smem > 48 * 1024)
     {
+        // per device, idempotent and cheap: set on every launch rather than tracking devices
         cudaError_t e = cudaFuncSetAttribute(cluster_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     cluster_refine_kernel<<<fs.nframes, kClusterThreads, smem, stream>>>(fs, p, cand, counts, scratch_table, scratch_dfs,
                                                                          points_xy, levels, npoints, out_refined);

@@ -45,6 +45,8 @@ struct ClusterParams
     int      max_points;      // per-frame capacity of the outputs
     int      record_capacity; // per-frame capacity of `records`
     void*    records;         // [nframes][record_capacity] scratch, cluster_record_bytes() each
+    int      smem_cands;      // candidates per frame the clustering CTA keeps in shared memory: 1024, 2048 or
+                              // 4096 (anything else = 4096), 22 bytes each. Longer lists use the global scratch.
 };
 size_t cluster_record_bytes();
 
@@ -105,7 +107,6 @@ void           blob_workspace_destroy(BlobWorkspace* ws);
 int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
                      cudaStream_t stream, float* ms_out);
 
-// shared-memory candidate capacity of the clustering kernel (lists up to this size never touch
-// the global scratch)
+// largest shared-memory candidate capacity of the clustering kernel (ClusterParams::smem_cands)
 constexpr int kClusterSmemCands = 4096;
 }
