@@ -100,6 +100,10 @@ typedef struct
                                  re-run on the GPU with a capacity of rows*cols.                 */
     int max_points;           /* per-frame output capacity (corners); 0 = default 1024           */
     int kernel_variant;       /* 0 = default (cascade); 1 = simple one-thread-per-pixel; 2 = tiled  */
+    int blur_radius;          /* > 0: cv::blur(Size(1+2R,1+2R)) every frame on the GPU before the corner
+                                 detector and the refinement, as the reference CLI does by default with
+                                 R = 1 (mrgingham-from-image.cc:106-111); 0 = frames are used as given.
+                                 Does not apply to the blob detector or the dense response.           */
 } mrg_b200_detector_config;
 
 /* returns 0 and a detector, or <0 */

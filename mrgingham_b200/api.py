@@ -31,7 +31,7 @@ class DetectorConfig(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("max_frames", ctypes.c_int),
                 ("max_rows", ctypes.c_int), ("max_cols", ctypes.c_int),
                 ("candidate_capacity", ctypes.c_int), ("max_points", ctypes.c_int),
-                ("kernel_variant", ctypes.c_int)]
+                ("kernel_variant", ctypes.c_int), ("blur_radius", ctypes.c_int)]
 
 
 def library_path():
@@ -224,9 +224,9 @@ class Detector:
     """Batched detector over equally-sized frames (include/mrgingham_b200.h section C)."""
 
     def __init__(self, max_frames=64, max_rows=0, max_cols=0, candidate_capacity=0, max_points=0, device=-1,
-                 kernel_variant=0):
+                 kernel_variant=0, blur_radius=0):
         self._h = ctypes.c_void_p()
-        cfg = DetectorConfig(device, max_frames, max_rows, max_cols, candidate_capacity, max_points, kernel_variant)
+        cfg = DetectorConfig(device, max_frames, max_rows, max_cols, candidate_capacity, max_points, kernel_variant, blur_radius)
         if lib().mrg_b200_detector_create(ctypes.byref(self._h), ctypes.byref(cfg)) != 0:
             raise RuntimeError("mrg_b200_detector_create() failed (no CUDA device?)")
         self.max_points = max_points if max_points > 0 else 1024

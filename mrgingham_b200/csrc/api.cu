@@ -100,7 +100,7 @@ struct mrg_b200_detector
     // of chunk c+1 (main stream).
     struct Slot
     {
-        DeviceBuffer stage, level_img, cand, counts, table, dfs, records, xy, outcounts;
+        DeviceBuffer stage, blurred, level_img, cand, counts, table, dfs, records, xy, outcounts;
         cudaEvent_t staged = nullptr, k1done = nullptr, k2done = nullptr;
         bool used = false;
     } slot[2];
@@ -173,7 +173,8 @@ LevelGeom level_geom(int rows, int cols, int level)
 // `stream` is made to wait for it) and, for level > 0, builds the level image on `stream`.
 // On return `out` describes the image the detector kernels must read.
 int stage_frames(mrg_b200_detector* det, mrg_b200_detector::Slot& S, const uint8_t* images, int on_device, int n, int rows, int cols,
-                 size_t pitch, size_t fstride, int level, cudaStream_t stream, cudaStream_t cstream, FrameSet* out)
+                 size_t pitch, size_t fstride, int level, cudaStream_t stream, cudaStream_t cstream, FrameSet* out,
+                 bool preprocess = false)
 {
     FrameSet src;
     if (on_device)
@@ -199,6 +200,15 @@ int stage_frames(mrg_b200_detector* det, mrg_b200_detector::Slot& S, const uint8
         src.base = (const uint8_t*)S.stage.p; src.frame_stride = sframe; src.pitch = spitch;
     }
     src.w = cols; src.h = rows; src.nframes = n;
+    if (preprocess && det->cfg.blur_radius > 0)
+    {
+        // the reference CLI's default preprocessing, on the device: the detector reads the blurred copy
+        const int bpitch = round_up(cols, 16);
+        const size_t bframe = (size_t)bpitch * rows;
+        if (S.blurred.ensure(bframe * n)) return -1;
+        CUDA_TRY(launch_box_blur(src, det->cfg.blur_radius, (uint8_t*)S.blurred.p, bpitch, bframe, stream));
+        src.base = (const uint8_t*)S.blurred.p; src.frame_stride = bframe; src.pitch = bpitch;
+    }
     if (level == 0) { *out = src; return 0; }
 
     const LevelGeom g = level_geom(rows, cols, level);
@@ -232,7 +242,7 @@ int rerun_big(mrg_b200_detector* det, const uint8_t* image, int on_device, int r
 {
     mrg_b200_detector::Slot& S = det->slot[0];
     FrameSet fs;
-    if (stage_frames(det, S, image, on_device, 1, rows, cols, pitch, pitch * rows, level, stream, stream, &fs)) return -1;
+    if (stage_frames(det, S, image, on_device, 1, rows, cols, pitch, pitch * rows, level, stream, stream, &fs, true)) return -1;
     const int cap = next_pow2((long long)fs.w * fs.h);
     const int mp = det->cfg.max_points;
     const int reccap = cap / 2 + 1;
@@ -305,7 +315,7 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
             CUDA_TRY(cudaStreamWaitEvent(cpy, S.k2done, 0));
         }
         FrameSet fs;
-        if (stage_frames(det, S, images + (size_t)f0 * fstride, on_device, n, rows, cols, pitch, fstride, level, stream, cpy, &fs)) return -1;
+        if (stage_frames(det, S, images + (size_t)f0 * fstride, on_device, n, rows, cols, pitch, fstride, level, stream, cpy, &fs, true)) return -1;
         CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t) * n, stream));
         if (chess_sparse(det, fs, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
         CUDA_TRY(cudaEventRecord(S.k1done, stream));
@@ -385,6 +395,7 @@ API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detecto
     if (det->cfg.candidate_capacity <= 0) det->cfg.candidate_capacity = 32768;
     det->cfg.candidate_capacity = next_pow2(det->cfg.candidate_capacity);
     if (det->cfg.max_points <= 0) det->cfg.max_points = 1024;
+    if (det->cfg.blur_radius < 0 || det->cfg.blur_radius > 4) { MSG("blur_radius must be in [0,4]; got %d.", det->cfg.blur_radius); delete det; return -1; }
     bool ok = cudaSetDevice(det->device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&det->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               // clustering runs at high priority so its few CTAs slot in as ChESS CTAs retire
@@ -713,7 +724,7 @@ static int refine_frames(mrg_b200_detector* det, cudaStream_t stream, const uint
 {
     mrg_b200_detector::Slot& S = det->slot[0];
     FrameSet fs;
-    if (stage_frames(det, S, images, on_device, n, rows, cols, pitch, fstride, level, stream, stream, &fs)) return -1;
+    if (stage_frames(det, S, images, on_device, n, rows, cols, pitch, fstride, level, stream, stream, &fs, true)) return -1;
     if (det->pts.ensure(sizeof(double) * 2 * npoints * n)) return -1;
     if (det->lvls.ensure((size_t)npoints * n)) return -1;
     if (ensure_chunk_scratch(det, S, n)) return -1;

@@ -50,3 +50,26 @@ def test_gpu_blur_matches_oracle():
         want = po.find_corners(b, 0)
         assert counts[i] == len(want) == 100 and np.array_equal(xy[i, :counts[i]], want)
     det.close()
+
+
+@pytest.mark.gpu
+def test_detector_with_cli_default_preprocessing():
+    # blur_radius=1 in the detector config = the reference CLI's default chain (blur, then find corners /
+    # refine), all on the device: raw frames in, the corners of the blurred frames out
+    from mrgingham_b200 import api
+    api._require_gpu()
+    raw = np.stack([synth.board_frame(800, 608, 10, seed=s, blur=False) for s in (5, 6, 7)])
+    det = api.Detector(max_frames=2, max_points=2048, blur_radius=1)
+    for level in (0, 1, 2):
+        xy, counts = det.find_corners(raw, level)
+        for i in range(len(raw)):
+            want = po.find_corners(po.box_blur(raw[i], 1), level)
+            assert counts[i] == len(want) and np.array_equal(xy[i, :counts[i]], want), (level, i)
+    # refinement reads the blurred frame too
+    b0 = po.box_blur(raw[0], 1)
+    pts = po.find_corners(b0, 1).astype(np.float64) / 1000.0
+    lv = np.full(len(pts), 1, np.int8)
+    n_want, xy_want, lv_want = po.refine_corners(b0, 0, pts, lv)
+    n_got, xy_got, lv_got = det.refine_corners(raw[:1], 0, pts[None], lv[None])
+    assert n_got[0] == n_want and np.array_equal(xy_got[0], xy_want) and np.array_equal(lv_got[0], lv_want)
+    det.close()
