@@ -66,7 +66,8 @@ struct CascadeParams
 {
     int nstrips, nsegs, seg_rows;   // work decomposition: item = (frame, segment, strip)
     int cap;
-    int stages, lookahead;
+    int stages;                     // depth of the shared-memory ring (TMA stages of 11 rows)
+    int nocarry;                    // 1: settle every flagged cell in its own block (2 stages held instead of 3)
 };
 
 struct WarpQueues
@@ -428,7 +429,7 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
             q_head += 32u;
             l3_phase(c, q, l3_head, false, lane);
         }
-        if ((int)(prev_mark - q_head) > 0 || (tp.lookahead && tail != q_head))   // lookahead != 0: never carry cells over
+        if ((int)(prev_mark - q_head) > 0 || (tp.nocarry && tail != q_head))
         {
             l2_batch(c, L, q, q_head, tail - q_head, lane);
             q_head = tail;
@@ -437,7 +438,7 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
         prev_mark = tail;
         // every cell of block it-1 is settled: this warp is done with the stage of block it-2
         // (of block it-1 when cells are never carried over)
-        const int hold = tp.lookahead ? 1 : 2;
+        const int hold = tp.nocarry ? 1 : 2;
         if (it >= hold) { release(it - hold, s_rel); if (++s_rel == nst) s_rel = 0; }
         if (++s == nst) { s = 0; full_parity ^= 1; }
     }
@@ -525,8 +526,9 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     CascadeParams tp;
     tp.cap = cand_capacity;
     // a stage is handed back two blocks after it was consumed (L2 reads it), so 3 stages are always held
-    tp.lookahead = env_int("MRG_B200_K1_NOCARRY", 0, 0, 1);     // experiment: settle every cell in its own block (2 stages held)
-    tp.stages = env_int("MRG_B200_K1_STAGES", 4, tp.lookahead ? 3 : 4, 12);
+    // tuning knobs (defaults are what bench.py measures): MRG_B200_K1_NW, MRG_B200_K1_STAGES, MRG_B200_K1_NOCARRY
+    tp.nocarry = env_int("MRG_B200_K1_NOCARRY", 0, 0, 1);
+    tp.stages = env_int("MRG_B200_K1_STAGES", 4, tp.nocarry ? 3 : 4, 12);
     const int sw = kWarpPx * nw;
     tp.nstrips = (fs.w - kMargin + sw - 1) / sw;
     const int out_rows = fs.h - 2*kMargin;
