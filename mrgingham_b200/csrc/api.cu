@@ -610,8 +610,21 @@ API int mrg_b200_find_blobs_batch(mrg_b200_detector* det, const uint8_t* images,
         if (stage_frames(det, det->slot[0], images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride,
                          0, stream, stream, &fs)) return -1;
         float ms = 0;
-        if (blob_find_frames(det->blobs, fs, xy_out + (size_t)f0 * 2 * mp, counts_out + f0, mp, stream, det->profiling ? &ms : nullptr)) return -1;
+        const int rc = blob_find_frames(det->blobs, fs, xy_out + (size_t)f0 * 2 * mp, counts_out + f0, mp, stream, det->profiling ? &ms : nullptr);
+        if (rc < 0) return -1;
         det->blob_ms += ms;
+        if (rc == 1)
+        {
+            // some frame of the chunk needs more scratch than the default: frame by frame, on the GPU
+            for (int i = 0; i < n; i++)
+            {
+                FrameSet one = fs; one.base = fs.base + (size_t)i * fs.frame_stride; one.nframes = 1;
+                if (blob_find_frames(det->blobs, one, xy_out + (size_t)(f0 + i) * 2 * mp, counts_out + f0 + i, mp, stream,
+                                     det->profiling ? &ms : nullptr)) return -1;
+                det->blob_ms += ms;
+                blob_workspace_reset_capacity(det->blobs);
+            }
+        }
     }
     return 0;
 }

@@ -226,8 +226,13 @@ struct Tracer
                 const int s_raw = s + 1 + j;                                     // what the original's ++s loop ends on (<= 15)
                 s = s_raw & 7;
                 const int x4 = x3 + kDx[s], y4 = y3 + kDy[s];
-                if ((unsigned)(s - 1) < (unsigned)s_end) { P.set_visited(x3, y3); P.set_rflag(x3, y3); }
-                else if (!P.visited(x3, y3)) P.set_visited(x3, y3);
+                // marks of (x3, y3): one look-up of the cached mark words per step
+                {
+                    P.seek_marks(x3, y3);
+                    const uint32_t bit = 1u << (x3 & 31);
+                    if ((unsigned)(s - 1) < (unsigned)s_end) { P.vword |= bit; P.rword |= bit; P.dirty = true; }
+                    else if (!(P.vword & bit)) { P.vword |= bit; P.dirty = true; }
+                }
                 if (!emit(x3, y3)) return false;
                 if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
                 x3 = x4; y3 = y4;
@@ -254,7 +259,11 @@ __global__ void __launch_bounds__(32)
 blob_trace_kernel(BlobGeom g, const uint32_t* __restrict__ planes, uint32_t* marksV, uint32_t* marksR,
                   uint32_t* pts, BlobRecord* recs, unsigned* rec_count, int* status)
 {
-    if (threadIdx.x != 0) return;
+    // One warp per (frame, threshold). The raster scan for 0/1 transitions is done by all 32 lanes
+    // (a lane looks at four words = 128 pixels; a 4K row is one coalesced 512-byte load); the groups that
+    // hold transitions are then handed, in raster order, to lane 0, which owns the mark planes and
+    // follows the borders exactly as the sequential original does.
+    const int lane = threadIdx.x;
     const int job = blockIdx.x, f = job / kNThr, k = job % kNThr;
     const size_t poff = ((size_t)f * kNThr + k) * g.h * g.wpr;
     Tracer T;
@@ -264,24 +273,22 @@ blob_trace_kernel(BlobGeom g, const uint32_t* __restrict__ planes, uint32_t* mar
     T.recs = recs; T.rec_count = rec_count; T.rec_cap = g.rec_cap; T.status = status;
     T.frame = f; T.thr = k; T.seq = 0;
 
-    // The scan runs on one thread, so its cost is instructions per word: rows are read four words at
-    // a time (the next group is requested before the current one is examined; wpr is a multiple of 4
-    // and the planes are 16-byte aligned) and a group without any 0/1 transition costs ~16 instructions.
-    const int groups = g.wpr / 4;
+    const int groups = g.wpr / 4;                         // wpr is a multiple of 4, the planes are 16-byte aligned
     for (int y = 0; y < g.h; y++)
     {
         const uint4* brow = reinterpret_cast<const uint4*>(T.P.B + (size_t)y * g.wpr);
-        uint32_t prevbit = 0;
-        uint4 nxt = brow[0];
-        for (int gi = 0; gi < groups; gi++)
+        uint32_t carry = 0;                               // last pixel of the previous 32 groups
+        for (int g0 = 0; g0 < groups; g0 += 32)
         {
-            const uint4 q = nxt;
-            if (gi + 1 < groups) nxt = brow[gi + 1];
+            const int gi = g0 + lane;
+            const uint4 q = gi < groups ? brow[gi] : make_uint4(0, 0, 0, 0);
+            const uint32_t pw = __shfl_up_sync(0xffffffffu, q.w, 1);
+            const uint32_t prevbit = lane == 0 ? carry : pw >> 31;
+            carry = __shfl_sync(0xffffffffu, q.w, 31) >> 31;
             // pixels that differ from their left neighbour
             uint32_t e0 = q.x ^ ((q.x << 1) | prevbit), e1 = q.y ^ ((q.y << 1) | (q.x >> 31));
             uint32_t e2 = q.z ^ ((q.z << 1) | (q.y >> 31)), e3 = q.w ^ ((q.w << 1) | (q.z >> 31));
-            prevbit = q.w >> 31;
-            const int left = g.w - gi * 128;                     // only x < w is examined (the scan stops before the frame)
+            const int left = g.w - gi * 128;              // only x < w is examined (the scan stops before the frame)
             if (left < 128)
             {
                 e0 &= left >= 32 ? ~0u : (left > 0 ? (1u << left) - 1 : 0u);
@@ -289,24 +296,39 @@ blob_trace_kernel(BlobGeom g, const uint32_t* __restrict__ planes, uint32_t* mar
                 e2 &= left >= 96 ? ~0u : (left > 64 ? (1u << (left - 64)) - 1 : 0u);
                 e3 &= left > 96 ? (1u << (left - 96)) - 1 : 0u;
             }
-            if ((e0 | e1 | e2 | e3) == 0) continue;
-#pragma unroll 1
-            for (int k = 0; k < 4; k++)
+            uint32_t m = __ballot_sync(0xffffffffu, (e0 | e1 | e2 | e3) != 0);
+            while (m)
             {
-                uint32_t ev = k == 0 ? e0 : k == 1 ? e1 : k == 2 ? e2 : e3;
-                const uint32_t cur = k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w;
-                while (ev)
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t cx = __shfl_sync(0xffffffffu, q.x, src), cy = __shfl_sync(0xffffffffu, q.y, src);
+                const uint32_t cz = __shfl_sync(0xffffffffu, q.z, src), cw = __shfl_sync(0xffffffffu, q.w, src);
+                const uint32_t f0 = __shfl_sync(0xffffffffu, e0, src), f1 = __shfl_sync(0xffffffffu, e1, src);
+                const uint32_t f2 = __shfl_sync(0xffffffffu, e2, src), f3 = __shfl_sync(0xffffffffu, e3, src);
+                int failed = 0;
+                if (lane == 0)
                 {
-                    const int bb = __ffs(ev) - 1;
-                    ev &= ev - 1;
-                    const int x = (gi * 4 + k) * 32 + bb;
-                    // 0 -> 1: an outer border starts here unless the pixel was already visited;
-                    // 1 -> 0: a hole border starts at x-1 unless that pixel carries the east flag
-                    const bool hole = !((cur >> bb) & 1u);
-                    const int sx = x - (hole ? 1 : 0);
-                    const bool start = hole ? !T.P.rflag(sx, y) : !T.P.visited(sx, y);
-                    if (start && !T.trace(sx, y, hole)) { atomicExch(status, 1); return; }
+#pragma unroll 1
+                    for (int kk = 0; kk < 4 && !failed; kk++)
+                    {
+                        uint32_t ev = kk == 0 ? f0 : kk == 1 ? f1 : kk == 2 ? f2 : f3;
+                        const uint32_t cur = kk == 0 ? cx : kk == 1 ? cy : kk == 2 ? cz : cw;
+                        while (ev)
+                        {
+                            const int bb = __ffs(ev) - 1;
+                            ev &= ev - 1;
+                            const int x = ((g0 + src) * 4 + kk) * 32 + bb;
+                            // 0 -> 1: an outer border starts here unless the pixel was already visited;
+                            // 1 -> 0: a hole border starts at x-1 unless that pixel carries the east flag
+                            const bool hole = !((cur >> bb) & 1u);
+                            const int sx = x - (hole ? 1 : 0);
+                            const bool start = hole ? !T.P.rflag(sx, y) : !T.P.visited(sx, y);
+                            if (start && !T.trace(sx, y, hole)) { failed = 1; break; }
+                        }
+                    }
                 }
+                failed = __shfl_sync(0xffffffffu, failed, 0);
+                if (failed) { if (lane == 0) atomicExch(status, 1); return; }
             }
         }
     }
@@ -612,7 +634,10 @@ static cudaError_t grow(void** p, size_t* have, size_t want)
     fprintf(stderr, "%s:%d in %s(): CUDA failure '%s' in " #expr ". Sorry.\n", __FILE__, __LINE__, __func__, cudaGetErrorString(_e)); return -1; } } while (0)
 
 // Blob detection over device-resident frames. xy_out: HOST [nframes][max_points][2] int32 (scaled
-// by 1000), counts_out: HOST [nframes]. Synchronous. Returns 0, or -1 on a CUDA failure.
+// by 1000), counts_out: HOST [nframes]. Synchronous. Returns 0, -1 on a CUDA failure, or 1 when the
+// scratch of a multi-frame chunk overflowed (nothing was produced: run the frames one at a time).
+void blob_workspace_reset_capacity(BlobWorkspace* ws) { ws->pts_cap = 1u << 18; ws->rec_per_job = 512; }
+
 int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
                      cudaStream_t stream, float* ms_out)
 {
@@ -663,7 +688,10 @@ int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int
             if (hc[0]) BLOB_TRY(cudaMemcpy(ws->host_recs.data(), ws->recs, sizeof(BlobRecord) * hc[0], cudaMemcpyDeviceToHost));
             break;
         }
-        // a point region or the record list overflowed: run the chunk again with four times the space
+        // A point region or the record list overflowed. A single frame is run again with four times the
+        // space; a chunk of several frames is handed back to the caller, who runs its frames one by one
+        // (growing the scratch for a whole chunk could ask for tens of GB because of one busy frame).
+        if (n > 1) { if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return 1; }
         if (attempt >= 6) { fprintf(stderr, "%s:%d in %s(): blob scratch still overflows after growing it 4096x. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
         ws->pts_cap *= 4; ws->rec_per_job *= 4;
     }

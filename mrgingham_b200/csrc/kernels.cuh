@@ -104,6 +104,9 @@ BlobWorkspace* blob_workspace_create();
 void           blob_workspace_destroy(BlobWorkspace* ws);
 // xy_out: HOST int32 [nframes][max_points][2] scaled by 1000, counts_out: HOST int32 [nframes].
 // Synchronous on `stream`. ms_out (optional): device time of the three kernels (CUDA events).
+// Returns 0; -1 on a CUDA failure; 1 if the scratch of a multi-frame chunk overflowed (nothing was
+// produced: call again frame by frame, then blob_workspace_reset_capacity()).
+void blob_workspace_reset_capacity(BlobWorkspace* ws);
 int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
                      cudaStream_t stream, float* ms_out);
 

@@ -82,6 +82,22 @@ def test_blobs_noise_overflows_default_scratch(api, oracle):
     det.close()
 
 
+def test_blobs_busy_frame_inside_a_chunk(api, oracle):
+    # one noise frame among ordinary ones: the chunk overflows its scratch and is redone frame by frame
+    frames = np.stack([synth.circle_grid_frame(640, 480, 8, seed=61), synth.noise_frame(640, 480, seed=62),
+                       synth.board_frame(640, 480, 10, seed=63)])
+    det = api.Detector(max_frames=3, max_points=4096)
+    xy, counts = det.find_blobs(frames)
+    for i in range(3):
+        want = oracle.find_blobs(frames[i])
+        assert counts[i] == len(want) and np.array_equal(xy[i, :counts[i]], want), i
+    xy, counts = det.find_blobs(frames[::2])          # and the workspace is back to normal afterwards
+    for k, i in enumerate((0, 2)):
+        want = oracle.find_blobs(frames[i])
+        assert counts[k] == len(want) and np.array_equal(xy[k, :counts[k]], want)
+    det.close()
+
+
 def test_blobs_4k_board(api, oracle):
     frame = synth.board_frame(3840, 2160, 14, seed=70)
     got = api.find_blobs_int(frame)
