@@ -263,7 +263,7 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
 }
 
 template<int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, 5)     // shared memory already limits a SM to 5 CTAs of 3 warps; the hint lets ptxas keep ~96 registers for scheduling
 chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, CascadeParams tp,
                      cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
 {
