@@ -491,7 +491,8 @@ API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* ima
             if (S.cand.ensure(sizeof(int16_t) * fe * n)) return -1;
             dresp = (int16_t*)S.cand.p;
         }
-        CUDA_TRY(launch_chess_dense(fs, dresp, fe, stream));
+        if (det->cfg.kernel_variant == 1) CUDA_TRY(launch_chess_dense(fs, dresp, fe, stream));
+        else                              CUDA_TRY(launch_chess_dense_tiled(fs, dresp, fe, stream));
         if (!response_on_device && cols > 2*kMargin && rows > 2*kMargin)
         {
             // only the interior travels back: the caller's border elements stay untouched (ChESS.c:62-63)

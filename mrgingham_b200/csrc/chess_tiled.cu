@@ -73,9 +73,11 @@ __device__ __forceinline__ uint32_t h2absadd(uint32_t a, uint32_t b)   // |a| + 
 // q_o is the pair (X+o, X+o+1). Pair 0 samples the ring at column offsets {-5,-4,-2,0,+2,+4,+5}
 // -> q_-5, q_-4, q_-2, q_0, q_2, q_4, q_5; pair 2 at the same offsets from X+2
 // -> q_-3, q_-2, q_0, q_2, q_4, q_6, q_7: four of the fourteen are shared.
-struct RowPairs { uint32_t m5, m4, m3, m2, c0, p2, p4, p5, p6, p7; };
+struct RowPairs { uint32_t m5, m4, m3, m2, c0, p2, p4, p5, p6, p7;
+                  uint32_t m1, p1, p3; };     // only filled in dense mode: the pairs local_mean needs
 
 // `row` points at the staged word holding bytes X-8..X-5 of this thread.
+template<bool DENSE>
 __device__ __forceinline__ RowPairs unpack_row(const uint8_t* row)
 {
     RowPairs q;
@@ -91,6 +93,13 @@ __device__ __forceinline__ RowPairs unpack_row(const uint8_t* row)
     q.p5 = __byte_perm(D, 0, 0x4241);
     q.p6 = __byte_perm(D, 0, 0x4342);
     q.p7 = __byte_perm(__byte_perm(D, E, 0x0043), 0, 0x4140);              // X+7 | X+8 straddles two words
+    if (DENSE)
+    {
+        q.m1 = __byte_perm(__byte_perm(B, C, 0x0043), 0, 0x4140);          // X-1 | X
+        q.p1 = __byte_perm(C, 0, 0x4241);                                  // X+1 | X+2
+        q.p3 = __byte_perm(__byte_perm(C, D, 0x0043), 0, 0x4140);          // X+3 | X+4
+    }
+    else q.m1 = q.p1 = q.p3 = 0;
     return q;
 }
 
@@ -172,10 +181,33 @@ __device__ __forceinline__ uint32_t pair_test(uint32_t a0, uint32_t b0, uint32_t
     return sumr - diff + 0x7FF07FF0u;
 }
 
-template<bool USE_TMA>
+// Dense mode: the exact response (ChESS.c:93-104) of one pixel pair from its sixteen ring-sample
+// pairs (a_k, b_k) = (s_k, s_k+8) and the three centre pairs (x-1, x, x+1); two int16 in one word.
+__device__ __forceinline__ uint32_t pair_response(uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2,
+                                                  uint32_t a3, uint32_t b3, uint32_t a4, uint32_t b4, uint32_t a5, uint32_t b5,
+                                                  uint32_t a6, uint32_t b6, uint32_t a7, uint32_t b7,
+                                                  uint32_t cm1, uint32_t c0, uint32_t cp1)
+{
+    const uint32_t p0 = a0 + b0, p1 = a1 + b1, p2 = a2 + b2, p3 = a3 + b3;
+    const uint32_t p4 = a4 + b4, p5 = a5 + b5, p6 = a6 + b6, p7 = a7 + b7;
+    // sum_response, half2 lanes (exact: every value <= 2040)
+    const uint32_t sumr = h2absadd(h2absadd(h2sub(p0, p4), h2sub(p1, p5)), h2absadd(h2sub(p2, p6), h2sub(p3, p7)));
+    const uint32_t diff = (__vabsdiffu4(a0, b0) + __vabsdiffu4(a1, b1)) + (__vabsdiffu4(a2, b2) + __vabsdiffu4(a3, b3)) +
+                          (__vabsdiffu4(a4, b4) + __vabsdiffu4(a5, b5)) + (__vabsdiffu4(a6, b6) + __vabsdiffu4(a7, b7));
+    const uint32_t mean = ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7));     // <= 4080 per lane
+    const uint32_t s3 = cm1 + c0 + cp1;                                          // <= 765 per lane
+    // local_mean = s3*16/3 truncated = (s3 * 699056) >> 17 for s3 <= 765 (checked exhaustively)
+    const int lm0 = (int)(((s3 & 0xFFFFu) * 699056u) >> 17), lm1 = (int)(((s3 >> 16) * 699056u) >> 17);
+    const int r0 = (int)(sumr & 0xFFFFu) - (int)(diff & 0xFFFFu) - abs((int)(mean & 0xFFFFu) - lm0);
+    const int r1 = (int)(sumr >> 16) - (int)(diff >> 16) - abs((int)(mean >> 16) - lm1);
+    return ((uint32_t)r0 & 0xFFFFu) | ((uint32_t)r1 << 16);
+}
+
+template<bool USE_TMA, bool DENSE>
 __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameSet& fs, const TileParams& tp,
                                            uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar, int* next_issue,
-                                           cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
+                                           cand_t* __restrict__ cand, uint32_t* __restrict__ counts,
+                                           int16_t* __restrict__ response = nullptr, size_t resp_frame_stride = 0)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     const int item = blockIdx.x;
@@ -232,9 +264,16 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
     // dy = +-4 uses q_{-4,4} / q_{-2,6}; dy = 0,+-2 uses q_{-5,5} / q_{-3,7}.
     uint32_t Wm5[kStageRows], Wm4[kStageRows], Wm3[kStageRows], Wm2[kStageRows], W0[kStageRows];
     uint32_t Wp2[kStageRows], Wp4[kStageRows], Wp5[kStageRows], Wp6[kStageRows], Wp7[kStageRows];
+    uint32_t Wm1[kStageRows], Wp1[kStageRows], Wp3[kStageRows];     // dense mode: centre pairs of the row 5 steps back
 #pragma unroll
     for (int j = 0; j < kStageRows; j++)
+    {
         Wm5[j] = Wm4[j] = Wm3[j] = Wm2[j] = W0[j] = Wp2[j] = Wp4[j] = Wp5[j] = Wp6[j] = Wp7[j] = 0;
+        Wm1[j] = Wp1[j] = Wp3[j] = 0;
+    }
+    int16_t* resp = DENSE ? response + (size_t)f * resp_frame_stride : nullptr;
+    // 8-byte stores of four responses need aligned rows; border columns are written one by one
+    const bool wide_ok = DENSE && !((uintptr_t)resp & 7) && !(w & 3);
 
 #pragma unroll 1
     for (int it = 0; it < nit; it++)
@@ -261,7 +300,7 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
 #pragma unroll
         for (int j = 0; j < kStageRows; j++)
         {
-            const RowPairs n = unpack_row(stage + j * kRowBytes);
+            const RowPairs n = unpack_row<DENSE>(stage + j * kRowBytes);
             // Rows outside [ys,ye) (window priming, segment tail) are computed like any other and
             // dropped below: cheaper than a test on the always-executed path.
             // The window slot of row R-k is (j + 11 - k) % 11; the new row R goes to slot j.
@@ -270,6 +309,32 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
             // opposite ring samples (s_k, s_k+8), k = 0..7:
             //   (+2,-5)(-2,+5)  (0,-5)(0,+5)  (-2,-5)(+2,+5)  (-4,-4)(+4,+4)
             //   (-5,-2)(+5,+2)  (-5,0)(+5,0)  (-5,+2)(+5,-2)  (-4,+4)(+4,-4)
+            if (DENSE)
+            {
+                // all four responses of the word, exactly; only interior pixels are written (ChESS.c:62-63)
+                const uint32_t ra = pair_response(Wp2[r10], n.m2,  W0[r10],  n.c0,  Wm2[r10], n.p2,  Wm4[r9],  Wp4[r1],
+                                                  Wm5[r7],  Wp5[r3], Wm5[r5], Wp5[r5], Wm5[r3], Wp5[r7], Wm4[r1], Wp4[r9],
+                                                  Wm1[r5], W0[r5], Wp1[r5]);
+                const uint32_t rb = pair_response(Wp4[r10], n.c0,  Wp2[r10], n.p2,  W0[r10],  n.p4,  Wm2[r9],  Wp6[r1],
+                                                  Wm3[r7],  Wp7[r3], Wm3[r5], Wp7[r5], Wm3[r3], Wp7[r7], Wm2[r1], Wp6[r9],
+                                                  Wp1[r5], Wp2[r5], Wp3[r5]);
+                const int y = ybase + j;
+                if (y >= ys && y < ye && x < w - kMargin && x + 3 >= kMargin)
+                {
+                    int16_t* o = resp + (size_t)y * w + x;
+                    if (wide_ok && x >= kMargin && x + 3 < w - kMargin)
+                        *reinterpret_cast<uint2*>(o) = make_uint2(ra, rb);
+                    else
+                    {
+                        const uint32_t v[2] = { ra, rb };
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if (x + i >= kMargin && x + i < w - kMargin) o[i] = (int16_t)(v[i >> 1] >> (16 * (i & 1)));
+                    }
+                }
+            }
+            else
+            {
             const uint32_t t0 = pair_test(Wp2[r10], n.m2,  W0[r10],  n.c0,  Wm2[r10], n.p2,  Wm4[r9],  Wp4[r1],
                                           Wm5[r7],  Wp5[r3], Wm5[r5], Wp5[r5], Wm5[r3], Wp5[r7], Wm4[r1], Wp4[r9]);
             const uint32_t t2 = pair_test(Wp4[r10], n.c0,  Wp2[r10], n.p2,  W0[r10],  n.p4,  Wm2[r9],  Wp6[r1],
@@ -277,8 +342,10 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
             // response <= sum - diff: only rows where some lane reaches the threshold can hold a
             // candidate; they are settled exactly after the block.
             if ((t0 | t2) & 0x80008000u) pending |= 1u << j;
+            }
             Wm5[j] = n.m5; Wm4[j] = n.m4; Wm3[j] = n.m3; Wm2[j] = n.m2; W0[j] = n.c0;
             Wp2[j] = n.p2; Wp4[j] = n.p4; Wp5[j] = n.p5; Wp6[j] = n.p6; Wp7[j] = n.p7;
+            if (DENSE) { Wm1[j] = n.m1; Wp1[j] = n.p1; Wp3[j] = n.p3; }
         }
 
         pending = __reduce_or_sync(kFull, pending);
@@ -301,10 +368,11 @@ __device__ __forceinline__ void strip_walk(const CUtensorMap* tmap, const FrameS
     }
 }
 
-template<bool USE_TMA>
-__global__ void __launch_bounds__(kTileThreads, 8)
+template<bool USE_TMA, bool DENSE>
+__global__ void __launch_bounds__(kTileThreads, DENSE ? 4 : 8)
 chess_tiled_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, TileParams tp,
-                   cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
+                   cand_t* __restrict__ cand, uint32_t* __restrict__ counts,
+                   int16_t* __restrict__ response, size_t resp_frame_stride)
 {
     __shared__ __align__(128) uint8_t ring[kStages * kStageBytes];
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
@@ -319,7 +387,7 @@ chess_tiled_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, TilePa
         }
         __syncthreads();
     }
-    strip_walk<USE_TMA>(&tmap, fs, tp, ring, full_bar, empty_bar, &next_issue, cand, counts);
+    strip_walk<USE_TMA, DENSE>(&tmap, fs, tp, ring, full_bar, empty_bar, &next_issue, cand, counts, response, resp_frame_stride);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -343,8 +411,8 @@ static bool make_tensor_map(CUtensorMap* map, const FrameSet& fs)
     return r == CUDA_SUCCESS;
 }
 
-cudaError_t launch_chess_sparse_tiled(const FrameSet& fs, cand_t* cand, uint32_t* counts,
-                                      int cand_capacity, cudaStream_t stream)
+static cudaError_t launch_tiled(const FrameSet& fs, cand_t* cand, uint32_t* counts, int cand_capacity,
+                                int16_t* response, size_t resp_frame_stride, cudaStream_t stream)
 {
     if (fs.w <= 2*kMargin || fs.h <= 2*kMargin || fs.nframes <= 0) return cudaSuccess;
     TileParams tp;
@@ -365,14 +433,34 @@ cudaError_t launch_chess_sparse_tiled(const FrameSet& fs, cand_t* cand, uint32_t
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
 
     CUtensorMap map;
-    if (make_tensor_map(&map, fs))
-        chess_tiled_kernel<true><<<(unsigned)items, kTileThreads, 0, stream>>>(map, fs, tp, cand, counts);
+    const bool tma = make_tensor_map(&map, fs);
+    if (!tma) memset(&map, 0, sizeof(map));
+    const unsigned grid = (unsigned)items;
+    if (response)
+    {
+        if (tma) chess_tiled_kernel<true,  true><<<grid, kTileThreads, 0, stream>>>(map, fs, tp, nullptr, nullptr, response, resp_frame_stride);
+        else     chess_tiled_kernel<false, true><<<grid, kTileThreads, 0, stream>>>(map, fs, tp, nullptr, nullptr, response, resp_frame_stride);
+    }
     else
     {
-        memset(&map, 0, sizeof(map));
-        chess_tiled_kernel<false><<<(unsigned)items, kTileThreads, 0, stream>>>(map, fs, tp, cand, counts);
+        if (tma) chess_tiled_kernel<true,  false><<<grid, kTileThreads, 0, stream>>>(map, fs, tp, cand, counts, nullptr, 0);
+        else     chess_tiled_kernel<false, false><<<grid, kTileThreads, 0, stream>>>(map, fs, tp, cand, counts, nullptr, 0);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_chess_sparse_tiled(const FrameSet& fs, cand_t* cand, uint32_t* counts,
+                                      int cand_capacity, cudaStream_t stream)
+{
+    return launch_tiled(fs, cand, counts, cand_capacity, nullptr, 0, stream);
+}
+
+// Dense int16 response (mrgingham_ChESS_response_5, ChESS.c:55-106) with the tiled kernel's machinery:
+// every interior pixel's exact response, 1 byte read + 2 bytes written per pixel.
+cudaError_t launch_chess_dense_tiled(const FrameSet& fs, int16_t* response, size_t response_frame_stride_elems,
+                                     cudaStream_t stream)
+{
+    return launch_tiled(fs, nullptr, nullptr, 0, response, response_frame_stride_elems, stream);
 }
 
 }

@@ -74,6 +74,11 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
 cudaError_t launch_chess_dense(const FrameSet& fs, int16_t* response, size_t response_frame_stride_elems,
                                cudaStream_t stream);
 
+// the same through the tiled kernel's TMA ring and packed 16-bit lanes (production path of the dense API;
+// launch_chess_dense above is the one-thread-per-pixel cross-check)
+cudaError_t launch_chess_dense_tiled(const FrameSet& fs, int16_t* response, size_t response_frame_stride_elems,
+                                     cudaStream_t stream);
+
 // K2: per-frame clustering of the candidate lists, exact emulation of
 // process_connected_components()'s find branch. One CTA per frame.
 //   cand/counts      from K1 (lists are sorted in place)

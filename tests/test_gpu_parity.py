@@ -365,3 +365,18 @@ def test_cascade_adversarial_frames(api, oracle):
         xy, counts = det.find_corners(frames, 0)
         _check_batch(xy, counts, frames, oracle, 0)
         det.close()
+
+
+def test_dense_response_kernels_agree(api, oracle):
+    # the dense API runs the tiled kernel's dense mode by default and the one-thread-per-pixel kernel with
+    # kernel_variant=1; both must equal the oracle on every interior pixel, for aligned and odd shapes
+    rng = np.random.default_rng(11)
+    for (w, h) in ((640, 480), (611, 457), (250, 64), (1030, 40), (15, 15), (16, 33), (257, 15)):
+        imgs = np.stack([synth.blurred_noise_frame(w, h, seed=int(w + h), passes=1),
+                         (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)])
+        for variant in (0, 1):
+            det = api.Detector(max_frames=2, kernel_variant=variant)
+            got = det.chess_response(imgs)
+            for i in range(2):
+                assert np.array_equal(got[i], oracle.chess_response_5(imgs[i], fill=0)), (w, h, variant, i)
+            det.close()
