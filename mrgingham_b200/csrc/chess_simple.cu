@@ -272,10 +272,68 @@ cudaError_t launch_box_blur(const FrameSet& src, int radius, uint8_t* dst, int d
     return cudaGetLastError();
 }
 
+// Level 1 fast path (every BASELINE size: W % 32 == 0, H even, 16-byte aligned rows): HBM-bound,
+// 1 byte read + 1/4 byte written per frame pixel. A thread turns two 128-bit loads (16 pixels of rows
+// 2dy and 2dy+1) into 8 output pixels; each 2x2 sum is two IDP.4A against a two-byte mask, seeded with
+// the rounding constant: out = (a + b + c + d + 2) >> 2, which is what cv::resize gives for exact halving
+// (no partial cells exist when W % 4 != 3 and H % 4 != 3).
+__global__ void __launch_bounds__(256)
+pyramid_l1_kernel(FrameSet src, uint8_t* __restrict__ dst, int dst_pitch, size_t dst_frame_stride, int ow, int oh)
+{
+    const int f = blockIdx.z, dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int g = blockIdx.x * 32 + (threadIdx.x & 31);          // group of 8 output pixels
+    if (dy >= oh || g * 8 >= ow) return;
+    const uint8_t* r0 = src.base + (size_t)f * src.frame_stride + (size_t)(2 * dy) * src.pitch + g * 16;
+    const uint4 a = *reinterpret_cast<const uint4*>(r0), b = *reinterpret_cast<const uint4*>(r0 + src.pitch);
+    const uint32_t wa[4] = { a.x, a.y, a.z, a.w }, wb[4] = { b.x, b.y, b.z, b.w };
+    uint32_t o[2] = { 0, 0 };
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+    {
+        const uint32_t lo = (uint32_t)__dp4a(wa[k], 0x00000101u, __dp4a(wb[k], 0x00000101u, 2u)) >> 2;
+        const uint32_t hi = (uint32_t)__dp4a(wa[k], 0x01010000u, __dp4a(wb[k], 0x01010000u, 2u)) >> 2;
+        o[k >> 1] |= (lo | (hi << 8)) << (16 * (k & 1));
+    }
+    *reinterpret_cast<uint2*>(dst + (size_t)f * dst_frame_stride + (size_t)dy * dst_pitch + g * 8) = make_uint2(o[0], o[1]);
+}
+
+// Level 2 fast path (W % 64 == 0, H % 4 == 0): output (dx, dy) averages bytes 1, 2 of the aligned word
+// 4dx.. in rows 4dy+1 and 4dy+2; a thread makes 4 outputs from two 128-bit loads. Half of the frame's
+// rows are never touched.
+__global__ void __launch_bounds__(256)
+pyramid_l2_kernel(FrameSet src, uint8_t* __restrict__ dst, int dst_pitch, size_t dst_frame_stride, int ow, int oh)
+{
+    const int f = blockIdx.z, dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int g = blockIdx.x * 32 + (threadIdx.x & 31);          // group of 4 output pixels
+    if (dy >= oh || g * 4 >= ow) return;
+    const uint8_t* r0 = src.base + (size_t)f * src.frame_stride + (size_t)(4 * dy + 1) * src.pitch + g * 16;
+    const uint4 a = *reinterpret_cast<const uint4*>(r0), b = *reinterpret_cast<const uint4*>(r0 + src.pitch);
+    const uint32_t wa[4] = { a.x, a.y, a.z, a.w }, wb[4] = { b.x, b.y, b.z, b.w };
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        o |= ((uint32_t)__dp4a(wa[k], 0x00010100u, __dp4a(wb[k], 0x00010100u, 2u)) >> 2) << (8 * k);
+    *reinterpret_cast<uint32_t*>(dst + (size_t)f * dst_frame_stride + (size_t)dy * dst_pitch + g * 4) = o;
+}
+
 cudaError_t launch_pyramid(const FrameSet& src, int level, uint8_t* dst, int dst_pitch,
                            size_t dst_frame_stride, int ow, int oh, cudaStream_t stream)
 {
     if (ow <= 0 || oh <= 0 || src.nframes <= 0) return cudaSuccess;
+    if (level == 2 && !(src.w & 63) && !(src.h & 3) && !((uintptr_t)src.base & 15) && !(src.pitch & 15) && !(src.frame_stride & 15) &&
+        !((uintptr_t)dst & 3) && !(dst_pitch & 3) && !(dst_frame_stride & 3) && src.nframes <= 65535)
+    {
+        dim3 grid((ow / 4 + 31) / 32, (oh + 7) / 8, src.nframes);
+        pyramid_l2_kernel<<<grid, 256, 0, stream>>>(src, dst, dst_pitch, dst_frame_stride, ow, oh);
+        return cudaGetLastError();
+    }
+    if (level == 1 && !(src.w & 31) && !(src.h & 1) && !((uintptr_t)src.base & 15) && !(src.pitch & 15) && !(src.frame_stride & 15) &&
+        !((uintptr_t)dst & 7) && !(dst_pitch & 7) && !(dst_frame_stride & 7) && src.nframes <= 65535)
+    {
+        dim3 grid((ow / 8 + 31) / 32, (oh + 7) / 8, src.nframes);
+        pyramid_l1_kernel<<<grid, 256, 0, stream>>>(src, dst, dst_pitch, dst_frame_stride, ow, oh);
+        return cudaGetLastError();
+    }
     dim3 grid((ow + 31) / 32, (oh + 7) / 8, src.nframes);
     pyramid_kernel<<<grid, 256, 0, stream>>>(src, level, dst, dst_pitch, dst_frame_stride, ow, oh);
     return cudaGetLastError();
