@@ -25,5 +25,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${
     python tools/bench_blobs.py --frames 64 --chunk 64 --steps 1 --warmup 1 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cluster_find -s 2 -c 1 -f -o $O/${R}_k2 \
     python bench.py --frames 512 --chunk 256 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/${R}_k2_ncu.log 2>&1
+python tools/bench_levels.py > $O/${R}_levels_4k_n14.jsonl 2>> $O/${R}_bench_n1.err
+python tools/sweep_resolutions.py > $O/${R}_cfg5_sweep.jsonl 2>> $O/${R}_bench_n1.err
+python tools/bench_dense.py > $O/${R}_dense_4k.txt 2>> $O/${R}_bench_n1.err
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $O/${R}_gpu.txt
 ls -la $O | tail -20
