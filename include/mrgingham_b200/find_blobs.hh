@@ -4,18 +4,11 @@
 // float32 keypoint coordinates are printed instead ("%f %f\n", find_blobs.cc:34-36; the values
 // printed here are the scaled integers divided by 1000, i.e. rounded to 1e-3 px); returns true.
 // The cv::Mat overload is compiled where OpenCV's C++ headers exist; mrgingham::ImageView works
-// everywhere (see find_chessboard_corners.hh). The file variant (find_blobs.cc:48-64) needs
-// cv::imread and is therefore only provided where OpenCV's highgui/imgcodecs headers exist.
+// everywhere (see find_chessboard_corners.hh). The file variant (find_blobs.cc:48-64) uses cv::imread
+// where OpenCV's highgui/imgcodecs headers exist and reads binary 8-bit PGM otherwise.
 #pragma once
 
 #include "find_chessboard_corners.hh"
-
-#if defined(MRGINGHAM_B200_HAVE_OPENCV) && defined(__has_include)
-#  if __has_include(<opencv2/highgui/highgui.hpp>)
-#    include <opencv2/highgui/highgui.hpp>
-#    define MRGINGHAM_B200_HAVE_OPENCV_IMREAD 1
-#  endif
-#endif
 
 namespace mrgingham
 {
@@ -42,6 +35,20 @@ namespace mrgingham
     {
         ImageView v;
         if (!mat_to_view(&v, image, __func__)) return true;
+        return find_blobs_from_image_array(points, v, dodump);
+    }
+#endif
+#ifndef MRGINGHAM_B200_HAVE_OPENCV_IMREAD
+    // without cv::imread: binary 8-bit PGM only (see read_pgm_p5 in find_chessboard_corners.hh)
+    inline bool find_blobs_from_image_file(std::vector<PointInt>* points, const char* filename, bool dodump = false)
+    {
+        std::vector<unsigned char> px; int rows, cols;
+        if (!read_pgm_p5(filename, &px, &rows, &cols))
+        {
+            fprintf(stderr, "%s:%d in %s(): Couldn't open image '%s'. Sorry.\n", __FILE__, __LINE__, __func__, filename);
+            return false;
+        }
+        const ImageView v = { rows, cols, (size_t)cols, px.data() };
         return find_blobs_from_image_array(points, v, dodump);
     }
 #endif

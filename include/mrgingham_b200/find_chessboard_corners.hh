@@ -17,6 +17,10 @@
 #  if __has_include(<opencv2/core/core.hpp>)
 #    include <opencv2/core/core.hpp>
 #    define MRGINGHAM_B200_HAVE_OPENCV 1
+#    if __has_include(<opencv2/highgui/highgui.hpp>)
+#      include <opencv2/highgui/highgui.hpp>
+#      define MRGINGHAM_B200_HAVE_OPENCV_IMREAD 1
+#    endif
 #  endif
 #endif
 
@@ -75,6 +79,57 @@ namespace mrgingham
                                                   image_pyramid_level, &(*points)[0].x, level, (int)points->size());
     }
 
+    // Image files (find_chessboard_corners.cc:622-648, find_blobs.cc:48-64 go through cv::imread with
+    // IMREAD_IGNORE_ORIENTATION | IMREAD_GRAYSCALE). Where OpenCV's imread is not available the file
+    // variants below read binary 8-bit PGM ("P5") only; anything else fails like an unreadable file does
+    // in the reference: the diagnostic "Couldn't open image" and false.
+    inline bool read_pgm_p5(const char* filename, std::vector<unsigned char>* pixels, int* rows, int* cols)
+    {
+        FILE* fp = fopen(filename, "rb");
+        if (!fp) return false;
+        auto token = [&](int* v) -> bool
+        {
+            int c = fgetc(fp);
+            for (;;)
+            {
+                while (c == ' ' || c == '\t' || c == '\n' || c == '\r') c = fgetc(fp);
+                if (c != '#') break;
+                while (c != '\n' && c != EOF) c = fgetc(fp);
+            }
+            if (c < '0' || c > '9') return false;
+            long n = 0;
+            while (c >= '0' && c <= '9') { n = n * 10 + (c - '0'); if (n > 100000) return false; c = fgetc(fp); }
+            *v = (int)n;           // the single whitespace after the last header token has just been consumed
+            return true;
+        };
+        int w = 0, h = 0, maxval = 0;
+        bool ok = fgetc(fp) == 'P' && fgetc(fp) == '5' && token(&w) && token(&h) && token(&maxval) &&
+                  w > 0 && h > 0 && maxval > 0 && maxval <= 255;
+        if (ok)
+        {
+            pixels->resize((size_t)w * h);
+            ok = fread(pixels->data(), 1, pixels->size(), fp) == pixels->size();
+        }
+        fclose(fp);
+        *rows = h; *cols = w;
+        return ok;
+    }
+
+#ifndef MRGINGHAM_B200_HAVE_OPENCV_IMREAD
+    inline bool find_chessboard_corners_from_image_file(std::vector<PointInt>* points, const char* filename,
+                                                        int image_pyramid_level, bool debug = false)
+    {
+        std::vector<unsigned char> px; int rows, cols;
+        if (!read_pgm_p5(filename, &px, &rows, &cols))
+        {
+            fprintf(stderr, "%s:%d in %s(): Couldn't open image '%s'. Sorry.\n", __FILE__, __LINE__, __func__, filename);
+            return false;
+        }
+        const ImageView v = { rows, cols, (size_t)cols, px.data() };
+        return find_chessboard_corners_from_image_array(points, v, image_pyramid_level, debug, filename);
+    }
+#endif
+
 #ifdef MRGINGHAM_B200_HAVE_OPENCV
     inline bool mat_to_view(ImageView* v, const cv::Mat& m, const char* who)
     {
@@ -95,6 +150,19 @@ namespace mrgingham
         if (!mat_to_view(&v, image_input, __func__)) return points_scaled_out->size() > 0;
         return find_chessboard_corners_from_image_array(points_scaled_out, v, image_pyramid_level, debug, debug_image_filename);
     }
+#ifdef MRGINGHAM_B200_HAVE_OPENCV_IMREAD
+    inline bool find_chessboard_corners_from_image_file(std::vector<PointInt>* points, const char* filename,
+                                                        int image_pyramid_level, bool debug = false)
+    {
+        cv::Mat image = cv::imread(filename, cv::IMREAD_IGNORE_ORIENTATION | cv::IMREAD_GRAYSCALE);
+        if (image.data == NULL)
+        {
+            fprintf(stderr, "%s:%d in %s(): Couldn't open image '%s'. Sorry.\n", __FILE__, __LINE__, __func__, filename);
+            return false;
+        }
+        return find_chessboard_corners_from_image_array(points, image, image_pyramid_level, debug, filename);
+    }
+#endif
     inline int refine_chessboard_corners_from_image_array(std::vector<PointDouble>* points, signed char* level,
                                                           const cv::Mat& image_input, int image_pyramid_level,
                                                           bool debug = false, const char* debug_image_filename = NULL)

@@ -77,3 +77,35 @@ def test_cxx_adapter_headers_compile(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "t"),
                     "-L" + lib, "-lmrgingham_b200", "-Wl,-rpath," + lib], check=True)
     subprocess.run([str(tmp_path / "t")], check=True)
+
+
+@pytest.mark.gpu
+def test_cxx_file_entry_points(tmp_path):
+    # find_chessboard_corners_from_image_file / find_blobs_from_image_file (find_chessboard_corners.cc:622-648,
+    # find_blobs.cc:48-64) through the C++ adapters, on PGM files, against the Python surface
+    import subprocess
+    from mrgingham_b200 import api, synth
+    board = synth.board_frame(640, 480, 10, seed=0)
+    dots = synth.circle_grid_frame(640, 480, 10, seed=1)
+    for name, img in (("board", board), ("dots", dots)):
+        with open(tmp_path / (name + ".pgm"), "wb") as f:
+            f.write(b"P5\n# test image\n%d %d\n255\n" % (img.shape[1], img.shape[0]) + img.tobytes())
+    src = tmp_path / "t.cc"
+    src.write_text('#include <mrgingham_b200/find_chessboard_corners.hh>\n#include <mrgingham_b200/find_blobs.hh>\n'
+                   'int main(int argc, char** argv) {\n'
+                   '  std::vector<mrgingham::PointInt> p, b;\n'
+                   '  if (!mrgingham::find_chessboard_corners_from_image_file(&p, argv[1], 1)) return 1;\n'
+                   '  if (!mrgingham::find_blobs_from_image_file(&b, argv[2])) return 2;\n'
+                   '  if (mrgingham::find_blobs_from_image_file(&b, "/nonexistent.pgm")) return 3;\n'
+                   '  for (auto& q : p) printf("c %d %d\\n", q.x, q.y);\n'
+                   '  for (auto& q : b) printf("b %d %d\\n", q.x, q.y);\n'
+                   '  return 0; }\n')
+    lib = os.path.join(ROOT, "mrgingham_b200")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "t"),
+                    "-L" + lib, "-lmrgingham_b200", "-Wl,-rpath," + lib], check=True)
+    out = subprocess.run([str(tmp_path / "t"), str(tmp_path / "board.pgm"), str(tmp_path / "dots.pgm")],
+                         check=True, capture_output=True, text=True).stdout.split("\n")
+    c = np.array([[int(v) for v in ln.split()[1:]] for ln in out if ln.startswith("c ")], dtype=np.int32).reshape(-1, 2)
+    b = np.array([[int(v) for v in ln.split()[1:]] for ln in out if ln.startswith("b ")], dtype=np.int32).reshape(-1, 2)
+    assert np.array_equal(c, api.find_chessboard_corners_int(board, 1))
+    assert np.array_equal(b, api.find_blobs_int(dots))
