@@ -186,7 +186,10 @@ int stage_frames(mrg_b200_detector* det, mrg_b200_detector::Slot& S, const uint8
         const int spitch = round_up(cols, 16);
         const size_t sframe = (size_t)spitch * rows;
         if (S.stage.ensure(sframe * n)) return -1;
-        if (fstride == pitch * (size_t)rows)
+        if (fstride == pitch * (size_t)rows && pitch == (size_t)spitch)
+            // dense rows on both sides: one linear copy
+            CUDA_TRY(cudaMemcpyAsync(S.stage.p, images, sframe * n, cudaMemcpyHostToDevice, cstream));
+        else if (fstride == pitch * (size_t)rows)
             CUDA_TRY(cudaMemcpy2DAsync(S.stage.p, spitch, images, pitch, cols, (size_t)rows * n, cudaMemcpyHostToDevice, cstream));
         else
             for (int i = 0; i < n; i++)
