@@ -14,4 +14,19 @@ bx, bc = det.find_blobs(small)
 for i in range(2):
     w = po.find_blobs(small[i]); assert bc[i] == len(w) and np.array_equal(bx[i,:bc[i]], w)
 b = det.box_blur(small, 1); assert np.array_equal(b[0], po.box_blur(small[0], 1))
-print("sanitizer workload ok", c, bc)
+# pyramid fast paths (levels 1, 2 on 16-byte aligned 1280-wide frames), the generic level kernel, the dense
+# response through the tiled kernel, the aligned 3x3 blur and the detector with on-device blur
+for level in (1, 2, 3):
+    xy, c2 = det.find_corners(frames, level)
+    for i in range(2):
+        w = po.find_corners(frames[i], level)
+        assert c2[i] == len(w) and np.array_equal(xy[i, :c2[i]], w)
+resp = det.chess_response(frames[:1])
+assert np.array_equal(resp[0], po.chess_response_5(frames[0], fill=0))
+assert np.array_equal(det.box_blur(frames[:1], 1)[0], po.box_blur(frames[0], 1))
+det2 = api.Detector(max_frames=2, max_points=1 << 14, candidate_capacity=1 << 18, blur_radius=1)
+xy, c3 = det2.find_corners(frames, 0)
+for i in range(2):
+    w = po.find_corners(po.box_blur(frames[i], 1), 0)
+    assert c3[i] == len(w) and np.array_equal(xy[i, :c3[i]], w)
+print("sanitizer workload ok", c, bc, c3)
