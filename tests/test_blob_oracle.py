@@ -40,3 +40,34 @@ def test_oracle_blobs_on_strided_view():
     big = np.zeros((img.shape[0], img.shape[1] + 13), np.uint8)
     big[:, :img.shape[1]] = img
     assert np.array_equal(po.find_blobs(big[:, :img.shape[1]]), GOLD["pts/circles_small_n7"])
+
+
+def test_oracle_blobs_match_cv2_on_random_frames():
+    # broader pinning than the 13 committed goldens, where cv2 is importable: the oracle against
+    # cv2.SimpleBlobDetector (the reference's parameters) on seeded random frames of several kinds
+    cv2 = pytest.importorskip("cv2")
+    from mrgingham_b200 import synth
+    p = cv2.SimpleBlobDetector_Params()
+    p.minArea = 20; p.maxArea = 80000; p.minDistBetweenBlobs = 5; p.blobColor = 0
+    det = cv2.SimpleBlobDetector_create(p)
+    rng = np.random.default_rng(77)
+    nonempty = 0
+    for t in range(36):
+        w, h = int(rng.integers(40, 420)), int(rng.integers(40, 320))
+        kind = t % 4
+        if kind == 0:
+            img = synth.blob_frame(w, h, seed=1000 + t, nblobs=int(rng.integers(3, 60)))
+        elif kind == 1:
+            img = synth.circle_grid_frame(max(w, 160), max(h, 160), int(rng.integers(3, 9)), seed=1000 + t,
+                                          noise_sigma=float(rng.uniform(0, 6)), blur=bool(t & 4))
+        elif kind == 2:
+            img = synth.blurred_noise_frame(w, h, seed=1000 + t, passes=int(rng.integers(1, 4)))
+        else:
+            img = synth.board_frame(max(w, 200), max(h, 160), int(rng.integers(4, 9)), seed=1000 + t)
+        kps = det.detect(img)
+        pts = np.array([kp.pt for kp in kps], dtype=np.float32).reshape(-1, 2)
+        want = np.trunc((pts * np.float32(1000)).astype(np.float64) + 0.5).astype(np.int32)
+        got = po.find_blobs(np.ascontiguousarray(img))
+        assert got.shape == want.shape and np.array_equal(got, want), (t, kind, img.shape, len(got), len(want))
+        nonempty += len(want) > 0
+    assert nonempty >= 20

@@ -117,3 +117,22 @@ def test_blobs_tiny_and_empty(api, oracle):
     xy, counts = det.find_blobs(np.zeros((0, 16, 16), np.uint8))
     assert len(counts) == 0
     det.close()
+
+
+def test_blobs_random_frames_match_oracle(api, oracle):
+    # the same kinds of seeded random frames the oracle is pinned on against cv2 (tests/test_blob_oracle.py)
+    rng = np.random.default_rng(78)
+    for t in range(24):
+        w, h = int(rng.integers(40, 700)), int(rng.integers(40, 500))
+        kind = t % 4
+        if kind == 0:
+            img = synth.blob_frame(w, h, seed=2000 + t, nblobs=int(rng.integers(3, 80)))
+        elif kind == 1:
+            img = synth.circle_grid_frame(max(w, 160), max(h, 160), int(rng.integers(3, 10)), seed=2000 + t,
+                                          noise_sigma=float(rng.uniform(0, 6)), blur=bool(t & 4))
+        elif kind == 2:
+            img = synth.blurred_noise_frame(w, h, seed=2000 + t, passes=int(rng.integers(1, 4)))
+        else:
+            img = synth.board_frame(max(w, 200), max(h, 160), int(rng.integers(4, 9)), seed=2000 + t)
+        img = np.ascontiguousarray(img)
+        assert np.array_equal(api.find_blobs_int(img), oracle.find_blobs(img)), (t, kind, img.shape)
