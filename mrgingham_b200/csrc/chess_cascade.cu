@@ -37,6 +37,7 @@
 // L2 reads its cells from the two staged blocks still resident in shared memory (a stage is handed
 // back two blocks late for that); L3 re-reads its few pixels from global memory.
 #include <cuda.h>
+#include <algorithm>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -532,10 +533,15 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     const int sw = kWarpPx * nw;
     tp.nstrips = (fs.w - kMargin + sw - 1) / sw;
     const int out_rows = fs.h - 2*kMargin;
-    // enough work items to fill the chip a few times over, but segments no shorter than 44 rows
-    const long long want_items = 148LL * 4 * 4;
+    // Work items = (frame, strip, row segment). Many short segments balance better (a CTA's time depends on
+    // how many edges cross its segment, and the last wave of CTAs is shorter) but each segment re-reads 10
+    // rows to prime its register window: ~275-row segments measured best on 4K batches (0.31 -> 0.35 of HBM
+    // peak against one segment per strip). Small batches get more, shorter segments to fill the chip
+    // (>= 2368 items), never shorter than 44 rows.
+    const int target_rows = env_int("MRG_B200_K1_SEGROWS", 275, 44, 1 << 20);
+    const long long want_items = env_int("MRG_B200_K1_ITEMS", 148 * 4 * 4, 1, 1 << 24);
     const long long per_seg = (long long)fs.nframes * tp.nstrips;
-    long long nsegs = (want_items + per_seg - 1) / per_seg;
+    long long nsegs = std::max((want_items + per_seg - 1) / per_seg, (long long)((out_rows + target_rows - 1) / target_rows));
     int seg_rows = (int)((out_rows + nsegs - 1) / nsegs);
     seg_rows = ((seg_rows + kBlkRows - 1) / kBlkRows) * kBlkRows;
     if (seg_rows < 44) seg_rows = 44;
