@@ -30,6 +30,7 @@
 //     are recomputed exactly from the staged bytes by an out-of-line scalar routine that appends
 //     the candidates. Whenever a response can exceed 15 it is computed exactly.
 #include <cuda.h>
+#include <algorithm>
 #include <cuda_fp16.h>
 #include <mutex>
 #include <stdio.h>
@@ -424,6 +425,8 @@ static cudaError_t launch_tiled(const FrameSet& fs, cand_t* cand, uint32_t* coun
     // enough work items to fill the chip a few times over, but segments no shorter than 40 rows
     const long long want_items = 148LL * 5 * 4;
     long long nsegs = (want_items + (long long)fs.nframes * tp.nstrips - 1) / ((long long)fs.nframes * tp.nstrips);
+    // ~275-row segments balance better than one segment per strip (measured on the cascade kernel)
+    nsegs = std::max(nsegs, (long long)((out_rows + 274) / 275));
     int seg_rows = (int)((out_rows + nsegs - 1) / nsegs);
     seg_rows = ((seg_rows + kStageRows - 1) / kStageRows) * kStageRows;
     if (seg_rows < 40) seg_rows = 40;
