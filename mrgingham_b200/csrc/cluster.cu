@@ -121,16 +121,22 @@ constexpr int kRegionMax = 48;
 struct LocalRegion
 {
     uint32_t lkey[kRegionMax];
+    int8_t   nb[kRegionMax][4];       // read as one 32-bit word per node: keep 4-byte aligned (right after lkey)
     uint16_t lr[kRegionMax];
-    int8_t   nb[kRegionMax][4];
     int8_t   dfs_parent[kRegionMax];
     uint8_t  dfs_dir[kRegionMax];
 };
 
 __device__ void grow_component_local(Component& c, LocalRegion& g, int seed, int w, int h)
 {
+    // Stackless depth-first replay of follow_connected_component() (find_chessboard_corners.cc:228-267) on
+    // the region's local graph. The node being expanded keeps its four neighbour indices (one 32-bit load)
+    // and its next direction in registers; per-node state goes to the local arrays only when the walk
+    // descends to a child, so a neighbour test costs one dependent load (lr[q]) instead of three.
     c.swx = c.swy = c.sw = 0; c.n = 0; c.peak = 0; c.peak_x = c.peak_y = 0; c.poisoned = false;
-    int cur = seed, parent = -1;
+    const uint32_t* nbw_of = reinterpret_cast<const uint32_t*>(&g.nb[0][0]);
+    int cur = seed, parent = -1, d = 0;
+    uint32_t nbw = 0;
     for (;;)
     {
         const int r = g.lr[cur];
@@ -146,18 +152,29 @@ __device__ void grow_component_local(Component& c, LocalRegion& g, int seed, int
             c.n++;
             if (x + 1 >= w - kMargin || x - 1 < kMargin || y + 1 >= h - kMargin || y - 1 < kMargin)
                 c.poisoned = true;
-            g.dfs_parent[cur] = (int8_t)parent; g.dfs_dir[cur] = 0;
+            g.dfs_parent[cur] = (int8_t)parent;
+            d = 0; nbw = nbw_of[cur];
         }
         else
-            cur = parent;
-        bool found = false;
-        while (cur >= 0)
         {
-            const int d = g.dfs_dir[cur];
-            if (d == 4) { cur = g.dfs_parent[cur]; continue; }
-            g.dfs_dir[cur] = (uint8_t)(d + 1);
-            const int q = g.nb[cur][d];
+            cur = parent;
+            if (cur < 0) break;
+            d = g.dfs_dir[cur]; nbw = nbw_of[cur];
+        }
+        bool found = false;
+        for (;;)
+        {
+            if (d == 4)
+            {
+                cur = g.dfs_parent[cur];
+                if (cur < 0) break;
+                d = g.dfs_dir[cur]; nbw = nbw_of[cur];
+                continue;
+            }
+            const int q = (int)(int8_t)(nbw >> (8 * d));
+            d++;
             if (q < 0 || g.lr[q] == 0) continue;
+            g.dfs_dir[cur] = (uint8_t)d;          // where to resume when the walk comes back to this node
             parent = cur; cur = q; found = true;
             break;
         }
