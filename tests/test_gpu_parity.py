@@ -380,3 +380,34 @@ def test_dense_response_kernels_agree(api, oracle):
             for i in range(2):
                 assert np.array_equal(got[i], oracle.chess_response_5(imgs[i], fill=0)), (w, h, variant, i)
             det.close()
+
+
+def test_full_size_symmetry_properties(api):
+    # Size-independent properties at BASELINE's full frame size, no oracle involved. The ChESS ring is
+    # symmetric under a horizontal mirror and a 180-degree turn, and adding a constant to every pixel
+    # changes neither sum, diff nor |mean - local_mean| (16*(s+3c)/3 truncates like 16*s/3 + 16c):
+    #   dense response of the transformed frame == transformed dense response,
+    #   number of pixels with response > 15 (the candidate list K1 emits) is unchanged.
+    frame = synth.board_frame(3840, 2160, 10, seed=321)
+    frame = np.minimum(frame, 235).astype(np.uint8)              # head-room for the +20 offset
+    variants = {"mirror": np.ascontiguousarray(frame[:, ::-1]), "rot180": np.ascontiguousarray(frame[::-1, ::-1]),
+                "offset": (frame + 20).astype(np.uint8)}
+    det = api.Detector(max_frames=4, max_points=1024)
+    base = det.chess_response(frame[None])[0]
+    assert (base > 15).sum() > 500
+    for name, img in variants.items():
+        r = det.chess_response(img[None])[0]
+        want = {"mirror": base[:, ::-1], "rot180": base[::-1, ::-1], "offset": base}[name]
+        assert np.array_equal(r, want), name
+    batch = np.stack([frame] + list(variants.values()))
+    xy, counts = det.find_corners(batch, 0)
+    cand = det.last_candidate_counts(4)
+    assert cand[0] == (base > 15).sum() and (cand == cand[0]).all(), cand
+    assert (counts == 100).all()
+    # the offset frame has the same corners to the last digit; the mirrored frame has the mirrored corners, up
+    # to the traversal-order dependence of the reference's clustering (membership is tested against the
+    # running peak), a few hundredths of a pixel
+    assert np.array_equal(xy[3, :100], xy[0, :100])
+    a = np.sort(xy[0, :100, 0]); b = np.sort((3839 * 1000) - xy[1, :100, 0])
+    assert np.abs(a - b).max() <= 100
+    det.close()
