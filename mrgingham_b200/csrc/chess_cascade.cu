@@ -512,17 +512,14 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     if (fs.w <= 2*kMargin || fs.h <= 2*kMargin || fs.nframes <= 0) return cudaSuccess;
     if (fs.h > 32767 || fs.w > 32767) { *launched = false; return cudaSuccess; }
 
-    // strip width: the one that stages the fewest bytes (ties -> wider)
+    // strip width: three warps per CTA (768-pixel strips, 4 % halo) unless that stages over 30 % more bytes
+    // than one-warp strips would (narrow frames). Two-warp strips measured slower than either at every
+    // size tried (fewer warps per SM for the shared memory they hold); MRG_B200_K1_NW forces a width.
     int nw = env_int("MRG_B200_K1_NW", 0, 1, 3);
     if (nw == 0)
     {
-        long long best = -1;
-        for (int k = 3; k >= 1; k--)
-        {
-            const int sw = kWarpPx * k;
-            const long long cost = (long long)((fs.w - kMargin + sw - 1) / sw) * (sw + 2 * kCHalo);
-            if (best < 0 || cost < best) { best = cost; nw = k; }
-        }
+        auto staged = [&](int k) { const int sw = kWarpPx * k; return (long long)((fs.w - kMargin + sw - 1) / sw) * (sw + 2 * kCHalo); };
+        nw = staged(3) * 10 <= staged(1) * 13 ? 3 : 1;
     }
     CascadeParams tp;
     tp.cap = cand_capacity;
