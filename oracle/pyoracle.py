@@ -174,6 +174,33 @@ def box_blur(image, radius=1):
     return out
 
 
+def normalize_minmax(image):
+    """cv::normalize(image, image, 0, 255, NORM_MINMAX) for 8-bit images (mrgingham-from-image.cc:77)"""
+    image = _check_image(image)
+    h, w = image.shape
+    lut = np.empty(256, dtype=np.uint8)
+    oracle_lib().preproc_oracle_normalize_lut(_ptr(image, _u8p), w, h, image.strides[0], _ptr(lut, _u8p))
+    return lut[image]
+
+
+def clahe(image, clip_limit=8.0):
+    """cv::createCLAHE(clip_limit).apply(image), 8x8 tiles (mrgingham-from-image.cc:43-44, :78)"""
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.empty((h, w), dtype=np.uint8)
+    oracle_lib().preproc_oracle_clahe(_ptr(image, _u8p), w, h, image.strides[0], ctypes.c_double(clip_limit), _ptr(out, _u8p))
+    return out
+
+
+def normalize_clahe(image):
+    """the CLI's --clahe chain: normalize, then CLAHE with clip limit 8"""
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.empty((h, w), dtype=np.uint8)
+    oracle_lib().preproc_oracle_normalize_clahe(_ptr(image, _u8p), w, h, image.strides[0], _ptr(out, _u8p))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference itself (oracle/_ref)
 # ---------------------------------------------------------------------------------------------
