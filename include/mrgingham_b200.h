@@ -104,6 +104,9 @@ typedef struct
                                  detector and the refinement, as the reference CLI does by default with
                                  R = 1 (mrgingham-from-image.cc:106-111); 0 = frames are used as given.
                                  Does not apply to the blob detector or the dense response.           */
+    int clahe;                /* nonzero: cv::normalize(0,255,NORM_MINMAX) then cv::CLAHE(clipLimit 8, 8x8 tiles)
+                                 on the GPU before the blur, the reference CLI's --clahe
+                                 (mrgingham-from-image.cc:43-44, 71-80). Same scope as blur_radius.    */
 } mrg_b200_detector_config;
 
 /* returns 0 and a detector, or <0 */
@@ -179,6 +182,18 @@ int mrg_b200_box_blur_batch(mrg_b200_detector* det,
                             int blur_radius,
                             uint8_t* out, int out_on_device,
                             void* stream);
+
+/* The whole preprocessing chain of the reference CLI (mrgingham-from-image.cc:71-111) as a stand-alone call:
+   if clahe: cv::normalize(image, 0, 255, NORM_MINMAX) and cv::createCLAHE(8)->apply(); then, if
+   blur_radius > 0, the blur above. Results are those of OpenCV 4.13.0. Arguments as for
+   mrg_b200_box_blur_batch(); at least one of the two steps must be asked for. */
+int mrg_b200_preprocess_batch(mrg_b200_detector* det,
+                              const uint8_t* images, int images_on_device,
+                              int nframes, int rows, int cols,
+                              size_t row_pitch, size_t frame_stride,
+                              int clahe, int blur_radius,
+                              uint8_t* out, int out_on_device,
+                              void* stream);
 
 /* Pyramid level image (what the reference gets from cv::resize, find_chessboard_corners.cc:449-450).
    out: HOST uint8 [orows][ocols] dense; returns 0 and the size, or <0. */

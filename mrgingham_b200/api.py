@@ -21,6 +21,7 @@ EXPORTS = (
     "mrg_b200_detector_create", "mrg_b200_detector_destroy",
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
     "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch", "mrg_b200_box_blur_batch",
+    "mrg_b200_preprocess_batch",
     "mrg_b200_chess_response_batch", "mrg_b200_pyramid_level",
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
     "mrg_b200_device_count",
@@ -31,7 +32,7 @@ class DetectorConfig(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("max_frames", ctypes.c_int),
                 ("max_rows", ctypes.c_int), ("max_cols", ctypes.c_int),
                 ("candidate_capacity", ctypes.c_int), ("max_points", ctypes.c_int),
-                ("kernel_variant", ctypes.c_int), ("blur_radius", ctypes.c_int)]
+                ("kernel_variant", ctypes.c_int), ("blur_radius", ctypes.c_int), ("clahe", ctypes.c_int)]
 
 
 def library_path():
@@ -79,6 +80,10 @@ def lib():
     L.mrg_b200_box_blur_batch.restype = ctypes.c_int
     L.mrg_b200_box_blur_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.mrg_b200_preprocess_batch.restype = ctypes.c_int
+    L.mrg_b200_preprocess_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_void_p]
     L.mrg_b200_chess_response_batch.restype = ctypes.c_int
     L.mrg_b200_chess_response_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
@@ -224,9 +229,10 @@ class Detector:
     """Batched detector over equally-sized frames (include/mrgingham_b200.h section C)."""
 
     def __init__(self, max_frames=64, max_rows=0, max_cols=0, candidate_capacity=0, max_points=0, device=-1,
-                 kernel_variant=0, blur_radius=0):
+                 kernel_variant=0, blur_radius=0, clahe=False):
         self._h = ctypes.c_void_p()
-        cfg = DetectorConfig(device, max_frames, max_rows, max_cols, candidate_capacity, max_points, kernel_variant, blur_radius)
+        cfg = DetectorConfig(device, max_frames, max_rows, max_cols, candidate_capacity, max_points, kernel_variant, blur_radius,
+                             int(bool(clahe)))
         if lib().mrg_b200_detector_create(ctypes.byref(self._h), ctypes.byref(cfg)) != 0:
             raise RuntimeError("mrg_b200_detector_create() failed (no CUDA device?)")
         self.max_points = max_points if max_points > 0 else 1024
@@ -295,6 +301,14 @@ class Detector:
     def box_blur(self, images, radius=1, out=None, stream=None):
         """cv::blur(Size(1+2R,1+2R)) as the reference CLI applies it by default (mrgingham-from-image.cc:106-111).
         Host images -> numpy result; a CUDA torch tensor -> a new CUDA tensor (or `out`), no host round trip."""
+        if not 1 <= int(radius) <= 4:
+            raise ValueError("radius must be in [1,4]")
+        return self.preprocess(images, clahe=False, blur_radius=radius, out=out, stream=stream)
+
+    def preprocess(self, images, clahe=False, blur_radius=1, out=None, stream=None):
+        """The reference CLI's preprocessing chain (mrgingham-from-image.cc:71-111): with clahe,
+        cv::normalize(0,255,NORM_MINMAX) + CLAHE(clipLimit 8); then cv::blur of the given radius (0 = none).
+        Host images -> numpy result; a CUDA torch tensor -> a new CUDA tensor (or `out`), no host round trip."""
         ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
         if on_dev:
             import torch
@@ -305,10 +319,10 @@ class Detector:
         else:
             out = np.empty((n, rows, cols), dtype=np.uint8)
             optr = out.ctypes.data
-        rc = lib().mrg_b200_box_blur_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(radius), optr, on_dev,
-                                           ctypes.c_void_p(stream) if stream else None)
+        rc = lib().mrg_b200_preprocess_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(bool(clahe)), int(blur_radius),
+                                             optr, on_dev, ctypes.c_void_p(stream) if stream else None)
         if rc != 0:
-            raise RuntimeError("mrg_b200_box_blur_batch() failed")
+            raise RuntimeError("mrg_b200_preprocess_batch() failed")
         return out
 
     def refine_corners(self, images, level, xy, levels, stream=None):

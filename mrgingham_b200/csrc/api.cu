@@ -100,7 +100,7 @@ struct mrg_b200_detector
     // of chunk c+1 (main stream).
     struct Slot
     {
-        DeviceBuffer stage, blurred, level_img, cand, counts, table, dfs, records, xy, outcounts;
+        DeviceBuffer stage, blurred, equalized, pre_scratch, level_img, cand, counts, table, dfs, records, xy, outcounts;
         cudaEvent_t staged = nullptr, k1done = nullptr, k2done = nullptr;
         bool used = false;
     } slot[2];
@@ -203,6 +203,15 @@ int stage_frames(mrg_b200_detector* det, mrg_b200_detector::Slot& S, const uint8
         src.base = (const uint8_t*)S.stage.p; src.frame_stride = sframe; src.pitch = spitch;
     }
     src.w = cols; src.h = rows; src.nframes = n;
+    if (preprocess && det->cfg.clahe)
+    {
+        // the reference CLI's --clahe: normalize to [0,255], then CLAHE(clipLimit 8) (mrgingham-from-image.cc:71-80)
+        const int epitch = round_up(cols, 16);
+        const size_t eframe = (size_t)epitch * rows;
+        if (S.equalized.ensure(eframe * n) || S.pre_scratch.ensure(clahe_scratch_bytes(n))) return -1;
+        CUDA_TRY(launch_normalize_clahe(src, true, 8.0, (uint8_t*)S.equalized.p, epitch, eframe, S.pre_scratch.p, stream));
+        src.base = (const uint8_t*)S.equalized.p; src.frame_stride = eframe; src.pitch = epitch;
+    }
     if (preprocess && det->cfg.blur_radius > 0)
     {
         // the reference CLI's default preprocessing, on the device: the detector reads the blurred copy
@@ -512,19 +521,21 @@ API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* ima
     return 0;
 }
 
-API int mrg_b200_box_blur_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
-                                int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
-                                int blur_radius, uint8_t* out, int out_on_device, void* stream_)
+// clahe (optional) then blur (optional) of a batch into a dense output; the order the reference CLI applies them in
+static int preprocess_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                            int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                            int clahe, int blur_radius, uint8_t* out, int out_on_device, void* stream_)
 {
     if (!det) return -1;
     std::lock_guard<std::mutex> g(det->mtx);
     if (nframes < 0 || rows <= 0 || cols <= 0 || row_pitch < (size_t)cols) { MSG("Bad batch geometry."); return -1; }
-    if (blur_radius < 1 || blur_radius > 4) { MSG("blur_radius must be in [1,4]; got %d.", blur_radius); return -1; }
+    if (blur_radius < 0 || blur_radius > 4) { MSG("blur_radius must be in [0,4]; got %d.", blur_radius); return -1; }
+    if (!clahe && blur_radius == 0) { MSG("Nothing to do: neither clahe nor a blur was asked for."); return -1; }
     if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
     CUDA_TRY(cudaSetDevice(det->device));
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
     const size_t fe = (size_t)rows * cols;
-    const int chunk = out_on_device && images_on_device ? std::max(nframes, 1) : std::max(1, det->cfg.max_frames);
+    const int chunk = std::min(out_on_device && images_on_device ? std::max(nframes, 1) : std::max(1, det->cfg.max_frames), 65535);
     for (int f0 = 0; f0 < nframes; f0 += chunk)
     {
         const int n = std::min(chunk, nframes - f0);
@@ -537,11 +548,39 @@ API int mrg_b200_box_blur_batch(mrg_b200_detector* det, const uint8_t* images, i
             if (S.level_img.ensure(fe * n)) return -1;
             d = (uint8_t*)S.level_img.p;
         }
-        CUDA_TRY(launch_box_blur(fs, blur_radius, d, cols, fe, stream));
+        if (clahe)
+        {
+            uint8_t* e = d; int epitch = cols; size_t eframe = fe;
+            if (blur_radius > 0)
+            {
+                epitch = round_up(cols, 16); eframe = (size_t)epitch * rows;
+                if (S.equalized.ensure(eframe * n)) return -1;
+                e = (uint8_t*)S.equalized.p;
+            }
+            if (S.pre_scratch.ensure(clahe_scratch_bytes(n))) return -1;
+            CUDA_TRY(launch_normalize_clahe(fs, true, 8.0, e, epitch, eframe, S.pre_scratch.p, stream));
+            fs.base = e; fs.pitch = epitch; fs.frame_stride = eframe;
+        }
+        if (blur_radius > 0) CUDA_TRY(launch_box_blur(fs, blur_radius, d, cols, fe, stream));
         if (!out_on_device) CUDA_TRY(cudaMemcpyAsync(out + (size_t)f0 * fe, d, fe * n, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
     }
     return 0;
+}
+
+API int mrg_b200_box_blur_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                int blur_radius, uint8_t* out, int out_on_device, void* stream_)
+{
+    if (blur_radius < 1 || blur_radius > 4) { MSG("blur_radius must be in [1,4]; got %d.", blur_radius); return -1; }
+    return preprocess_batch(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, 0, blur_radius, out, out_on_device, stream_);
+}
+
+API int mrg_b200_preprocess_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                  int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                  int clahe, int blur_radius, uint8_t* out, int out_on_device, void* stream_)
+{
+    return preprocess_batch(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, clahe != 0, blur_radius, out, out_on_device, stream_);
 }
 
 API int mrg_b200_pyramid_level(mrg_b200_detector* det, const uint8_t* image, int rows, int cols, size_t row_pitch,

@@ -60,6 +60,12 @@ cudaError_t launch_pyramid(const FrameSet& src, int level, uint8_t* dst, int dst
 cudaError_t launch_box_blur(const FrameSet& src, int radius, uint8_t* dst, int dst_pitch, size_t dst_frame_stride,
                             cudaStream_t stream);
 
+// Kpre2: cv::normalize(0,255,NORM_MINMAX) (if `normalize`) then cv::CLAHE(clip_limit, 8x8 tiles), the reference
+// CLI's --clahe (mrgingham-from-image.cc:43-44, 71-80). scratch: clahe_scratch_bytes(nframes) bytes.
+size_t clahe_scratch_bytes(int nframes);
+cudaError_t launch_normalize_clahe(const FrameSet& fs, bool normalize, double clip_limit, uint8_t* dst, int dst_pitch,
+                                   size_t dst_frame_stride, void* scratch, cudaStream_t stream);
+
 // K1 (simple variant): ChESS response, one thread per pixel, emits candidates
 cudaError_t launch_chess_sparse_simple(const FrameSet& fs, cand_t* cand, uint32_t* counts,
                                        int cand_capacity, cudaStream_t stream);

@@ -27,3 +27,44 @@ def test_oracle_preproc_matches_cv2():
         assert np.array_equal(po.normalize_minmax(img), n), img.shape
         assert np.array_equal(po.clahe(img), cl.apply(img)), img.shape
         assert np.array_equal(po.normalize_clahe(img), cl.apply(n)), img.shape
+
+
+@pytest.mark.gpu
+def test_gpu_preproc_matches_oracle():
+    import torch
+    from mrgingham_b200 import api
+    api._require_gpu()
+    det = api.Detector(max_frames=2)
+    for img in _images():
+        want = po.normalize_clahe(img)
+        got = det.preprocess(img[None], clahe=True, blur_radius=0)[0]
+        assert np.array_equal(got, want), img.shape
+        got = det.preprocess(img[None], clahe=True, blur_radius=1)[0]
+        assert np.array_equal(got, po.box_blur(want, 1)), img.shape
+    # a batch (more frames than one chunk), host and device-resident, aligned and odd-offset views
+    raw = np.stack([synth.board_frame(403, 351, 10, seed=s) // (1 + s % 3) + 7 * s for s in range(5)]).astype(np.uint8)
+    want = np.stack([po.normalize_clahe(f) for f in raw])
+    assert np.array_equal(det.preprocess(raw, clahe=True, blur_radius=0), want)
+    wide = np.zeros((5, 351, 448), np.uint8)
+    for off in (0, 4, 5):
+        wide[:, :, off:off + 403] = raw
+        t = torch.from_numpy(wide).cuda()[:, :, off:off + 403]
+        got = det.preprocess(t, clahe=True, blur_radius=0)
+        assert got.is_cuda and np.array_equal(got.cpu().numpy(), want), off
+    det.close()
+
+
+@pytest.mark.gpu
+def test_detector_with_clahe_chain():
+    # clahe + blur in the detector config = the reference CLI run with --clahe: raw frames in, corners of the
+    # equalised, blurred frames out
+    from mrgingham_b200 import api
+    api._require_gpu()
+    raw = np.stack([(synth.board_frame(800, 608, 10, seed=s, blur=False) // 3 + 50).astype(np.uint8) for s in (5, 6, 7)])
+    det = api.Detector(max_frames=2, max_points=2048, blur_radius=1, clahe=True)
+    for level in (0, 1):
+        xy, counts = det.find_corners(raw, level)
+        for i in range(len(raw)):
+            want = po.find_corners(po.box_blur(po.normalize_clahe(raw[i]), 1), level)
+            assert counts[i] == len(want) and len(want) > 0 and np.array_equal(xy[i, :counts[i]], want), (level, i)
+    det.close()
