@@ -56,6 +56,23 @@ bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols,
                                                 bool (*add_points)(int* xy, int N, double scale, void* cookie),
                                                 void* cookie);
 
+/* Replaces mrgingham_pywrap_cplusplus_bridge.cc:72-138 (declared in ...bridge.h:25-42): what the reference's
+   Python find_board() binds. Corners (or blobs) -> grid of gridn x gridn -> refinement; image_pyramid_level < 0
+   tries levels 3,2,1,0 and keeps the first that yields a grid. Returns false when no grid was found, on error,
+   or for doblobs with a level other than 0; otherwise calls add_points(xy, gridn*gridn, cookie) once and returns
+   its result. debug, debug_sequence_x/y only produce diagnostics in the reference and are ignored here. */
+bool find_chessboard_from_image_array_C(int Nrows, int Ncols,
+                                        int stride,
+                                        char* imagebuffer, /* const */
+                                        const int gridn,
+                                        int image_pyramid_level,
+                                        bool doblobs,
+                                        bool debug,
+                                        int debug_sequence_x,
+                                        int debug_sequence_y,
+                                        bool (*add_points)(double* xy, int N, void* cookie),
+                                        void* cookie);
+
 /* ===========================================================================================
    B. C mirror of the reference's C++ API for the path
    =========================================================================================== */
@@ -83,6 +100,32 @@ int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int Ncol
    (x,y) pairs scaled by 1000, in the reference's keypoint order. */
 int mrg_b200_find_blobs(const uint8_t* image, int Nrows, int Ncols, int stride,
                         int* xy_out, int cap);
+
+/* mrgingham::find_grid_from_points(), find_grid.cc:1216-1445 (host code; no GPU involved).
+   xy: npoints (x,y) pairs scaled by 1000; xy_out: gridn*gridn (x,y) doubles in pixels, row by row from the
+   board's top edge. Returns 1 if exactly one gridn x gridn grid was found, else 0 (xy_out untouched).
+   The reference's neighbour graph comes from Boost.Polygon's Voronoi diagram; this library builds the same
+   graph itself (exact Delaunay triangulation) - see DESIGN.md for what that does and does not pin. */
+int mrg_b200_find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out);
+
+/* The neighbour graph the grid finder walks (the content of the reference's --debug Voronoi dump,
+   find_grid.cc:391-430): ring[ring_off[i] .. ring_off[i+1]) = the points whose Voronoi cells share an edge with
+   point i's cell, counter-clockwise in (x,y) from the +x direction. ring_off has npoints+1 entries. Returns
+   the total ring length (only the first ring_cap entries are written) or <0. */
+int mrg_b200_voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* ring, int ring_cap);
+
+/* mrgingham::find_chessboard_from_image_array(), mrgingham.cc:36-140. image_pyramid_level < 0: levels 3,2,1,0
+   in turn until one yields a grid. refine != 0 (the reference: refinement_level != NULL): the grid's points
+   are then refined level by level down to 0 (mrgingham.cc:81-99); levels_out (may be NULL) receives the level
+   each point ended at. xy_out: gridn*gridn (x,y) doubles in full-resolution pixels.
+   Returns the level the grid was found at, or <0 (not found, or error). */
+int mrg_b200_find_chessboard_from_image_array(const uint8_t* image, int Nrows, int Ncols, int stride,
+                                              int gridn, int image_pyramid_level, int refine,
+                                              double* xy_out, signed char* levels_out);
+
+/* mrgingham::find_circle_grid_from_image_array(), mrgingham.cc:10-21: blobs -> grid. Returns 1 or 0. */
+int mrg_b200_find_circle_grid_from_image_array(const uint8_t* image, int Nrows, int Ncols, int stride,
+                                               int gridn, double* xy_out);
 
 /* ===========================================================================================
    C. Batched / device-resident entry points (additive)
@@ -161,6 +204,22 @@ int mrg_b200_find_blobs_batch(mrg_b200_detector* det,
                               size_t row_pitch, size_t frame_stride,
                               int32_t* xy_out, int32_t* counts_out,
                               void* stream);
+
+/* Whole boards over a batch of equally-sized frames: the batched form of
+   mrg_b200_find_chessboard_from_image_array() / mrg_b200_find_circle_grid_from_image_array(). Host frames are
+   copied to the device once per chunk and stay there for every level and refinement pass; the corner /
+   refinement kernels run over all frames that still need them, the grid finder on host threads.
+     xy_out           HOST double [nframes][gridn*gridn][2], valid where found_level_out[i] >= 0
+     levels_out       HOST int8 [nframes][gridn*gridn] or NULL (filled when refine != 0)
+     found_level_out  HOST int32 [nframes]: level the grid was found at, or -1
+   doblobs needs image_pyramid_level == 0 and ignores refine. Synchronous. Returns 0 or <0. */
+int mrg_b200_find_boards_batch(mrg_b200_detector* det,
+                               const uint8_t* images, int images_on_device,
+                               int nframes, int rows, int cols,
+                               size_t row_pitch, size_t frame_stride,
+                               int gridn, int image_pyramid_level, int doblobs, int refine,
+                               double* xy_out, signed char* levels_out, int32_t* found_level_out,
+                               void* stream);
 
 /* Dense ChESS response over a batch (the batched form of section A's function).
    response: int16 [nframes][rows][cols]; elements outside the 7-pixel interior are not written. */

@@ -13,6 +13,7 @@ _i16p = ctypes.POINTER(ctypes.c_int16)
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _f64p = ctypes.POINTER(ctypes.c_double)
 _i8p = ctypes.POINTER(ctypes.c_int8)
+_ADD_POINTS_D = ctypes.CFUNCTYPE(ctypes.c_bool, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_void_p)
 _ADD_POINTS = ctypes.CFUNCTYPE(ctypes.c_bool, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_double, ctypes.c_void_p)
 
 EXPORTS = (
@@ -22,6 +23,8 @@ EXPORTS = (
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
     "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch", "mrg_b200_box_blur_batch",
     "mrg_b200_preprocess_batch",
+    "find_chessboard_from_image_array_C", "mrg_b200_find_grid_from_points", "mrg_b200_voronoi_neighbours",
+    "mrg_b200_find_chessboard_from_image_array", "mrg_b200_find_circle_grid_from_image_array", "mrg_b200_find_boards_batch",
     "mrg_b200_chess_response_batch", "mrg_b200_pyramid_level",
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
     "mrg_b200_device_count",
@@ -54,6 +57,23 @@ def lib():
     L.find_chessboard_corners_from_image_array_C.argtypes = [
         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_bool, ctypes.c_bool,
         _ADD_POINTS, ctypes.c_void_p]
+    L.find_chessboard_from_image_array_C.restype = ctypes.c_bool
+    L.find_chessboard_from_image_array_C.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_bool, ctypes.c_bool,
+        ctypes.c_int, ctypes.c_int, _ADD_POINTS_D, ctypes.c_void_p]
+    L.mrg_b200_find_grid_from_points.restype = ctypes.c_int
+    L.mrg_b200_find_grid_from_points.argtypes = [_i32p, ctypes.c_int, ctypes.c_int, _f64p]
+    L.mrg_b200_voronoi_neighbours.restype = ctypes.c_int
+    L.mrg_b200_voronoi_neighbours.argtypes = [_i32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int]
+    L.mrg_b200_find_chessboard_from_image_array.restype = ctypes.c_int
+    L.mrg_b200_find_chessboard_from_image_array.argtypes = [_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                            ctypes.c_int, _f64p, _i8p]
+    L.mrg_b200_find_circle_grid_from_image_array.restype = ctypes.c_int
+    L.mrg_b200_find_circle_grid_from_image_array.argtypes = [_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p]
+    L.mrg_b200_find_boards_batch.restype = ctypes.c_int
+    L.mrg_b200_find_boards_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             _f64p, _i8p, _i32p, ctypes.c_void_p]
     L.mrg_b200_find_chessboard_corners.restype = ctypes.c_int
     L.mrg_b200_find_chessboard_corners.argtypes = [_u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, ctypes.c_int]
     L.mrg_b200_refine_chessboard_corners.restype = ctypes.c_int
@@ -173,11 +193,32 @@ def find_points(image, image_pyramid_level=0, blobs=False, debug=False):
 find_chessboard_corners = find_points
 
 
-def find_board(*args, **kwargs):
-    """mrgingham.find_board needs the grid finder (find_grid.cc), which is outside the hot path
-    this package replaces."""
-    raise NotImplementedError("find_board: the grid search is not part of mrgingham_b200; feed find_points() "
-                              "output to the reference's find_grid_from_points()")
+def find_board(image, image_pyramid_level=-1, gridn=10, blobs=False, debug=False, debug_sequence=None):
+    """mrgingham.find_board (mrgingham_pywrap.c:227-337): corners (or blobs) -> gridn x gridn grid -> refinement.
+    Returns the ordered (gridn*gridn, 2) float64 pixel coordinates, or None if no board was found.
+    image_pyramid_level < 0 tries levels 3,2,1,0 in turn (mrgingham.cc:127-138)."""
+    if blobs and image_pyramid_level != 0:
+        raise RuntimeError("blob detector requires that image_pyramid_level == 0")
+    dsx = dsy = -1
+    if debug_sequence is not None:
+        try:
+            dsx, dsy = (int(v) for v in str(debug_sequence).split(","))
+        except ValueError:
+            raise RuntimeError("Couldn't parse debug_sequence as an 'INTEGER,INTEGER' string")
+    image = _check_image(image, ndim_exact=2)
+    _require_gpu()
+    result = {}
+
+    def add_points(xy, n, cookie):
+        result["xy"] = np.ctypeslib.as_array(xy, shape=(2 * n,)).astype(np.float64).reshape(n, 2)
+        return True
+
+    cb = _ADD_POINTS_D(add_points)
+    ok = lib().find_chessboard_from_image_array_C(image.shape[0], image.shape[1], image.strides[0], image.ctypes.data,
+                                                  int(gridn), int(image_pyramid_level), bool(blobs), bool(debug), dsx, dsy, cb, None)
+    if not ok or "xy" not in result:
+        return None
+    return result["xy"]
 
 
 find_chessboard = find_board
@@ -211,6 +252,46 @@ def find_blobs_int(image, cap=1 << 14):
     if n > cap:
         return find_blobs_int(image, cap=n)
     return xy[:n].copy()
+
+
+def find_grid_from_points(points, gridn=10):
+    """mrgingham::find_grid_from_points (find_grid.cc:1216-1445): points = (N,2) int PointInt list (x1000);
+    returns the ordered (gridn*gridn, 2) float64 pixel coordinates, or None. Host code: works without a GPU."""
+    pts = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+    out = np.empty((gridn * gridn, 2), dtype=np.float64)
+    if len(pts) == 0 or lib().mrg_b200_find_grid_from_points(_ptr(pts, _i32p), len(pts), int(gridn), _ptr(out, _f64p)) != 1:
+        return None
+    return out
+
+
+def voronoi_neighbours(points):
+    """per point, the indices of the points whose Voronoi cells share an edge with its cell, counter-clockwise
+    in (x,y) from +x: the graph find_grid_from_points() walks (find_grid.cc:36-140)"""
+    pts = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+    n = len(pts)
+    off = np.zeros(n + 1, dtype=np.int32)
+    ring = np.zeros(8 * n + 16, dtype=np.int32)
+    total = lib().mrg_b200_voronoi_neighbours(_ptr(pts, _i32p), n, _ptr(off, _i32p), _ptr(ring, _i32p), len(ring))
+    if total > len(ring):
+        ring = np.zeros(total, dtype=np.int32)
+        total = lib().mrg_b200_voronoi_neighbours(_ptr(pts, _i32p), n, _ptr(off, _i32p), _ptr(ring, _i32p), len(ring))
+    if total < 0:
+        raise RuntimeError("mrg_b200_voronoi_neighbours() failed")
+    return [ring[off[i]:off[i + 1]].tolist() for i in range(n)]
+
+
+def find_chessboard_from_image_array(image, gridn=10, image_pyramid_level=-1, refine=True):
+    """mrgingham::find_chessboard_from_image_array (mrgingham.cc:106-140): returns (level_found, xy, levels);
+    level_found < 0 if there is no board (xy, levels are then None)"""
+    image = _check_image(image, ndim_exact=2)
+    _require_gpu()
+    xy = np.zeros((gridn * gridn, 2), dtype=np.float64)
+    lv = np.zeros(gridn * gridn, dtype=np.int8)
+    r = lib().mrg_b200_find_chessboard_from_image_array(_ptr(image, _u8p), image.shape[0], image.shape[1], image.strides[0],
+                                                        int(gridn), int(image_pyramid_level), int(bool(refine)), _ptr(xy, _f64p), _ptr(lv, _i8p))
+    if r < 0:
+        return r, None, None
+    return r, xy, (lv if refine else None)
 
 
 def refine_chessboard_corners(image, image_pyramid_level, xy, levels):
@@ -324,6 +405,20 @@ class Detector:
         if rc != 0:
             raise RuntimeError("mrg_b200_preprocess_batch() failed")
         return out
+
+    def find_boards(self, images, gridn=10, level=-1, blobs=False, refine=True, stream=None):
+        """whole boards over a batch (mrg_b200_find_boards_batch): returns (found_level int32 [n] (-1 = no board),
+        xy float64 [n, gridn*gridn, 2], levels int8 [n, gridn*gridn])"""
+        ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
+        xy = np.zeros((n, gridn * gridn, 2), dtype=np.float64)
+        lv = np.zeros((n, gridn * gridn), dtype=np.int8)
+        found = np.full(n, -1, dtype=np.int32)
+        rc = lib().mrg_b200_find_boards_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(gridn), int(level),
+                                              int(bool(blobs)), int(bool(refine)), _ptr(xy, _f64p), _ptr(lv, _i8p), _ptr(found, _i32p),
+                                              ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_find_boards_batch() failed")
+        return found, xy, lv
 
     def refine_corners(self, images, level, xy, levels, stream=None):
         """batched refinement: xy float64 [n, npoints, 2], levels int8 [n, npoints];

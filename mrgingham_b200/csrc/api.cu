@@ -7,9 +7,12 @@
 #include <mutex>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 #include "../../include/mrgingham_b200.h"
 #include "kernels.cuh"
+#include "find_grid.hh"
 
 using namespace mrgb200;
 
@@ -118,6 +121,9 @@ struct mrg_b200_detector
     int k2_smem_cands = kClusterSmemCands;   // adapted to the candidate counts of the previous batch (collect_locked)
     BlobWorkspace* blobs = nullptr;
     float blob_ms = 0;
+    // board finder: the frames of the chunk being worked on, kept on the device across the level loop
+    std::mutex   boards_mtx;
+    DeviceBuffer boards_frames;
 
     struct Pending
     {
@@ -877,4 +883,207 @@ API int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int 
     if (mrg_b200_refine_corners_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level,
                                       xy_inout, levels, Npoints, &nref, nullptr)) return -1;
     return nref;
+}
+
+// ===========================================================================================
+// Boards: corners (or blobs) -> grid -> refinement (mrgingham.cc:10-140)
+// ===========================================================================================
+namespace
+{
+// runs fn(i) for i in [0,n) on a few host threads
+template <class F> void parallel_for(int n, F fn)
+{
+    const int nt = std::min<int>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u), n / 4);
+    if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < n; ) fn(i); });
+    for (auto& t : th) t.join();
+}
+
+// One chunk of frames already on the device. level < 0: try levels 3,2,1,0 and keep the first that gives a grid
+// (mrgingham.cc:127-138). strict_level0: a level-0 pass needs pitch == cols, as the reference's corner finder does.
+int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, int rows, int cols, size_t pitch, size_t fstride,
+                      int gridn, int level, bool doblobs, bool refine, bool strict_level0,
+                      double* xy_out, signed char* levels_out, int32_t* found_out, void* stream)
+{
+    const int npts = gridn * gridn;
+    for (int i = 0; i < n; i++) found_out[i] = -1;
+    std::vector<int32_t> xy, counts(n);
+    std::vector<int> todo;
+    const int first_level = level < 0 ? 3 : level, last_level = level < 0 ? 0 : level;
+    for (int L = first_level; L >= last_level; L--)
+    {
+        todo.clear();
+        for (int i = 0; i < n; i++) if (found_out[i] < 0) todo.push_back(i);
+        if (todo.empty()) break;
+        if (L == 0 && !doblobs && strict_level0 && rows > 1 && pitch != (size_t)cols)
+        { MSG("I can only handle continuous arrays (stride == width) currently."); break; }
+        for (;;)
+        {
+            const int mp = det->cfg.max_points;
+            xy.resize((size_t)2 * mp * n);
+            bool overflow = false;
+            // contiguous runs of frames still without a grid
+            for (size_t k = 0; k < todo.size(); )
+            {
+                size_t e = k + 1;
+                while (e < todo.size() && todo[e] == todo[e - 1] + 1) e++;
+                const int a = todo[k], cnt = (int)(e - k);
+                const int rc = doblobs
+                    ? mrg_b200_find_blobs_batch(det, d_images + (size_t)a * fstride, 1, cnt, rows, cols, pitch, fstride,
+                                                xy.data() + (size_t)2 * mp * a, counts.data() + a, stream)
+                    : mrg_b200_find_corners_batch(det, d_images + (size_t)a * fstride, 1, cnt, rows, cols, pitch, fstride, L,
+                                                  xy.data() + (size_t)2 * mp * a, counts.data() + a, stream);
+                if (rc) return -1;
+                k = e;
+            }
+            int most = 0;
+            for (int i : todo) if (counts[i] > mp) { overflow = true; most = std::max(most, (int)counts[i]); }
+            if (!overflow) break;
+            det->cfg.max_points = next_pow2(most);     // more points than the output capacity: grow it and look again
+        }
+        const int mp = det->cfg.max_points;
+        parallel_for((int)todo.size(), [&](int k)
+        {
+            const int i = todo[k];
+            if (find_grid_from_points(xy.data() + (size_t)2 * mp * i, counts[i], gridn, xy_out + (size_t)2 * npts * i))
+                found_out[i] = L;
+        });
+    }
+    if (!refine || doblobs) return 0;
+
+    // mrgingham.cc:81-99: every point starts at the level the grid was found at; refine level by level while
+    // any point of the frame moves
+    std::vector<signed char> own_levels;
+    if (!levels_out) { own_levels.resize((size_t)npts * n); levels_out = own_levels.data(); }
+    int top = 0;
+    for (int i = 0; i < n; i++)
+        if (found_out[i] >= 0) { top = std::max(top, found_out[i]); for (int k = 0; k < npts; k++) levels_out[(size_t)npts * i + k] = (signed char)found_out[i]; }
+    std::vector<char> stopped(n, 0);
+    std::vector<int32_t> nref(n);
+    for (int L = top - 1; L >= 0; L--)
+    {
+        todo.clear();
+        for (int i = 0; i < n; i++) if (found_out[i] > L && !stopped[i]) todo.push_back(i);
+        for (size_t k = 0; k < todo.size(); )
+        {
+            size_t e = k + 1;
+            while (e < todo.size() && todo[e] == todo[e - 1] + 1) e++;
+            const int a = todo[k], cnt = (int)(e - k);
+            if (mrg_b200_refine_corners_batch(det, d_images + (size_t)a * fstride, 1, cnt, rows, cols, pitch, fstride, L,
+                                              xy_out + (size_t)2 * npts * a, levels_out + (size_t)npts * a, npts, nref.data() + a, stream)) return -1;
+            k = e;
+        }
+        for (int i : todo) if (nref[i] <= 0) stopped[i] = 1;
+    }
+    return 0;
+}
+
+int find_boards(mrg_b200_detector* det, const uint8_t* images, int on_device, int nframes, int rows, int cols,
+                size_t pitch, size_t fstride, int gridn, int level, bool doblobs, bool refine, bool strict_level0,
+                double* xy_out, signed char* levels_out, int32_t* found_out, void* stream_)
+{
+    if (!det) return -1;
+    if (nframes < 0 || rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767 || pitch < (size_t)cols) { MSG("Bad batch geometry."); return -1; }
+    if (gridn < 2 || gridn > 181) { MSG("gridn must be in [2,181]; got %d.", gridn); return -1; }
+    if (level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); for (int i = 0; i < nframes; i++) found_out[i] = -1; return 0; }
+    if (doblobs && level != 0) { MSG("The blob detector works at image_pyramid_level 0 only."); return -1; }
+    std::lock_guard<std::mutex> g(det->boards_mtx);
+    const int npts = gridn * gridn;
+    const int chunk = std::max(1, det->cfg.max_frames);
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        const uint8_t* d = images + (size_t)f0 * fstride;
+        size_t dpitch = pitch, dfstride = fstride;
+        if (!on_device)
+        {
+            // the frames go to the device once and stay there for every level and refinement pass
+            CUDA_TRY(cudaSetDevice(det->device));
+            cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+            dpitch = pitch == (size_t)cols ? (size_t)cols : (size_t)round_up(cols, 16);
+            dfstride = dpitch * rows;
+            if (det->boards_frames.ensure(dfstride * n)) return -1;
+            if (dpitch == pitch && fstride == dfstride)
+                CUDA_TRY(cudaMemcpyAsync(det->boards_frames.p, d, dfstride * n, cudaMemcpyHostToDevice, stream));
+            else
+                for (int i = 0; i < n; i++)
+                    CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)det->boards_frames.p + i * dfstride, dpitch, d + i * fstride, pitch, cols, rows,
+                                               cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            d = (const uint8_t*)det->boards_frames.p;
+        }
+        if (find_boards_chunk(det, d, n, rows, cols, dpitch, dfstride, gridn, level, doblobs, refine, strict_level0,
+                              xy_out + (size_t)2 * npts * f0, levels_out ? levels_out + (size_t)npts * f0 : nullptr, found_out + f0, stream_)) return -1;
+    }
+    return 0;
+}
+}   // namespace
+
+API int mrg_b200_find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out)
+{
+    if (gridn < 2 || npoints < 0 || (npoints > 0 && !xy) || !xy_out) return 0;
+    return find_grid_from_points(xy, npoints, gridn, xy_out) ? 1 : 0;
+}
+
+API int mrg_b200_voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* ring, int ring_cap)
+{
+    if (npoints <= 0 || !xy || !ring_off || (ring_cap > 0 && !ring)) return -1;
+    return voronoi_neighbours(xy, npoints, ring_off, ring, ring_cap);
+}
+
+API int mrg_b200_find_boards_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                   int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                   int gridn, int image_pyramid_level, int doblobs, int refine,
+                                   double* xy_out, signed char* levels_out, int32_t* found_level_out, void* stream)
+{
+    return find_boards(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, gridn, image_pyramid_level,
+                       doblobs != 0, refine != 0, false, xy_out, levels_out, found_level_out, stream);
+}
+
+API int mrg_b200_find_chessboard_from_image_array(const uint8_t* image, int Nrows, int Ncols, int stride,
+                                                  int gridn, int image_pyramid_level, int refine,
+                                                  double* xy_out, signed char* levels_out)
+{
+    if (Nrows <= 0 || Ncols <= 0 || stride < Ncols) { MSG("Bad image geometry."); return -1; }
+    std::lock_guard<std::mutex> g(g_default_mtx);
+    mrg_b200_detector* det = default_detector();
+    if (!det) return -1;
+    int32_t found = -1;
+    if (find_boards(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, gridn, image_pyramid_level,
+                    false, refine != 0, true, xy_out, levels_out, &found, nullptr)) return -1;
+    return found;
+}
+
+API int mrg_b200_find_circle_grid_from_image_array(const uint8_t* image, int Nrows, int Ncols, int stride,
+                                                   int gridn, double* xy_out)
+{
+    if (Nrows <= 0 || Ncols <= 0 || stride < Ncols) { MSG("Bad image geometry."); return 0; }
+    std::lock_guard<std::mutex> g(g_default_mtx);
+    mrg_b200_detector* det = default_detector();
+    if (!det) return 0;
+    int32_t found = -1;
+    if (find_boards(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, gridn, 0,
+                    true, false, true, xy_out, nullptr, &found, nullptr)) return 0;
+    return found >= 0 ? 1 : 0;
+}
+
+// mrgingham_pywrap_cplusplus_bridge.cc:72-138, what the reference's Python find_board() binds
+API bool find_chessboard_from_image_array_C(int Nrows, int Ncols, int stride, char* imagebuffer, const int gridn,
+                                            int image_pyramid_level, bool doblobs, bool debug,
+                                            int debug_sequence_x, int debug_sequence_y,
+                                            bool (*add_points)(double* xy, int N, void* cookie), void* cookie)
+{
+    (void)debug; (void)debug_sequence_x; (void)debug_sequence_y;   // diagnostics only in the reference
+    if (gridn < 2) return false;
+    std::vector<double> xy((size_t)2 * gridn * gridn);
+    if (doblobs)
+    {
+        if (image_pyramid_level != 0) return false;
+        if (mrg_b200_find_circle_grid_from_image_array((const uint8_t*)imagebuffer, Nrows, Ncols, stride, gridn, xy.data()) != 1) return false;
+    }
+    else if (mrg_b200_find_chessboard_from_image_array((const uint8_t*)imagebuffer, Nrows, Ncols, stride, gridn, image_pyramid_level, 1,
+                                                       xy.data(), nullptr) < 0) return false;
+    return (*add_points)(xy.data(), gridn * gridn, cookie);
 }

@@ -1,0 +1,544 @@
+// Host side of SURVEY.md row F1: the grid finder, mrgingham::find_grid_from_points (find_grid.cc:1216-1445),
+// which turns the detector's unordered corner list into the ordered gridn x gridn board. A few hundred
+// points per frame: this is host code (one call per frame, microseconds), not a kernel.
+//
+// The reference gets its neighbour graph from Boost.Polygon's voronoi_diagram (find_grid.cc:7,1226). This
+// file builds what the reference reads from that diagram from scratch:
+//   * an exact Delaunay triangulation of the integer sites (sorted insertion outside the current hull,
+//     Lawson flips, all predicates in 128-bit integers), whose edges, minus those between cocircular sites
+//     (Voronoi edges of zero length, which Boost removes too), are the Voronoi edges;
+//   * per cell, the neighbouring cells in counter-clockwise order in (x,y) (find_grid.cc:40-41: clockwise as
+//     seen in an image), cells visited in sorted-site order as Boost creates them.
+// PARITY UNPINNED for this row: Boost is not in this image, so the reference's grid finder cannot be run
+// here. The one thing this construction does not reproduce is which edge Boost starts a cell's walk at; it
+// matters only when several neighbours pass the reference's "first match wins" test (find_grid.cc:216-221).
+// Everything on top of the graph follows the reference's arithmetic (doubles, the float32 crossing test,
+// the truncating integer divisions).
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <set>
+#include <vector>
+
+#include "find_grid.hh"
+
+namespace mrgb200
+{
+namespace
+{
+typedef long long i64;
+typedef __int128  i128;
+
+constexpr int    kScale = 1000;        // FIND_GRID_SCALE, mrgingham-internal.h:3
+constexpr int    kScalePow2 = 1024;    // FIND_GRID_SCALE_APPROX_POWER2, mrgingham-internal.h:6
+constexpr double kMinCos = 0.984, kMinRatio = 0.7, kMaxRatio = 1.4, kMaxRatioDeviation = 0.35;   // find_grid.cc:202-205
+constexpr i64    kMaxCoord = 1ll << 29;   // keeps the in-circle determinant inside 128 bits
+
+struct P2 { i64 x, y; };
+
+inline i64 orient(const P2& a, const P2& b, const P2& c)      // > 0: a,b,c counter-clockwise
+{
+    return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
+}
+// sign of the in-circle determinant: > 0 iff d is strictly inside the circle through the ccw triangle a,b,c
+inline int incircle(const P2& a, const P2& b, const P2& c, const P2& d)
+{
+    const i64 ax = a.x - d.x, ay = a.y - d.y, bx = b.x - d.x, by = b.y - d.y, cx = c.x - d.x, cy = c.y - d.y;
+    const i128 a2 = (i128)ax * ax + (i128)ay * ay, b2 = (i128)bx * bx + (i128)by * by, c2 = (i128)cx * cx + (i128)cy * cy;
+    const i128 det = a2 * ((i128)bx * cy - (i128)by * cx) - b2 * ((i128)ax * cy - (i128)ay * cx) + c2 * ((i128)ax * by - (i128)ay * bx);
+    return det > 0 ? 1 : det < 0 ? -1 : 0;
+}
+// true if a comes before b going counter-clockwise from the +x direction
+inline bool angle_less(const P2& a, const P2& b)
+{
+    const int ha = (a.y > 0 || (a.y == 0 && a.x > 0)) ? 0 : 1, hb = (b.y > 0 || (b.y == 0 && b.x > 0)) ? 0 : 1;
+    if (ha != hb) return ha < hb;
+    return a.x * b.y - a.y * b.x > 0;
+}
+
+// ---- the neighbour graph ----
+struct Graph
+{
+    std::vector<P2>  pts;        // by source index
+    std::vector<int> sites;      // distinct sites, sorted by (x,y): the order cells are visited in
+    // counter-clockwise ring of edge-neighbours of every site (by source index)
+    std::vector<int> ring_off, ring;
+    // the walk of find_grid.cc:86-140 precomputed: each edge-neighbour followed by the in-between cell, if any
+    std::vector<int> adj_off, adj;
+
+    int ring_pos(int a, int b) const
+    {
+        for (int k = ring_off[a]; k < ring_off[a + 1]; k++) if (ring[k] == b) return k;
+        return -1;
+    }
+    int prev(int a, int b) const { const int k = ring_pos(a, b); return ring[k == ring_off[a] ? ring_off[a + 1] - 1 : k - 1]; }
+};
+
+struct Tri { int v[3]; int n[3]; };
+
+class Triangulation
+{
+public:
+    Triangulation(const std::vector<P2>& pts, const std::vector<int>& order) : P(pts), ord(order) {}
+
+    // neighbour sets (unordered) of every site; false if no triangle exists (all sites on one line)
+    bool run(std::vector<std::vector<int>>* nb)
+    {
+        const int n = (int)ord.size();
+        int m = 2;
+        while (m < n && orient(P[ord[0]], P[ord[1]], P[ord[m]]) == 0) m++;
+        if (m >= n) return false;
+        hnext.assign(P.size(), -1); hprev.assign(P.size(), -1); htri.assign(P.size(), -1);
+        T.reserve(2 * n);
+        seed(m);
+        for (int i = m + 1; i < n; i++) if (!insert(ord[i])) return false;
+
+        nb->assign(P.size(), std::vector<int>());
+        for (size_t t = 0; t < T.size(); t++)
+            for (int i = 0; i < 3; i++)
+            {
+                // directed edge a -> b, opposite vertex c
+                const int a = T[t].v[(i + 1) % 3], b = T[t].v[(i + 2) % 3], c = T[t].v[i], u = T[t].n[i];
+                if (u < 0) { (*nb)[a].push_back(b); (*nb)[b].push_back(a); continue; }
+                int j = 0; while (T[u].n[j] != (int)t) j++;
+                // the Voronoi edge between a and b has zero length when the two triangles share a circumcircle
+                if (incircle(P[c], P[a], P[b], P[T[u].v[j]]) == 0) continue;
+                (*nb)[a].push_back(b);
+            }
+        return true;
+    }
+
+private:
+    const std::vector<P2>& P;
+    const std::vector<int>& ord;
+    std::vector<Tri> T;
+    std::vector<int> hnext, hprev, htri;      // convex hull, counter-clockwise; htri[v] owns the edge v -> hnext[v]
+    int last = -1;                            // most recently inserted site (always a hull corner)
+    std::vector<std::pair<int,int>> stack;
+
+    int add(int a, int b, int c) { Tri t; t.v[0] = a; t.v[1] = b; t.v[2] = c; t.n[0] = t.n[1] = t.n[2] = -1; T.push_back(t); return (int)T.size() - 1; }
+    void link_hull(int a, int b, int t) { hnext[a] = b; hprev[b] = a; htri[a] = t; }
+    // make t's edge (a -> b) and u's edge (b -> a) neighbours
+    void glue(int t, int u, int a, int b)
+    {
+        for (int i = 0; i < 3; i++)
+        {
+            if (T[t].v[(i + 1) % 3] == a && T[t].v[(i + 2) % 3] == b) T[t].n[i] = u;
+            if (T[u].v[(i + 1) % 3] == b && T[u].v[(i + 2) % 3] == a) T[u].n[i] = t;
+        }
+    }
+
+    // ord[0..m-1] lie on one line (in sorted order along it); ord[m] is off it: a fan
+    void seed(int m)
+    {
+        const int q = ord[m];
+        const bool left = orient(P[ord[0]], P[ord[1]], P[q]) > 0;
+        int prev_t = -1;
+        for (int i = 0; i + 1 < m; i++)
+        {
+            const int a = ord[i], b = ord[i + 1];
+            const int t = left ? add(a, b, q) : add(b, a, q);
+            if (left) link_hull(a, b, t); else link_hull(b, a, t);
+            if (prev_t >= 0) { if (left) glue(prev_t, t, a, q); else glue(prev_t, t, q, a); }
+            prev_t = t;
+        }
+        if (left) { link_hull(ord[m - 1], q, prev_t); link_hull(q, ord[0], 0); }
+        else      { link_hull(q, ord[m - 1], prev_t); link_hull(ord[0], q, 0); }
+        last = q;
+    }
+
+    // p is lexicographically beyond every inserted site, so it is outside the hull and sees `last`
+    bool insert(int p)
+    {
+        int lo = last, hi = last;
+        while (orient(P[hi], P[hnext[hi]], P[p]) < 0) hi = hnext[hi];
+        while (orient(P[hprev[lo]], P[lo], P[p]) < 0) lo = hprev[lo];
+        if (lo == hi) return false;     // cannot happen for sorted distinct sites
+        int prev_t = -1, first_t = -1;
+        for (int a = lo; a != hi; )
+        {
+            const int b = hnext[a], old = htri[a];
+            const int t = add(b, a, p);
+            glue(t, old, b, a);
+            if (prev_t >= 0) glue(prev_t, t, p, a); else first_t = t;
+            prev_t = t;
+            stack.push_back(std::make_pair(t, 2));
+            a = b;
+        }
+        link_hull(lo, p, first_t);
+        link_hull(p, hi, prev_t);
+        last = p;
+        legalize();
+        return true;
+    }
+
+    void legalize()
+    {
+        while (!stack.empty())
+        {
+            const int t = stack.back().first, i = stack.back().second;
+            stack.pop_back();
+            const int u = T[t].n[i];
+            if (u < 0) continue;
+            int j = 0; while (T[u].n[j] != t) j++;
+            const int a = T[t].v[i], b = T[t].v[(i + 1) % 3], c = T[t].v[(i + 2) % 3], d = T[u].v[j];
+            if (incircle(P[a], P[b], P[c], P[d]) <= 0) continue;
+            // flip the shared edge b-c to a-d: t = (a,b,d), u = (a,d,c)
+            const int n_ac = T[t].n[(i + 1) % 3], n_ab = T[t].n[(i + 2) % 3];
+            const int n_bd = T[u].n[(j + 1) % 3], n_dc = T[u].n[(j + 2) % 3];
+            T[t].v[0] = a; T[t].v[1] = b; T[t].v[2] = d; T[t].n[0] = n_bd; T[t].n[1] = u; T[t].n[2] = n_ab;
+            T[u].v[0] = a; T[u].v[1] = d; T[u].v[2] = c; T[u].n[0] = n_dc; T[u].n[1] = n_ac; T[u].n[2] = t;
+            if (n_bd >= 0) { for (int k = 0; k < 3; k++) if (T[n_bd].n[k] == u) T[n_bd].n[k] = t; } else htri[b] = t;
+            if (n_ac >= 0) { for (int k = 0; k < 3; k++) if (T[n_ac].n[k] == t) T[n_ac].n[k] = u; } else htri[c] = u;
+            stack.push_back(std::make_pair(t, 0));
+            stack.push_back(std::make_pair(u, 0));
+        }
+    }
+};
+
+bool build_graph(Graph* g, const int* xy, int n)
+{
+    g->pts.resize(n);
+    for (int i = 0; i < n; i++)
+    {
+        g->pts[i].x = xy[2 * i]; g->pts[i].y = xy[2 * i + 1];
+        if (g->pts[i].x < -kMaxCoord || g->pts[i].x > kMaxCoord || g->pts[i].y < -kMaxCoord || g->pts[i].y > kMaxCoord) return false;
+    }
+    // sorted, distinct sites (Boost sorts the site events and drops repeated ones)
+    std::vector<int>& s = g->sites;
+    s.resize(n);
+    for (int i = 0; i < n; i++) s[i] = i;
+    const std::vector<P2>& P = g->pts;
+    std::sort(s.begin(), s.end(), [&](int a, int b) { return P[a].x != P[b].x ? P[a].x < P[b].x : P[a].y != P[b].y ? P[a].y < P[b].y : a < b; });
+    s.erase(std::unique(s.begin(), s.end(), [&](int a, int b) { return P[a].x == P[b].x && P[a].y == P[b].y; }), s.end());
+
+    std::vector<std::vector<int>> nb;
+    Triangulation tri(P, s);
+    if (!tri.run(&nb))
+    {
+        // every site on one line: consecutive sites are neighbours
+        nb.assign(n, std::vector<int>());
+        for (size_t k = 0; k + 1 < s.size(); k++) { nb[s[k]].push_back(s[k + 1]); nb[s[k + 1]].push_back(s[k]); }
+    }
+    g->ring_off.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) g->ring_off[i + 1] = g->ring_off[i] + (int)nb[i].size();
+    g->ring.resize(g->ring_off[n]);
+    for (int i = 0; i < n; i++)
+    {
+        std::vector<int>& r = nb[i];
+        std::sort(r.begin(), r.end(), [&](int a, int b)
+                  { const P2 va = { P[a].x - P[i].x, P[a].y - P[i].y }, vb = { P[b].x - P[i].x, P[b].y - P[i].y }; return angle_less(va, vb); });
+        std::copy(r.begin(), r.end(), g->ring.begin() + g->ring_off[i]);
+    }
+    // the neighbours the reference looks at from each cell (find_grid.cc:86-140)
+    g->adj_off.assign(n + 1, 0);
+    g->adj.clear();
+    for (int a = 0; a < n; a++)
+    {
+        for (int k = g->ring_off[a]; k < g->ring_off[a + 1]; k++)
+        {
+            const int b = g->ring[k];
+            g->adj.push_back(b);
+            const int c = g->ring[k + 1 == g->ring_off[a + 1] ? g->ring_off[a] : k + 1];
+            const P2 v0 = { P[b].x - P[a].x, P[b].y - P[a].y }, v1 = { P[c].x - P[a].x, P[c].y - P[a].y };
+            if (v1.x * v0.y > v0.x * v1.y) continue;            // b, c do not turn the right way: the graph's boundary
+            if (g->prev(b, a) != c) continue;                   // a, b, c are not a triangle
+            const int d = g->prev(b, c);
+            const P2 vm = { P[d].x - P[a].x, P[d].y - P[a].y };
+            if (v1.x * vm.y > vm.x * v1.y) continue;            // the in-between cell must lie between b and c
+            if (vm.x * v0.y > v0.x * vm.y) continue;
+            g->adj.push_back(d);
+        }
+        g->adj_off[a + 1] = (int)g->adj.size();
+    }
+    return true;
+}
+
+// ---- sequences (find_grid.cc:160-343) ----
+struct Walk
+{
+    i64    dlx, dly;        // most recent step
+    double ratio_sum;
+    int    ratio_n;
+};
+
+// the first neighbour of c that continues the sequence, or -1
+int step(const Graph& g, Walk* w, int c)
+{
+    const std::vector<P2>& P = g.pts;
+    const double last_len = hypot((double)w->dlx, (double)w->dly);
+    for (int k = g.adj_off[c]; k < g.adj_off[c + 1]; k++)
+    {
+        const int cand = g.adj[k];
+        const i64 dx = P[cand].x - P[c].x, dy = P[cand].y - P[c].y;
+        const double len = hypot((double)dx, (double)dy);
+        const double cos_err = ((double)w->dlx * (double)dx + (double)w->dly * (double)dy) / (last_len * len);
+        if (cos_err < kMinCos) continue;
+        const double ratio = len / last_len;
+        if (ratio < kMinRatio || ratio > kMaxRatio) continue;
+        if (w->ratio_n > 2)
+        {
+            const double dev = ratio - w->ratio_sum / (double)w->ratio_n;
+            if (dev < -kMaxRatioDeviation || dev > kMaxRatioDeviation) continue;
+        }
+        w->ratio_sum += ratio;
+        w->ratio_n++;
+        w->dlx = dx; w->dly = dy;
+        return cand;
+    }
+    return -1;
+}
+
+struct Sequence
+{
+    int    c0, c1, clast;
+    double mean_dx, mean_dy;
+};
+
+// cells c0, c1 and the gridn-2 that follow (valid for a Sequence that was found: the walk is deterministic)
+void sequence_cells(const Graph& g, const Sequence& s, int gridn, int* cells)
+{
+    cells[0] = s.c0; cells[1] = s.c1;
+    Walk w = { g.pts[s.c1].x - g.pts[s.c0].x, g.pts[s.c1].y - g.pts[s.c0].y, 0.0, 0 };
+    int c = s.c1;
+    for (int i = 0; i < gridn - 2; i++) { c = step(g, &w, c); cells[2 + i] = c; }
+}
+
+// find_grid.cc:776-822 (float32 throughout)
+bool is_crossing(const std::vector<P2>& P, int a0, int a1, int b0, int b1)
+{
+    const float l0x = (float)(int)(P[a1].x - P[a0].x), l0y = (float)(int)(P[a1].y - P[a0].y);
+    const float p0x = (float)(int)(P[b0].x - P[a0].x), p0y = (float)(int)(P[b0].y - P[a0].y);
+    const float p1x = (float)(int)(P[b1].x - P[a0].x), p1y = (float)(int)(P[b1].y - P[a0].y);
+    const float d2 = l0x * l0x + l0y * l0y;
+    const float r0x = p0x * l0x + p0y * l0y, r0y = -p0x * l0y + p0y * l0x;
+    const float r1x = p1x * l0x + p1y * l0y, r1y = -p1x * l0y + p1y * l0x;
+    if (r0y * r1y > 0) return false;
+    if ((r0x < 0 && r1x < 0) || (r0x > d2 && r1x > d2)) return false;
+    const float k = r0y / (r0y - r1y);
+    const float x = r0x + k * (r1x - r0x);
+    return x >= 0.0f && x <= d2;
+}
+
+struct Cycle { int e[4]; };
+
+struct Finder
+{
+    const Graph&             g;
+    int                      gridn;
+    std::vector<Sequence>    seq;
+    std::vector<int>         outer;                        // indices into seq
+    std::map<int, std::vector<int>> outer_from;            // first cell -> indices into outer
+
+    int first(int i) const { return seq[outer[i]].c0; }
+    int last (int i) const { return seq[outer[i]].clast; }
+
+    // find_grid.cc:826-960: extend e[0..count-1] to the unique 4-cycle that returns to `start`
+    bool extend_cycle(Cycle* cyc, int count, int start) const
+    {
+        bool  found = false;
+        Cycle best = {};
+        const int cur = cyc->e[count - 1];
+        std::map<int, std::vector<int>>::const_iterator it = outer_from.find(last(cur));
+        if (it == outer_from.end()) return false;
+        const std::vector<int>& nxt = it->second;
+        for (size_t k = 0; k < nxt.size(); k++)
+        {
+            const int e = nxt[k];
+            if (last(e) == first(cur)) continue;                   // straight back
+            if (count != 3)
+            {
+                if (last(e) == start) continue;                    // closes too early
+                if (count == 2 && is_crossing(g.pts, first(cyc->e[0]), last(cyc->e[0]), first(e), last(e))) continue;
+                cyc->e[count] = e;
+                if (!extend_cycle(cyc, count + 1, start)) continue;
+                if (found) return false;                           // two different cycles: ambiguous
+                found = true;
+                best = *cyc;
+            }
+            else
+            {
+                if (last(e) != start) continue;
+                if (is_crossing(g.pts, first(cyc->e[1]), last(cyc->e[1]), first(e), last(e))) return false;
+                cyc->e[3] = e;
+                return true;
+            }
+        }
+        if (!found) return false;
+        *cyc = best;
+        return true;
+    }
+
+    // find_grid.cc:962-1013
+    bool opposite(const Cycle& a, const Cycle& b) const
+    {
+        int ia = 0, ib = -1;
+        for (int k = 0; k < 4; k++) if (last(b.e[k]) == first(a.e[0])) { ib = k; break; }
+        if (ib < 0) return false;
+        for (int k = 0; k < 4; k++)
+        {
+            if (first(a.e[ia]) != last(b.e[ib]) || last(a.e[ia]) != first(b.e[ib])) return false;
+            ia = (ia + 1) % 4; ib = (ib + 3) % 4;
+        }
+        return true;
+    }
+
+    // find_grid.cc:1015-1187: 0/1 = which cycle runs clockwise, top[] = the top edge of each; <0: give up
+    int orient_cycles(const Cycle* cyc[2], int top[2]) const
+    {
+        const std::vector<P2>& P = g.pts;
+        int v[4][2];
+        for (int i = 0; i < 4; i++)
+        {
+            v[i][0] = (int)(P[last(cyc[0]->e[i])].x - P[first(cyc[0]->e[i])].x) / kScalePow2;
+            v[i][1] = (int)(P[last(cyc[0]->e[i])].y - P[first(cyc[0]->e[i])].y) / kScalePow2;
+        }
+        bool sign[4];
+        for (int i = 0; i < 4; i++) { const int j = (i + 1) % 4; sign[i] = (i64)v[j][0] * v[i][1] < (i64)v[i][0] * v[j][1]; }
+        int clockwise;
+        if      ( sign[0] &&  sign[1] &&  sign[2] &&  sign[3]) clockwise = 0;
+        else if (!sign[0] && !sign[1] && !sign[2] && !sign[3]) clockwise = 1;
+        else return -1;                                            // not convex
+
+        for (int ic = 0; ic < 2; ic++)
+        {
+            // the two edges that share the vertex with the smallest y; the more horizontal one is the top
+            i64 ymin[2] = { INT_MAX, INT_MAX };
+            int edge[2] = { -1, -1 }, lo[2] = { 0, 0 }, hi[2] = { 0, 0 };
+            for (int i = 0; i < 4; i++)
+            {
+                const int p0 = first(cyc[ic]->e[i]), p1 = last(cyc[ic]->e[i]);
+                const bool up = P[p0].y < P[p1].y;
+                const i64 y = up ? P[p0].y : P[p1].y;
+                const int l = up ? p0 : p1, h = up ? p1 : p0;
+                if (y < ymin[0])
+                {
+                    ymin[1] = ymin[0]; edge[1] = edge[0]; lo[1] = lo[0]; hi[1] = hi[0];
+                    ymin[0] = y; edge[0] = i; lo[0] = l; hi[0] = h;
+                }
+                else if (y < ymin[1]) { ymin[1] = y; edge[1] = i; lo[1] = l; hi[1] = h; }
+            }
+            i64 v0y = (int)(P[hi[0]].y - P[lo[0]].y) / kScalePow2, v0x = (int)(P[hi[0]].x - P[lo[0]].x) / kScalePow2;
+            i64 v1y = (int)(P[hi[1]].y - P[lo[1]].y) / kScalePow2, v1x = (int)(P[hi[1]].x - P[lo[1]].x) / kScalePow2;
+            if (v0x < 0) v0x = -v0x;
+            if (v1x < 0) v1x = -v1x;
+            const i64 cross = (v0x * v1y - v0y * v1x) * (v0x * v1y - v0y * v1x);
+            const i64 denom = (v0x * v0x + v0y * v0y) * (v1x * v1x + v1y * v1y);
+            if ((cross < 0 ? -cross : cross) * 8 < denom * 1) return -1;        // too close to call (sin^2 < 1/8)
+            const i64 l = v0y * v1x, r = v1y * v0x;
+            top[ic] = (l < 0 ? -l : l) < (r < 0 ? -r : r) ? edge[0] : edge[1];
+        }
+        return clockwise;
+    }
+};
+}   // namespace
+
+int voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* ring, int ring_cap)
+{
+    Graph g;
+    if (npoints <= 0 || !build_graph(&g, xy, npoints)) return -1;
+    for (int i = 0; i <= npoints; i++) ring_off[i] = g.ring_off[i];
+    for (int k = 0; k < g.ring_off[npoints] && k < ring_cap; k++) ring[k] = g.ring[k];
+    return g.ring_off[npoints];
+}
+
+bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out)
+{
+    if (npoints <= 0 || gridn < 2 || !xy || !xy_out) return false;
+    Graph g;
+    if (!build_graph(&g, xy, npoints)) return false;
+    Finder F = { g, gridn, {}, {}, {} };
+
+    // every run of gridn cells, from every cell towards every neighbour (find_grid.cc:505-566)
+    for (size_t si = 0; si < g.sites.size(); si++)
+    {
+        const int c = g.sites[si];
+        for (int k = g.adj_off[c]; k < g.adj_off[c + 1]; k++)
+        {
+            const int c1 = g.adj[k];
+            Walk w = { g.pts[c1].x - g.pts[c].x, g.pts[c1].y - g.pts[c].y, 0.0, 0 };
+            double mx = (double)w.dlx, my = (double)w.dly;
+            int cur = c1, clast = -1;
+            for (int i = 0; i < gridn - 2; i++)
+            {
+                cur = step(g, &w, cur);
+                if (cur < 0) { clast = -1; break; }
+                mx += (double)w.dlx; my += (double)w.dly;
+                clast = cur;
+            }
+            if (clast < 0) continue;
+            const Sequence s = { c, c1, clast, mx / (double)(gridn - 1), my / (double)(gridn - 1) };
+            F.seq.push_back(s);
+        }
+    }
+
+    // the board's outer edges start at cells that start at least two sequences (find_grid.cc:1244-1275)
+    std::map<int, int> started;
+    for (size_t i = 0; i < F.seq.size(); i++) started[F.seq[i].c0]++;
+    for (size_t i = 0; i < F.seq.size(); i++) if (started[F.seq[i].c0] >= 2) F.outer.push_back((int)i);
+    if (F.outer.size() < 8) return false;
+    for (size_t i = 0; i < F.outer.size(); i++) F.outer_from[F.first((int)i)].push_back((int)i);
+
+    // 4-cycles of outer edges (find_grid.cc:1290-1317)
+    std::vector<Cycle> cycles;
+    std::set<int> used;
+    for (int i = 0; i < (int)F.outer.size(); i++)
+    {
+        if (used.count(i)) continue;
+        Cycle c = {}; c.e[0] = i;
+        if (!F.extend_cycle(&c, 1, F.first(i))) continue;
+        cycles.push_back(c);
+        for (int k = 0; k < 4; k++) used.insert(c.e[k]);
+    }
+    if (cycles.size() < 2) return false;
+
+    // exactly one pair of cycles running the same way round in opposite directions (find_grid.cc:1329-1353)
+    int pair[2] = { -1, -1 };
+    for (size_t a = 0; a < cycles.size(); a++)
+        for (size_t b = a + 1; b < cycles.size(); b++)
+            if (F.opposite(cycles[a], cycles[b]))
+            {
+                if (pair[0] >= 0) return false;
+                pair[0] = (int)a; pair[1] = (int)b;
+            }
+    if (pair[0] < 0) return false;
+
+    const Cycle* cyc[2] = { &cycles[pair[0]], &cycles[pair[1]] };
+    int top[2];
+    const int cw = F.orient_cycles(cyc, top);
+    if (cw < 0) return false;
+
+    // rows run from the i-th cell of the left edge to the i-th cell of the right edge (find_grid.cc:1385-1433)
+    std::map<int, std::vector<int>> seq_from;
+    for (size_t i = 0; i < F.seq.size(); i++) seq_from[F.seq[i].c0].push_back((int)i);
+    auto from_to = [&](int a, int b) -> int
+    {
+        std::map<int, std::vector<int>>::const_iterator it = seq_from.find(a);
+        if (it == seq_from.end()) return -1;
+        for (size_t k = 0; k < it->second.size(); k++) if (F.seq[it->second[k]].clast == b) return it->second[k];
+        return -1;
+    };
+    std::vector<int> rows(gridn), left(gridn), right(gridn), cells(gridn);
+    rows[0] = F.outer[cyc[cw]->e[top[cw]]];
+    sequence_cells(g, F.seq[F.outer[cyc[1 - cw]->e[(top[1 - cw] + 1) % 4]]], gridn, left.data());
+    sequence_cells(g, F.seq[F.outer[cyc[cw]->e[(top[cw] + 1) % 4]]], gridn, right.data());
+    for (int i = 1; i < gridn; i++)
+    {
+        rows[i] = from_to(left[i], right[i]);
+        if (rows[i] < 0 || from_to(right[i], left[i]) < 0) return false;
+    }
+    for (int i = 0; i < gridn; i++)
+    {
+        sequence_cells(g, F.seq[rows[i]], gridn, cells.data());
+        for (int k = 0; k < gridn; k++)
+        {
+            xy_out[2 * (i * gridn + k)]     = (double)g.pts[cells[k]].x / (double)kScale;
+            xy_out[2 * (i * gridn + k) + 1] = (double)g.pts[cells[k]].y / (double)kScale;
+        }
+    }
+    return true;
+}
+
+}

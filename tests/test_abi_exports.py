@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "mrgingham_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(mrg_b200_\w+|mrgingham_ChESS_response_5|find_chessboard_corners_from_image_array_C)\s*\(", src)
+    names = re.findall(r"\b(mrg_b200_\w+|mrgingham_ChESS_response_5|find_chessboard_corners_from_image_array_C|find_chessboard_from_image_array_C)\s*\(", src)
     return sorted(set(n for n in names if n not in ("mrg_b200_detector", "mrg_b200_detector_config")))
 
 
@@ -66,12 +66,21 @@ def test_cxx_adapter_headers_compile(tmp_path):
     import subprocess
     src = tmp_path / "t.cc"
     src.write_text('#include <mrgingham_b200/find_chessboard_corners.hh>\n#include <mrgingham_b200/find_blobs.hh>\n'
+                   '#include <mrgingham_b200/mrgingham.hh>\n'
                    'int main(int argc, char**) {\n'
                    '  std::vector<mrgingham::PointInt> p; std::vector<mrgingham::PointDouble> q; signed char lv[1];\n'
                    '  mrgingham::ImageView v = {0, 0, 0, nullptr};\n'
                    '  if (argc > 100) { mrgingham::find_chessboard_corners_from_image_array(&p, v, 0);\n'
                    '    mrgingham::refine_chessboard_corners_from_image_array(&q, lv, v, 0);\n'
-                   '    mrgingham::find_blobs_from_image_array(&p, v); }\n'
+                   '    mrgingham::find_blobs_from_image_array(&p, v);\n'
+                   '    signed char* rl = NULL; mrgingham::find_chessboard_from_image_array(q, &rl, 10, v); free(rl);\n'
+                   '    mrgingham::find_circle_grid_from_image_array(q, v, 10); }\n'
+                   '  // the grid finder is host code: a 4x4 lattice sheared off the axes, found without a GPU\n'
+                   '  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++)\n'
+                   '    p.push_back(mrgingham::PointInt(100000 + j*50000 + i*3000, 100000 + i*50000 - j*3000));\n'
+                   '  if (!mrgingham::find_grid_from_points(q, p, 4) || q.size() != 16) return 1;\n'
+                   '  if (q[0].x != 100.0 || q[0].y != 100.0 || q[1].x != 150.0 || q[1].y != 97.0 || q[4].x != 103.0) return 2;\n'
+                   '  if (mrgingham::find_grid_from_points(q, p, 5) || q.size() != 16) return 3;\n'
                    '  return 0; }\n')
     lib = os.path.join(ROOT, "mrgingham_b200")
     subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(tmp_path / "t"),
