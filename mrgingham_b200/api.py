@@ -294,6 +294,20 @@ def find_chessboard_from_image_array(image, gridn=10, image_pyramid_level=-1, re
     return r, xy, (lv if refine else None)
 
 
+VNLOG_LEGEND = "# filename x y level"
+
+
+def format_vnlog(filename, xy, levels):
+    """the reference CLI's output records for one image (mrgingham-from-image.cc:174-187, legend :349):
+    'filename x y level' per point ("%s %f %f %d"), or 'filename - - -' when no board was found (xy is None).
+    levels: one level per point, or a single int (the level the board was found at, when not refined)."""
+    if xy is None:
+        return "%s - - -\n" % filename
+    xy = np.asarray(xy, dtype=np.float64).reshape(-1, 2)
+    lv = np.broadcast_to(np.asarray(levels, dtype=np.int64), (len(xy),))
+    return "".join("%s %f %f %d\n" % (filename, x, y, l) for (x, y), l in zip(xy, lv))
+
+
 def refine_chessboard_corners(image, image_pyramid_level, xy, levels):
     """mrgingham::refine_chessboard_corners_from_image_array: returns (nrefined, xy', levels')"""
     image = _check_image(image, ndim_exact=2)

@@ -123,7 +123,7 @@ struct mrg_b200_detector
     float blob_ms = 0;
     // board finder: the frames of the chunk being worked on, kept on the device across the level loop
     std::mutex   boards_mtx;
-    DeviceBuffer boards_frames;
+    DeviceBuffer boards_frames, boards_gather;
 
     struct Pending
     {
@@ -442,10 +442,11 @@ API void mrg_b200_detector_destroy(mrg_b200_detector* det)
     cudaDeviceSynchronize();
     for (auto& S : det->slot)
     {
-        for (DeviceBuffer* b : { &S.stage, &S.level_img, &S.cand, &S.counts, &S.table, &S.dfs, &S.records, &S.xy, &S.outcounts }) b->release();
+        for (DeviceBuffer* b : { &S.stage, &S.blurred, &S.equalized, &S.pre_scratch, &S.level_img, &S.cand, &S.counts, &S.table, &S.dfs, &S.records, &S.xy, &S.outcounts }) b->release();
         for (cudaEvent_t e : { S.staged, S.k1done, S.k2done }) if (e) cudaEventDestroy(e);
     }
-    for (DeviceBuffer* b : { &det->big_cand, &det->big_table, &det->big_dfs, &det->big_records, &det->pts, &det->lvls }) b->release();
+    for (DeviceBuffer* b : { &det->big_cand, &det->big_table, &det->big_dfs, &det->big_records, &det->pts, &det->lvls, &det->boards_frames,
+                             &det->boards_gather }) b->release();
     if (det->ev_fork) cudaEventDestroy(det->ev_fork);
     if (det->aux_stream) cudaStreamDestroy(det->aux_stream);
     if (det->copy_stream) cudaStreamDestroy(det->copy_stream);
@@ -901,16 +902,40 @@ template <class F> void parallel_for(int n, F fn)
     for (auto& t : th) t.join();
 }
 
+// The frames idx[] of a device-resident chunk as one contiguous batch: in place when they are consecutive,
+// otherwise copied (device to device, a few microseconds per frame) into the detector's gather buffer.
+int gather_frames(mrg_b200_detector* det, cudaStream_t stream, const uint8_t* d_images, int rows, int cols, size_t pitch, size_t fstride,
+                  const std::vector<int>& idx, const uint8_t** base, size_t* gpitch, size_t* gfstride)
+{
+    bool consecutive = true;
+    for (size_t k = 1; k < idx.size(); k++) consecutive = consecutive && idx[k] == idx[k - 1] + 1;
+    if (consecutive) { *base = d_images + (size_t)idx[0] * fstride; *gpitch = pitch; *gfstride = fstride; return 0; }
+    const size_t p = (size_t)round_up(cols, 16), fs = p * rows;
+    if (det->boards_gather.ensure(fs * idx.size())) return -1;
+    for (size_t k = 0; k < idx.size(); )
+    {
+        size_t e = k + 1;
+        while (e < idx.size() && idx[e] == idx[e - 1] + 1 && fstride == pitch * rows) e++;
+        CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)det->boards_gather.p + k * fs, p, d_images + (size_t)idx[k] * fstride, pitch, cols,
+                                   (size_t)rows * (e - k), cudaMemcpyDeviceToDevice, stream));
+        k = e;
+    }
+    *base = (const uint8_t*)det->boards_gather.p; *gpitch = p; *gfstride = fs;
+    return 0;
+}
+
 // One chunk of frames already on the device. level < 0: try levels 3,2,1,0 and keep the first that gives a grid
 // (mrgingham.cc:127-138). strict_level0: a level-0 pass needs pitch == cols, as the reference's corner finder does.
 int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, int rows, int cols, size_t pitch, size_t fstride,
                       int gridn, int level, bool doblobs, bool refine, bool strict_level0,
-                      double* xy_out, signed char* levels_out, int32_t* found_out, void* stream)
+                      double* xy_out, signed char* levels_out, int32_t* found_out, void* stream_)
 {
     const int npts = gridn * gridn;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
     for (int i = 0; i < n; i++) found_out[i] = -1;
     std::vector<int32_t> xy, counts(n);
     std::vector<int> todo;
+    const uint8_t* base; size_t gp, gfs;
     const int first_level = level < 0 ? 3 : level, last_level = level < 0 ? 0 : level;
     for (int L = first_level; L >= last_level; L--)
     {
@@ -919,35 +944,26 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
         if (todo.empty()) break;
         if (L == 0 && !doblobs && strict_level0 && rows > 1 && pitch != (size_t)cols)
         { MSG("I can only handle continuous arrays (stride == width) currently."); break; }
+        // the frames still without a grid, as one batch (results in the order of todo[])
+        const int cnt = (int)todo.size();
+        if (gather_frames(det, stream, d_images, rows, cols, pitch, fstride, todo, &base, &gp, &gfs)) return -1;
         for (;;)
         {
             const int mp = det->cfg.max_points;
-            xy.resize((size_t)2 * mp * n);
-            bool overflow = false;
-            // contiguous runs of frames still without a grid
-            for (size_t k = 0; k < todo.size(); )
-            {
-                size_t e = k + 1;
-                while (e < todo.size() && todo[e] == todo[e - 1] + 1) e++;
-                const int a = todo[k], cnt = (int)(e - k);
-                const int rc = doblobs
-                    ? mrg_b200_find_blobs_batch(det, d_images + (size_t)a * fstride, 1, cnt, rows, cols, pitch, fstride,
-                                                xy.data() + (size_t)2 * mp * a, counts.data() + a, stream)
-                    : mrg_b200_find_corners_batch(det, d_images + (size_t)a * fstride, 1, cnt, rows, cols, pitch, fstride, L,
-                                                  xy.data() + (size_t)2 * mp * a, counts.data() + a, stream);
-                if (rc) return -1;
-                k = e;
-            }
+            xy.resize((size_t)2 * mp * cnt);
+            const int rc = doblobs ? mrg_b200_find_blobs_batch(det, base, 1, cnt, rows, cols, gp, gfs, xy.data(), counts.data(), stream)
+                                   : mrg_b200_find_corners_batch(det, base, 1, cnt, rows, cols, gp, gfs, L, xy.data(), counts.data(), stream);
+            if (rc) return -1;
             int most = 0;
-            for (int i : todo) if (counts[i] > mp) { overflow = true; most = std::max(most, (int)counts[i]); }
-            if (!overflow) break;
+            for (int k = 0; k < cnt; k++) most = std::max(most, (int)counts[k]);
+            if (most <= mp) break;
             det->cfg.max_points = next_pow2(most);     // more points than the output capacity: grow it and look again
         }
         const int mp = det->cfg.max_points;
-        parallel_for((int)todo.size(), [&](int k)
+        parallel_for(cnt, [&](int k)
         {
             const int i = todo[k];
-            if (find_grid_from_points(xy.data() + (size_t)2 * mp * i, counts[i], gridn, xy_out + (size_t)2 * npts * i))
+            if (find_grid_from_points(xy.data() + (size_t)2 * mp * k, counts[k], gridn, xy_out + (size_t)2 * npts * i))
                 found_out[i] = L;
         });
     }
@@ -962,20 +978,28 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
         if (found_out[i] >= 0) { top = std::max(top, found_out[i]); for (int k = 0; k < npts; k++) levels_out[(size_t)npts * i + k] = (signed char)found_out[i]; }
     std::vector<char> stopped(n, 0);
     std::vector<int32_t> nref(n);
+    std::vector<double> txy;
+    std::vector<signed char> tlv;
     for (int L = top - 1; L >= 0; L--)
     {
         todo.clear();
         for (int i = 0; i < n; i++) if (found_out[i] > L && !stopped[i]) todo.push_back(i);
-        for (size_t k = 0; k < todo.size(); )
+        if (todo.empty()) break;
+        const int cnt = (int)todo.size();
+        if (gather_frames(det, stream, d_images, rows, cols, pitch, fstride, todo, &base, &gp, &gfs)) return -1;
+        txy.resize((size_t)2 * npts * cnt); tlv.resize((size_t)npts * cnt);
+        for (int k = 0; k < cnt; k++)
         {
-            size_t e = k + 1;
-            while (e < todo.size() && todo[e] == todo[e - 1] + 1) e++;
-            const int a = todo[k], cnt = (int)(e - k);
-            if (mrg_b200_refine_corners_batch(det, d_images + (size_t)a * fstride, 1, cnt, rows, cols, pitch, fstride, L,
-                                              xy_out + (size_t)2 * npts * a, levels_out + (size_t)npts * a, npts, nref.data() + a, stream)) return -1;
-            k = e;
+            memcpy(&txy[(size_t)2 * npts * k], xy_out + (size_t)2 * npts * todo[k], sizeof(double) * 2 * npts);
+            memcpy(&tlv[(size_t)npts * k], levels_out + (size_t)npts * todo[k], npts);
         }
-        for (int i : todo) if (nref[i] <= 0) stopped[i] = 1;
+        if (mrg_b200_refine_corners_batch(det, base, 1, cnt, rows, cols, gp, gfs, L, txy.data(), tlv.data(), npts, nref.data(), stream)) return -1;
+        for (int k = 0; k < cnt; k++)
+        {
+            memcpy(xy_out + (size_t)2 * npts * todo[k], &txy[(size_t)2 * npts * k], sizeof(double) * 2 * npts);
+            memcpy(levels_out + (size_t)npts * todo[k], &tlv[(size_t)npts * k], npts);
+            if (nref[k] <= 0) stopped[todo[k]] = 1;
+        }
     }
     return 0;
 }

@@ -67,6 +67,7 @@ struct Graph
     std::vector<int> ring_off, ring;
     // the walk of find_grid.cc:86-140 precomputed: each edge-neighbour followed by the in-between cell, if any
     std::vector<int> adj_off, adj;
+    std::vector<double> adj_dx, adj_dy, adj_len;   // the step to each of them and its hypot()
 
     int ring_pos(int a, int b) const
     {
@@ -83,8 +84,9 @@ class Triangulation
 public:
     Triangulation(const std::vector<P2>& pts, const std::vector<int>& order) : P(pts), ord(order) {}
 
-    // neighbour sets (unordered) of every site; false if no triangle exists (all sites on one line)
-    bool run(std::vector<std::vector<int>>* nb)
+    // directed neighbour pairs (a,b), each neighbour relation in both directions; false if no triangle exists
+    // (all sites on one line)
+    bool run(std::vector<std::pair<int,int>>* nb)
     {
         const int n = (int)ord.size();
         int m = 2;
@@ -95,17 +97,18 @@ public:
         seed(m);
         for (int i = m + 1; i < n; i++) if (!insert(ord[i])) return false;
 
-        nb->assign(P.size(), std::vector<int>());
+        nb->clear();
+        nb->reserve(3 * T.size() + 16);
         for (size_t t = 0; t < T.size(); t++)
             for (int i = 0; i < 3; i++)
             {
                 // directed edge a -> b, opposite vertex c
                 const int a = T[t].v[(i + 1) % 3], b = T[t].v[(i + 2) % 3], c = T[t].v[i], u = T[t].n[i];
-                if (u < 0) { (*nb)[a].push_back(b); (*nb)[b].push_back(a); continue; }
+                if (u < 0) { nb->push_back(std::make_pair(a, b)); nb->push_back(std::make_pair(b, a)); continue; }
                 int j = 0; while (T[u].n[j] != (int)t) j++;
                 // the Voronoi edge between a and b has zero length when the two triangles share a circumcircle
                 if (incircle(P[c], P[a], P[b], P[T[u].v[j]]) == 0) continue;
-                (*nb)[a].push_back(b);
+                nb->push_back(std::make_pair(a, b));
             }
         return true;
     }
@@ -214,24 +217,25 @@ bool build_graph(Graph* g, const int* xy, int n)
     std::sort(s.begin(), s.end(), [&](int a, int b) { return P[a].x != P[b].x ? P[a].x < P[b].x : P[a].y != P[b].y ? P[a].y < P[b].y : a < b; });
     s.erase(std::unique(s.begin(), s.end(), [&](int a, int b) { return P[a].x == P[b].x && P[a].y == P[b].y; }), s.end());
 
-    std::vector<std::vector<int>> nb;
+    std::vector<std::pair<int,int>> nb;
     Triangulation tri(P, s);
     if (!tri.run(&nb))
     {
         // every site on one line: consecutive sites are neighbours
-        nb.assign(n, std::vector<int>());
-        for (size_t k = 0; k + 1 < s.size(); k++) { nb[s[k]].push_back(s[k + 1]); nb[s[k + 1]].push_back(s[k]); }
+        nb.clear();
+        for (size_t k = 0; k + 1 < s.size(); k++) { nb.push_back(std::make_pair(s[k], s[k + 1])); nb.push_back(std::make_pair(s[k + 1], s[k])); }
     }
     g->ring_off.assign(n + 1, 0);
-    for (int i = 0; i < n; i++) g->ring_off[i + 1] = g->ring_off[i] + (int)nb[i].size();
+    for (size_t k = 0; k < nb.size(); k++) g->ring_off[nb[k].first + 1]++;
+    for (int i = 0; i < n; i++) g->ring_off[i + 1] += g->ring_off[i];
     g->ring.resize(g->ring_off[n]);
-    for (int i = 0; i < n; i++)
     {
-        std::vector<int>& r = nb[i];
-        std::sort(r.begin(), r.end(), [&](int a, int b)
-                  { const P2 va = { P[a].x - P[i].x, P[a].y - P[i].y }, vb = { P[b].x - P[i].x, P[b].y - P[i].y }; return angle_less(va, vb); });
-        std::copy(r.begin(), r.end(), g->ring.begin() + g->ring_off[i]);
+        std::vector<int> fill(g->ring_off.begin(), g->ring_off.end() - 1);
+        for (size_t k = 0; k < nb.size(); k++) g->ring[fill[nb[k].first]++] = nb[k].second;
     }
+    for (int i = 0; i < n; i++)
+        std::sort(g->ring.begin() + g->ring_off[i], g->ring.begin() + g->ring_off[i + 1], [&](int a, int b)
+                  { const P2 va = { P[a].x - P[i].x, P[a].y - P[i].y }, vb = { P[b].x - P[i].x, P[b].y - P[i].y }; return angle_less(va, vb); });
     // the neighbours the reference looks at from each cell (find_grid.cc:86-140)
     g->adj_off.assign(n + 1, 0);
     g->adj.clear();
@@ -253,13 +257,21 @@ bool build_graph(Graph* g, const int* xy, int n)
         }
         g->adj_off[a + 1] = (int)g->adj.size();
     }
+    g->adj_dx.resize(g->adj.size()); g->adj_dy.resize(g->adj.size()); g->adj_len.resize(g->adj.size());
+    for (int a = 0; a < n; a++)
+        for (int k = g->adj_off[a]; k < g->adj_off[a + 1]; k++)
+        {
+            g->adj_dx[k] = (double)(P[g->adj[k]].x - P[a].x); g->adj_dy[k] = (double)(P[g->adj[k]].y - P[a].y);
+            g->adj_len[k] = hypot(g->adj_dx[k], g->adj_dy[k]);
+        }
     return true;
 }
 
 // ---- sequences (find_grid.cc:160-343) ----
 struct Walk
 {
-    i64    dlx, dly;        // most recent step
+    double dlx, dly;        // most recent step (integer-valued)
+    double last_len;        // its length
     double ratio_sum;
     int    ratio_n;
 };
@@ -267,14 +279,15 @@ struct Walk
 // the first neighbour of c that continues the sequence, or -1
 int step(const Graph& g, Walk* w, int c)
 {
-    const std::vector<P2>& P = g.pts;
-    const double last_len = hypot((double)w->dlx, (double)w->dly);
+    const double last_len = w->last_len, lx = w->dlx, ly = w->dly;
     for (int k = g.adj_off[c]; k < g.adj_off[c + 1]; k++)
     {
-        const int cand = g.adj[k];
-        const i64 dx = P[cand].x - P[c].x, dy = P[cand].y - P[c].y;
-        const double len = hypot((double)dx, (double)dy);
-        const double cos_err = ((double)w->dlx * (double)dx + (double)w->dly * (double)dy) / (last_len * len);
+        const double dx = g.adj_dx[k], dy = g.adj_dy[k], len = g.adj_len[k];
+        const double dot = lx * dx + ly * dy, prod = last_len * len;
+        // far below the threshold: no need for the division (it is made whenever the outcome could be close;
+        // prod == 0 gives the reference's NaN, which passes its test)
+        if (prod > 0.0 && dot < 0.98 * prod) continue;
+        const double cos_err = dot / prod;
         if (cos_err < kMinCos) continue;
         const double ratio = len / last_len;
         if (ratio < kMinRatio || ratio > kMaxRatio) continue;
@@ -285,8 +298,8 @@ int step(const Graph& g, Walk* w, int c)
         }
         w->ratio_sum += ratio;
         w->ratio_n++;
-        w->dlx = dx; w->dly = dy;
-        return cand;
+        w->dlx = dx; w->dly = dy; w->last_len = len;
+        return g.adj[k];
     }
     return -1;
 }
@@ -301,7 +314,8 @@ struct Sequence
 void sequence_cells(const Graph& g, const Sequence& s, int gridn, int* cells)
 {
     cells[0] = s.c0; cells[1] = s.c1;
-    Walk w = { g.pts[s.c1].x - g.pts[s.c0].x, g.pts[s.c1].y - g.pts[s.c0].y, 0.0, 0 };
+    Walk w = { (double)(g.pts[s.c1].x - g.pts[s.c0].x), (double)(g.pts[s.c1].y - g.pts[s.c0].y), 0.0, 0.0, 0 };
+    w.last_len = hypot(w.dlx, w.dly);
     int c = s.c1;
     for (int i = 0; i < gridn - 2; i++) { c = step(g, &w, c); cells[2 + i] = c; }
 }
@@ -458,14 +472,14 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
         for (int k = g.adj_off[c]; k < g.adj_off[c + 1]; k++)
         {
             const int c1 = g.adj[k];
-            Walk w = { g.pts[c1].x - g.pts[c].x, g.pts[c1].y - g.pts[c].y, 0.0, 0 };
-            double mx = (double)w.dlx, my = (double)w.dly;
+            Walk w = { g.adj_dx[k], g.adj_dy[k], g.adj_len[k], 0.0, 0 };
+            double mx = w.dlx, my = w.dly;
             int cur = c1, clast = -1;
             for (int i = 0; i < gridn - 2; i++)
             {
                 cur = step(g, &w, cur);
                 if (cur < 0) { clast = -1; break; }
-                mx += (double)w.dlx; my += (double)w.dly;
+                mx += w.dlx; my += w.dly;
                 clast = cur;
             }
             if (clast < 0) continue;

@@ -120,11 +120,26 @@ def test_grid_failures_agree_with_oracle():
     assert api.find_grid_from_points(pts, 9) is None and go.find_grid_from_points(pts, 9) is None
 
 
+def test_vnlog_records():
+    # mrgingham-from-image.cc:174-187
+    assert api.format_vnlog("a.png", None, 0) == "a.png - - -\n"
+    got = api.format_vnlog("a.png", [[1.5, 2.25], [100.0, 7.0]], [0, 2])
+    assert got == "a.png 1.500000 2.250000 0\na.png 100.000000 7.000000 2\n"
+    assert api.format_vnlog("b", [[1, 2]], 3) == "b 1.000000 2.000000 3\n"
+    assert api.VNLOG_LEGEND == "# filename x y level"
+
+
+_grid_cache = {}
+
+
 def oracle_board(img, gridn, level, refine=True):
     """mrgingham.cc:36-140 from the oracles: returns (level found, xy, levels) or (-1, None, None)"""
     for L in ([3, 2, 1, 0] if level < 0 else [level]):
-        pts = po.find_corners(img, L)
-        grid = go.find_grid_from_points(pts, gridn) if len(pts) else None
+        key = (img.tobytes(), gridn, L)
+        if key not in _grid_cache:
+            pts = po.find_corners(img, L)
+            _grid_cache[key] = go.find_grid_from_points(pts, gridn) if len(pts) else None
+        grid = _grid_cache[key]
         if grid is None:
             continue
         lv = np.full(len(grid), L, np.int8)
