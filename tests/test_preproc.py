@@ -15,6 +15,8 @@ def _images():
     yield synth.blurred_noise_frame(200, 160, seed=4)
     yield (synth.blob_frame(256, 192, seed=5) // 3 + 40).astype(np.uint8)   # narrow dynamic range
     yield np.full((64, 64), 77, np.uint8)                               # constant: normalises to zero
+    yield synth.blurred_noise_frame(2100, 130, seed=6)                  # several 1024-pixel patches, 17-row tiles
+    yield synth.board_frame(1283, 1030, 10, seed=7)
     for (w, h) in ((8, 8), (9, 17), (16, 9), (33, 65), (640, 480)):
         yield rng.integers(0, 256, (h, w)).astype(np.uint8)
 

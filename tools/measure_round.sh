@@ -28,5 +28,8 @@ ncu --set full --clock-control none --import-source on -k regex:cluster_find -s 
 python tools/bench_levels.py > $O/${R}_levels_4k_n14.jsonl 2>> $O/${R}_bench_n1.err
 python tools/sweep_resolutions.py > $O/${R}_cfg5_sweep.jsonl 2>> $O/${R}_bench_n1.err
 python tools/bench_dense.py > $O/${R}_dense_4k.txt 2>> $O/${R}_bench_n1.err
+python tools/bench_preproc.py > $O/${R}_preproc_4k.txt 2>> $O/${R}_bench_n1.err
+python tools/bench_boards.py > $O/${R}_boards_4k.jsonl 2>> $O/${R}_bench_n1.err
+python tools/bench_boards.py --gridn 10 --level 0 >> $O/${R}_boards_4k.jsonl 2>> $O/${R}_bench_n1.err
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $O/${R}_gpu.txt
 ls -la $O | tail -20

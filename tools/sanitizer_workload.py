@@ -30,3 +30,9 @@ for i in range(2):
     w = po.find_corners(po.box_blur(frames[i], 1), 0)
     assert c3[i] == len(w) and np.array_equal(xy[i, :c3[i]], w)
 print("sanitizer workload ok", c, bc, c3)
+# the --clahe chain (both apply kernels: tall and short tiles, aligned and odd widths) and whole boards
+for img in (frames[0], synth.board_frame(403, 351, 10, seed=5), synth.noise_frame(131, 77, seed=6)):
+    assert np.array_equal(det.preprocess(img[None], clahe=True, blur_radius=0)[0], po.normalize_clahe(img))
+found, bxy, blv = det.find_boards(frames, gridn=10, level=-1)
+assert found[0] >= 0 and found[1] < 0
+print("preproc + boards ok", found)
