@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY. CPU restatement of the reference's grid finder, find_grid.cc:1216-1445
 (mrgingham::find_grid_from_points), for checking the library's host-side grid finder.
 
-PARITY UNPINNED: the reference takes its neighbour graph from Boost.Polygon's voronoi_diagram
-(find_grid.cc:7,1226-1227), which is not in this image, so the reference's grid finder cannot be built or
-run here and it ships no golden vectors for it. What is restated exactly is everything the reference
-itself computes on top of that graph (the neighbour walk, find_grid.cc:86-140; the sequence search,
+PARITY: pinned by tests/test_grid_vs_ref.py against the reference's own find_grid.cc, compiled unmodified
+over a stand-in for Boost.Polygon's voronoi_diagram (oracle/shim/boost/polygon/voronoi.hpp; Boost itself is
+not in this image and the reference ships no golden vectors for the grid finder), so what stays MODELLED
+is only the neighbour graph Boost would hand over -- the conventions listed below, which the stand-in
+shares. What is restated exactly is everything the reference itself computes on top of that graph (the neighbour walk, find_grid.cc:86-140; the sequence search,
 :207-343; the outer-edge cycles, :776-1013; the orientation logic, :1015-1187; the row fill, :1385-1439).
 What stands in for Boost here:
   * Two sites are neighbours iff their Voronoi cells share an edge of non-zero length. This module decides

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY: ctypes handles onto the CPU oracle (oracle/libmrg_oracle.so, the
 restatement in mrg_oracle.c) and, where it was built, onto the unmodified reference hot path
-(oracle/_ref/libmrgingham_ref.so, see oracle/Makefile).
+(oracle/_ref/libmrgingham_ref.so, see oracle/Makefile) and the unmodified reference grid finder / board
+pipeline (oracle/_ref/libmrgingham_ref_grid.so: find_grid.cc + mrgingham.cc over a Boost.Polygon voronoi stand-in).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may import this module.
 Nothing under mrgingham_b200/ does.
@@ -14,6 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(_HERE, "libmrg_oracle.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libmrgingham_ref.so")
+_REF_GRID_SO = os.path.join(_HERE, "_ref", "libmrgingham_ref_grid.so")
 
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _i16p = ctypes.POINTER(ctypes.c_int16)
@@ -26,7 +28,7 @@ def build(ref=True):
     """compile the oracle (always) and the reference build (only where /root/reference exists)"""
     subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
     if ref and os.path.isdir("/root/reference"):
-        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", _HERE, "ref", "refgrid"], check=True)
 
 
 def _ptr(a, t):
@@ -242,3 +244,62 @@ def ref_shim_resize(image, level):
     ref_lib().ref_shim_resize(_ptr(image, _u8p), h, w, image.strides[0], level, _ptr(out, _u8p),
                               ctypes.byref(oh), ctypes.byref(ow))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's grid finder and board pipeline (oracle/_ref/libmrgingham_ref_grid.so): find_grid.cc and
+# mrgingham.cc, unmodified, over the Voronoi stand-in oracle/shim/boost/polygon/voronoi.hpp
+# ---------------------------------------------------------------------------------------------
+_ref_grid = None
+
+
+def have_ref_grid():
+    return os.path.exists(_REF_GRID_SO)
+
+
+def ref_grid_lib():
+    global _ref_grid
+    if _ref_grid is None:
+        _ref_grid = ctypes.CDLL(_REF_GRID_SO)
+        _ref_grid.ref_find_grid_from_points.restype = ctypes.c_int
+        _ref_grid.ref_find_chessboard_from_image_array.restype = ctypes.c_int
+        _ref_grid.ref_shim_voronoi_rings.restype = ctypes.c_int
+    return _ref_grid
+
+
+def ref_find_grid_from_points(points, gridn):
+    """mrgingham::find_grid_from_points (find_grid.cc:1216). points: int32 [n,2] scaled by 1000.
+    Returns float64 [gridn*gridn, 2] or None."""
+    pts = np.ascontiguousarray(np.asarray(points).reshape(-1, 2), dtype=np.int32)
+    out = np.empty((gridn * gridn, 2), dtype=np.float64)
+    r = ref_grid_lib().ref_find_grid_from_points(_ptr(pts, _i32p), len(pts), gridn, _ptr(out, _f64p))
+    assert r in (0, 1)
+    return out if r == 1 else None
+
+
+def ref_find_chessboard(image, gridn, level=-1, refine=True):
+    """mrgingham::find_chessboard_from_image_array (mrgingham.cc:106). Returns (level found at or -1, points or
+    None, per-point refinement levels or None)."""
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.empty((gridn * gridn, 2), dtype=np.float64)
+    lv = np.empty(gridn * gridn, dtype=np.int8)
+    r = ref_grid_lib().ref_find_chessboard_from_image_array(_ptr(image, _u8p), h, w, image.strides[0], gridn, level,
+                                                            1 if refine else 0, _ptr(out, _f64p), _ptr(lv, _i8p))
+    assert r >= -1
+    return (r, out, lv) if r >= 0 else (-1, None, None)
+
+
+def ref_shim_voronoi_rings(points):
+    """the stand-in's diagram: list of (source index, [neighbour source indices in next() order]) per cell, in
+    cell creation order"""
+    pts = np.ascontiguousarray(np.asarray(points).reshape(-1, 2), dtype=np.int32)
+    n = ref_grid_lib().ref_shim_voronoi_rings(_ptr(pts, _i32p), len(pts), None, 0)
+    buf = np.empty(n, dtype=np.int32)
+    ref_grid_lib().ref_shim_voronoi_rings(_ptr(pts, _i32p), len(pts), _ptr(buf, _i32p), n)
+    cells, at = [], 1
+    for _ in range(int(buf[0])):
+        src, k = int(buf[at]), int(buf[at + 1])
+        cells.append((src, [int(v) for v in buf[at + 2:at + 2 + k]]))
+        at += 2 + k
+    return cells

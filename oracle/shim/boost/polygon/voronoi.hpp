@@ -29,6 +29,8 @@
 #pragma once
 
 #include <stddef.h>
+#include <math.h>      // the real header pulls <cmath> in; find_grid.cc relies on that for hypot/atan2/fabs/M_PI
+#include <cmath>
 #include <algorithm>
 #include <iterator>
 #include <vector>

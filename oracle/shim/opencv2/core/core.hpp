@@ -9,6 +9,7 @@
 // pins bit-for-bit against cv2 4.13.0 (the in-container OpenCV).
 #pragma once
 
+#include <assert.h>     // the real OpenCV headers pull it in; mrgingham.cc:83 relies on that
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>

@@ -1,7 +1,7 @@
 """Grid finder and whole-board entry points (find_grid.cc:1216-1445, mrgingham.cc:10-140).
 
-PARITY UNPINNED for the grid finder: the reference's needs Boost.Polygon, which this image lacks, and the
-reference ships no golden vectors for it. What is checked instead:
+The comparison with the reference's own compiled find_grid.cc / mrgingham.cc (over a Boost.Polygon voronoi stand-in)
+lives in tests/test_grid_vs_ref.py. This file checks the pieces that do not need the reference build:
   * the library's neighbour graph (its own exact Delaunay triangulation) against the oracle's, which decides
     Voronoi adjacency from the definition, including degenerate inputs (lattices, cocircular, collinear,
     repeated points);

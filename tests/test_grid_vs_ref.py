@@ -1,0 +1,152 @@
+"""The grid finder and the whole-board pipeline against the REFERENCE'S OWN CODE: find_grid.cc and mrgingham.cc,
+unmodified, compiled by oracle/Makefile (target `refgrid`) into oracle/_ref/libmrgingham_ref_grid.so over the
+cv::Mat shim and a stand-in for the one thing this image lacks, Boost.Polygon's voronoi_diagram
+(oracle/shim/boost/polygon/voronoi.hpp; it decides Voronoi adjacency from the definition and fixes the same three
+conventions DESIGN.md 5d states: cells in sorted-site order, rings counter-clockwise, first edge from +x).
+
+So everything the reference computes ABOVE the neighbour graph -- the neighbour walk, the sequence search and its
+thresholds, outer-edge cycles, orientation, row fill, the 3,2,1,0 level loop and the refinement loop -- is pinned
+to the reference's compiled code; only Boost's own incident_edge() choice stays modelled.
+
+Skipped where the reference build is absent (it needs /root/reference at build time; the built .so travels to
+the GPU box)."""
+import numpy as np
+import pytest
+
+from mrgingham_b200 import api, synth
+from oracle import grid_oracle as go
+from oracle import pyoracle as po
+
+from test_grid import board_points, same
+
+pytestmark = pytest.mark.skipif(not po.have_ref_grid(), reason="oracle/_ref/libmrgingham_ref_grid.so not built (needs /root/reference)")
+
+
+def _point_sets():
+    rng = np.random.default_rng(7)
+    for t in range(36):
+        n = int(rng.integers(1, 70))
+        kind = t % 6
+        if kind == 0:
+            pts = rng.integers(0, 4000000, (n, 2))
+        elif kind == 1:
+            pts = rng.integers(0, 6, (n, 2))                                   # repeated, collinear and cocircular points
+        elif kind == 2:
+            pts = np.array([[i * 1000, j * 1000] for i in range(6) for j in range(5)])           # a perfect lattice
+        elif kind == 3:
+            pts = np.array([[i * 300 + j * 400, -i * 400 + j * 300] for i in range(5) for j in range(5)])   # rotated lattice
+        elif kind == 4:
+            pts = np.c_[np.arange(n) * 7, np.arange(n) * 3]                      # every point on one line
+        else:
+            pts = rng.integers(0, 40, (n, 2)) * np.array([1, 1000])
+        yield pts[rng.permutation(len(pts))].astype(np.int32)
+    ring = [(3, 4), (4, 3), (5, 0), (0, 5), (-3, 4), (-4, 3), (-5, 0), (0, -5), (3, -4), (4, -3), (-3, -4), (-4, -3)]
+    yield (np.array(ring + [(0, 0)]) * 1000).astype(np.int32)
+    yield (np.array(ring) * 1000).astype(np.int32)
+
+
+def test_voronoi_standin_matches_the_definition_oracle_and_the_library():
+    """three independent constructions of the same graph: the stand-in under the reference (C++, bisector
+    intervals in 128-bit integers), the Python definition oracle, the library's Delaunay triangulation"""
+    for pts in _point_sets():
+        g = go._Graph(pts)
+        cells = po.ref_shim_voronoi_rings(pts)
+        assert [c[0] for c in cells] == g.sites, pts.tolist()
+        lib = api.voronoi_neighbours(pts)
+        for src, ring in cells:
+            assert ring == g.ring[src], (pts.tolist(), src)
+            assert ring == lib[src], (pts.tolist(), src)
+
+
+def test_grid_equals_reference_on_boards():
+    for seed in range(40):
+        gridn = (10, 14, 6, 4, 8)[seed % 5]
+        pts, truth = board_points(gridn, 1920, 1080, seed, extras=(seed % 3) * 5)
+        want = po.ref_find_grid_from_points(pts, gridn)
+        got = api.find_grid_from_points(pts, gridn)
+        assert want is not None and np.array_equal(want, truth), seed
+        assert same(got, want), seed
+
+
+def test_grid_equals_reference_under_strong_perspective():
+    n_found = 0
+    for seed in range(40):
+        gridn = (8, 10, 6)[seed % 3]
+        pts, _ = board_points(gridn, 1280, 960, 300 + seed, rot=0.7, persp=0.4, noise=0.3, extras=(seed % 4) * 3)
+        want = po.ref_find_grid_from_points(pts, gridn)
+        assert same(api.find_grid_from_points(pts, gridn), want), seed
+        n_found += want is not None
+    assert 10 <= n_found
+
+
+def test_grid_equals_reference_on_failures_and_degenerate_input():
+    rng = np.random.default_rng(11)
+    pts, _ = board_points(10, 1920, 1080, 1)
+    cases = [(pts[:50], 10), (np.delete(pts, 17, axis=0), 10), (np.r_[pts, pts[:5]], 10),
+             (rng.integers(0, 1000000, (80, 2)).astype(np.int32), 10),
+             (pts[:1], 10), (pts[:2], 10), (pts[:3], 10), (pts, 9), (pts, 11), (pts, 2), (pts, 3),
+             (np.array([[i * 50000 + 100000, j * 50000 + 100000] for i in range(10) for j in range(10)], np.int32), 10),
+             (np.array([[i * 50000 + 100000, j * 50000 + 100000] for i in range(12) for j in range(12)], np.int32), 10),
+             (np.r_[board_points(6, 900, 900, 5)[0], board_points(6, 900, 900, 6)[0] + np.array([1000000, 0], np.int32)], 6)]
+    for s in range(12):                                   # boards with random corners knocked out / jittered
+        p, _ = board_points(10, 1920, 1080, 50 + s, extras=4)
+        p = p.copy()
+        if s % 2:
+            p = np.delete(p, rng.integers(0, len(p), 1 + s % 3), axis=0)
+        else:
+            k = rng.integers(0, len(p), 2)
+            p[k] += rng.integers(-9000, 9000, (2, 2)).astype(np.int32)
+        cases.append((p, 10))
+    for k, (c, gridn) in enumerate(cases):
+        assert same(api.find_grid_from_points(c, gridn), po.ref_find_grid_from_points(c, gridn)), k
+
+
+def test_grid_oracle_restatement_equals_reference():
+    """the Python restatement (used by the GPU tests' oracle pipeline and by smoke()) is itself pinned here"""
+    for seed in range(6):
+        gridn = (10, 6, 4)[seed % 3]
+        pts, _ = board_points(gridn, 1920, 1080, 500 + seed, extras=5)
+        assert same(go.find_grid_from_points(pts, gridn), po.ref_find_grid_from_points(pts, gridn)), seed
+    pts, _ = board_points(8, 1280, 960, 301, rot=0.7, persp=0.4, noise=0.3)
+    assert same(go.find_grid_from_points(pts, 8), po.ref_find_grid_from_points(pts, 8))
+    pts, _ = board_points(10, 1920, 1080, 1)
+    assert same(go.find_grid_from_points(pts[:50], 10), po.ref_find_grid_from_points(pts[:50], 10))
+
+
+@pytest.mark.gpu
+def test_boards_equal_reference_pipeline():
+    """corners -> grid -> refinement, auto level and fixed levels, against mrgingham::find_chessboard_from_image_array
+    itself (mrgingham.cc:106-140) running the reference's detector, grid finder and refinement loop"""
+    api._require_gpu()
+    frames = [(1280, 960, 10, 1, 2.0), (1920, 1080, 14, 2, 2.0), (800, 608, 10, 3, 2.0), (640, 480, 6, 4, 2.0),
+              (1024, 768, 10, 3, 12.0), (3840, 2160, 14, 7, 2.0)]
+    for (w, h, gridn, seed, sigma) in frames:
+        img = synth.board_frame(w, h, gridn, seed=seed, noise_sigma=sigma)
+        for level in ((-1, 0, 1, 2) if w < 3000 else (-1,)):
+            for refine in (True, False):
+                L, xy, lv = po.ref_find_chessboard(img, gridn, level, refine)
+                Lg, xyg, lvg = api.find_chessboard_from_image_array(img, gridn, level, refine=refine)
+                assert Lg == L, (w, h, level, refine)
+                if L >= 0:
+                    assert np.array_equal(xyg, xy), (w, h, level, refine)
+                    if refine:
+                        assert np.array_equal(lvg, lv), (w, h, level, refine)
+    for img in (synth.noise_frame(320, 240, seed=1), np.full((200, 300), 128, np.uint8)):
+        assert po.ref_find_chessboard(img, 10)[0] == -1 and api.find_board(img) is None
+
+
+@pytest.mark.gpu
+def test_board_batch_equals_reference_pipeline():
+    api._require_gpu()
+    frames = [synth.board_frame(1024, 768, 10, seed=s) for s in range(4)]
+    frames[1] = synth.noise_frame(1024, 768, seed=9)
+    raw = np.stack(frames)
+    det = api.Detector(max_frames=3)
+    for level in (-1, 2):
+        found, xy, lv = det.find_boards(raw, gridn=10, level=level)
+        for i, f in enumerate(raw):
+            L, wxy, wlv = po.ref_find_chessboard(f, 10, level, True)
+            assert found[i] == L, (level, i)
+            if L >= 0:
+                assert np.array_equal(xy[i], wxy) and np.array_equal(lv[i], wlv), (level, i)
+    det.close()
