@@ -29,6 +29,9 @@ def build(ref=True):
     subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
     if ref and os.path.isdir("/root/reference"):
         subprocess.run(["make", "-s", "-C", _HERE, "ref", "refgrid"], check=True)
+        # the reference's own Python module linked against the product library (drop-in demonstration for the tests)
+        if os.path.exists(os.path.join(os.path.dirname(_HERE), "mrgingham_b200", "libmrgingham_b200.so")):
+            subprocess.run(["make", "-s", "-C", _HERE, "pymodule"], check=True)
 
 
 def _ptr(a, t):
