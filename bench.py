@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--gridn", type=int, default=10)
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--base-frames", type=int, default=8, help="distinct synthetic frames, tiled to --frames")
-    ap.add_argument("--chunk", type=int, default=512, help="frames per kernel launch")
+    ap.add_argument("--chunk", type=int, default=2048, help="frames per kernel launch (at least two launches per rank are made)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -286,7 +286,7 @@ def run_ours(a):
     # ---- e2e: host (pinned) frames through the C ABI, H2D + D2H inside the timed region
     e2e = None
     if not a.no_e2e:
-        pool_n = min(nloc, chunk)
+        pool_n = min(nloc, chunk, 512)     # 4.2 GB of pinned host memory per call
         pool = torch.empty((pool_n, H, W), dtype=torch.uint8).pin_memory()
         for i in range(pool_n):
             pool[i].copy_(torch.from_numpy(base[(lo + i) % K]))

@@ -417,7 +417,9 @@ API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detecto
     bool ok = cudaSetDevice(det->device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&det->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               // clustering runs at high priority so its few CTAs slot in as ChESS CTAs retire
-              cudaStreamCreateWithPriority(&det->aux_stream, cudaStreamNonBlocking, -1) == cudaSuccess &&
+              // (MRG_B200_K2_PRIORITY=0: A/B knob, default priority -- they then wait for the ChESS grid's tail)
+              cudaStreamCreateWithPriority(&det->aux_stream, cudaStreamNonBlocking,
+                                           (getenv("MRG_B200_K2_PRIORITY") && atoi(getenv("MRG_B200_K2_PRIORITY")) == 0) ? 0 : -1) == cudaSuccess &&
               cudaStreamCreateWithFlags(&det->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&det->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int b = 0; b < 2 && ok; b++)
