@@ -149,6 +149,9 @@ struct Launch
     }
 };
 
+// batch launch sizes: see enqueue_locked()
+constexpr int kTaperMinFrames = 128;
+
 int chess_sparse(mrg_b200_detector* det, const FrameSet& fs, cand_t* cand, uint32_t* counts, int cap, cudaStream_t stream)
 {
     Launch l(det, 0, stream);
@@ -308,8 +311,24 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
     // K2(c) with K1(c+1)); default: its own high-priority stream
     static const bool k2_on_main = [] { const char* e = getenv("MRG_B200_K2_STREAM"); return e && !strcmp(e, "main"); }();
     cudaStream_t aux = k2_on_main ? stream : det->aux_stream, cpy = det->copy_stream;
+    // Launch sizes. For HOST frames the kernels of the last chunk run after its copy with nothing left to overlap,
+    // so the last max_frames of a batch go up in halves down to 128 frames (512 frames: 256, 128, 128): the
+    // exposed tail is one short copy-less launch pair instead of a full one (+1.8 % end to end on 4K frames).
+    // Device-resident batches keep full-size launches: the ChESS kernel loses more on short launches than the
+    // shorter tail wins (measured 1.97 against 2.01 Tpix/s). MRG_B200_TAPER=0/1 forces it off/on for both.
+    static const int taper_env = [] { const char* e = getenv("MRG_B200_TAPER"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool taper = taper_env < 0 ? !on_device : taper_env != 0;
+    std::vector<int> sizes;
+    for (int left = nframes; left > 0; )
+    {
+        int n = std::min(chunk, left);
+        if (taper && left <= chunk && left >= 2 * kTaperMinFrames)
+            n = std::min(left, std::max(kTaperMinFrames, ((left / 2 + 63) / 64) * 64));
+        sizes.push_back(n);
+        left -= n;
+    }
     // size both slots before anything is in flight (growing a buffer frees it)
-    for (int b = 0; b < 2 && b * chunk < nframes; b++)
+    for (int b = 0; b < 2 && b < (int)sizes.size(); b++)
     {
         mrg_b200_detector::Slot& S = det->slot[b];
         const int n = std::min(chunk, nframes);
@@ -321,10 +340,10 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
     CUDA_TRY(cudaEventRecord(det->ev_fork, stream));
     CUDA_TRY(cudaStreamWaitEvent(aux, det->ev_fork, 0));
     CUDA_TRY(cudaStreamWaitEvent(cpy, det->ev_fork, 0));
-    int c = 0;
-    for (int f0 = 0; f0 < nframes; f0 += chunk, c++)
+    int f0 = 0;
+    for (int c = 0; c < (int)sizes.size(); f0 += sizes[c], c++)
     {
-        const int n = std::min(chunk, nframes - f0);
+        const int n = sizes[c];
         mrg_b200_detector::Slot& S = det->slot[c & 1];
         if (S.used)
         {
