@@ -9,9 +9,10 @@
 //     (Voronoi edges of zero length, which Boost removes too), are the Voronoi edges;
 //   * per cell, the neighbouring cells in counter-clockwise order in (x,y) (find_grid.cc:40-41: clockwise as
 //     seen in an image), cells visited in sorted-site order as Boost creates them.
-// PARITY UNPINNED for this row: Boost is not in this image, so the reference's grid finder cannot be run
-// here. The one thing this construction does not reproduce is which edge Boost starts a cell's walk at; it
-// matters only when several neighbours pass the reference's "first match wins" test (find_grid.cc:216-221).
+// Parity: Boost is not in this image; tests/test_grid_vs_ref.py compares this file with the reference's own
+// find_grid.cc compiled over a stand-in for Boost's voronoi_diagram that fixes the same conventions. The one
+// thing that stays modelled is which edge Boost starts a cell's walk at; it matters only when several
+// neighbours pass the reference's "first match wins" test (find_grid.cc:216-221).
 // Everything on top of the graph follows the reference's arithmetic (doubles, the float32 crossing test,
 // the truncating integer divisions).
 #include <algorithm>
