@@ -31,7 +31,7 @@ def build(ref=True):
         subprocess.run(["make", "-s", "-C", _HERE, "ref", "refgrid"], check=True)
         # the reference's own Python module linked against the product library (drop-in demonstration for the tests)
         if os.path.exists(os.path.join(os.path.dirname(_HERE), "mrgingham_b200", "libmrgingham_b200.so")):
-            subprocess.run(["make", "-s", "-C", _HERE, "pymodule"], check=True)
+            subprocess.run(["make", "-s", "-C", _HERE, "pymodule", "hybrid"], check=True)
 
 
 def _ptr(a, t):
@@ -306,3 +306,33 @@ def ref_shim_voronoi_rings(points):
         cells.append((src, [int(v) for v in buf[at + 2:at + 2 + k]]))
         at += 2 + k
     return cells
+
+
+# ---------------------------------------------------------------------------------------------
+# the hybrid build (oracle/_ref/libmrgingham_hybrid.so): the reference's mrgingham.cc + find_grid.cc compiled
+# against THIS repo's adapter headers and linked with the product library -- the reference's orchestration
+# running on the CUDA detector. Same extern "C" handles as the reference grid build.
+# ---------------------------------------------------------------------------------------------
+_HYBRID_SO = os.path.join(_HERE, "_ref", "libmrgingham_hybrid.so")
+_hybrid = None
+
+
+def have_hybrid():
+    return os.path.exists(_HYBRID_SO)
+
+
+def hybrid_find_chessboard(image, gridn, level=-1, refine=True):
+    """mrgingham::find_chessboard_from_image_array of the reference's mrgingham.cc, with the corner detector and the
+    refinement coming from libmrgingham_b200.so through the cv::Mat adapter overloads. Needs a GPU."""
+    global _hybrid
+    if _hybrid is None:
+        _hybrid = ctypes.CDLL(_HYBRID_SO)
+        _hybrid.ref_find_chessboard_from_image_array.restype = ctypes.c_int
+    image = _check_image(image)
+    h, w = image.shape
+    out = np.empty((gridn * gridn, 2), dtype=np.float64)
+    lv = np.empty(gridn * gridn, dtype=np.int8)
+    r = _hybrid.ref_find_chessboard_from_image_array(_ptr(image, _u8p), h, w, image.strides[0], gridn, level,
+                                                     1 if refine else 0, _ptr(out, _f64p), _ptr(lv, _i8p))
+    assert r >= -1
+    return (r, out, lv) if r >= 0 else (-1, None, None)

@@ -34,6 +34,8 @@ namespace boost { namespace polygon {
 
 // mrgingham.cc references the blob detector (find_blobs.cc wraps cv::SimpleBlobDetector, which cannot be
 // built here); these stand-ins only satisfy the linker and are never reached by the calls below.
+// (Not in the `hybrid` build of oracle/Makefile: there find_blobs.hh is this repo's adapter header.)
+#ifndef REF_CAPI_HYBRID
 namespace mrgingham
 {
     bool find_blobs_from_image_array(std::vector<PointInt>*, const cv::Mat&, bool)
@@ -47,6 +49,7 @@ namespace mrgingham
         return false;
     }
 }
+#endif
 
 // points: n x (x, y) ints scaled by 1000 (PointInt). out: gridn*gridn x (x, y) doubles. Returns 1 if a grid was found.
 API int ref_find_grid_from_points(const int* xy, int n, int gridn, double* out)

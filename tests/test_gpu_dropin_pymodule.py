@@ -82,3 +82,21 @@ def test_reference_module_on_the_cuda_path_equals_reference_cpu():
     assert pts.shape == ref.shape and np.array_equal(pts, ref)
     with pytest.raises(Exception):
         m.find_points(dots, image_pyramid_level=1, blobs=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not po.have_hybrid(), reason="oracle/_ref/libmrgingham_hybrid.so not built (needs /root/reference)")
+def test_reference_orchestrator_on_the_cuda_detector_equals_reference_cpu():
+    """Source-level drop-in, executed: the reference's mrgingham.cc and find_grid.cc compiled against this repo's
+    find_chessboard_corners.hh / find_blobs.hh (cv::Mat overloads) and linked with the product library
+    (`make -C oracle hybrid`) against the all-reference build, image by image."""
+    api._require_gpu()
+    for (w, h, gridn, seed) in ((1280, 960, 10, 1), (800, 608, 10, 3), (1920, 1080, 14, 2)):
+        img = synth.board_frame(w, h, gridn, seed=seed)
+        for level, refine in ((-1, True), (1, True), (0, False)):
+            L, xy, lv = po.ref_find_chessboard(img, gridn, level, refine)
+            Lh, xyh, lvh = po.hybrid_find_chessboard(img, gridn, level, refine)
+            assert Lh == L, (w, level)
+            if L >= 0:
+                assert np.array_equal(xyh, xy) and (not refine or np.array_equal(lvh, lv)), (w, level)
+    assert po.hybrid_find_chessboard(synth.noise_frame(320, 240, seed=1), 10)[0] == -1
