@@ -69,6 +69,11 @@ struct Graph
     // the walk of find_grid.cc:86-140 precomputed: each edge-neighbour followed by the in-between cell, if any
     std::vector<int> adj_off, adj;
     std::vector<double> adj_dx, adj_dy, adj_len;   // the step to each of them and its hypot()
+    // Per step (entry of adj: a -> b), the steps out of b that may follow it in a sequence: those that pass the
+    // direction and length-ratio tests of find_grid.cc:247-284, which depend on the two steps only. In adj order
+    // ("first match wins", find_grid.cc:216-221), with the length ratio each one contributes.
+    std::vector<int> cont_off, cont;
+    std::vector<double> cont_ratio;
 
     int ring_pos(int a, int b) const
     {
@@ -269,29 +274,51 @@ bool build_graph(Graph* g, const int* xy, int n)
 }
 
 // ---- sequences (find_grid.cc:160-343) ----
+// The walk's tests on direction (cos of the turn >= 0.984) and length ratio (0.7 .. 1.4) involve only the previous
+// step and the candidate step, both edges of the static graph, so they are evaluated once per pair of consecutive
+// steps here instead of once per visit (every cell starts a walk towards every neighbour: ~50 visits per pair on
+// a 14x14 board); the test against the running mean ratio stays in step().
+void build_continuations(Graph* g)
+{
+    const int n = (int)g->pts.size(), E = (int)g->adj.size();
+    g->cont_off.assign(E + 1, 0);
+    g->cont.clear(); g->cont_ratio.clear();
+    g->cont.reserve(E); g->cont_ratio.reserve(E);
+    for (int a = 0; a < n; a++)
+        for (int e = g->adj_off[a]; e < g->adj_off[a + 1]; e++)
+        {
+            const int b = g->adj[e];
+            const double lx = g->adj_dx[e], ly = g->adj_dy[e], last_len = g->adj_len[e];
+            for (int k = g->adj_off[b]; k < g->adj_off[b + 1]; k++)
+            {
+                const double dx = g->adj_dx[k], dy = g->adj_dy[k], len = g->adj_len[k];
+                const double dot = lx * dx + ly * dy, prod = last_len * len;
+                // far below the threshold: no need for the division (it is made whenever the outcome could be close;
+                // prod == 0 gives the reference's NaN, which passes its test)
+                if (prod > 0.0 && dot < 0.98 * prod) continue;
+                const double cos_err = dot / prod;
+                if (cos_err < kMinCos) continue;
+                const double ratio = len / last_len;
+                if (ratio < kMinRatio || ratio > kMaxRatio) continue;
+                g->cont.push_back(k); g->cont_ratio.push_back(ratio);
+            }
+            g->cont_off[e + 1] = (int)g->cont.size();
+        }
+}
+
 struct Walk
 {
-    double dlx, dly;        // most recent step (integer-valued)
-    double last_len;        // its length
+    int    e;               // most recent step (entry of Graph::adj)
     double ratio_sum;
     int    ratio_n;
 };
 
-// the first neighbour of c that continues the sequence, or -1
-int step(const Graph& g, Walk* w, int c)
+// the first step that continues the sequence after step w->e: its entry (the cell is g.adj[entry]), or -1
+int step(const Graph& g, Walk* w)
 {
-    const double last_len = w->last_len, lx = w->dlx, ly = w->dly;
-    for (int k = g.adj_off[c]; k < g.adj_off[c + 1]; k++)
+    for (int t = g.cont_off[w->e]; t < g.cont_off[w->e + 1]; t++)
     {
-        const double dx = g.adj_dx[k], dy = g.adj_dy[k], len = g.adj_len[k];
-        const double dot = lx * dx + ly * dy, prod = last_len * len;
-        // far below the threshold: no need for the division (it is made whenever the outcome could be close;
-        // prod == 0 gives the reference's NaN, which passes its test)
-        if (prod > 0.0 && dot < 0.98 * prod) continue;
-        const double cos_err = dot / prod;
-        if (cos_err < kMinCos) continue;
-        const double ratio = len / last_len;
-        if (ratio < kMinRatio || ratio > kMaxRatio) continue;
+        const double ratio = g.cont_ratio[t];
         if (w->ratio_n > 2)
         {
             const double dev = ratio - w->ratio_sum / (double)w->ratio_n;
@@ -299,8 +326,8 @@ int step(const Graph& g, Walk* w, int c)
         }
         w->ratio_sum += ratio;
         w->ratio_n++;
-        w->dlx = dx; w->dly = dy; w->last_len = len;
-        return g.adj[k];
+        w->e = g.cont[t];
+        return w->e;
     }
     return -1;
 }
@@ -308,6 +335,7 @@ int step(const Graph& g, Walk* w, int c)
 struct Sequence
 {
     int    c0, c1, clast;
+    int    e0;              // the step c0 -> c1 (entry of Graph::adj)
     double mean_dx, mean_dy;
 };
 
@@ -315,10 +343,8 @@ struct Sequence
 void sequence_cells(const Graph& g, const Sequence& s, int gridn, int* cells)
 {
     cells[0] = s.c0; cells[1] = s.c1;
-    Walk w = { (double)(g.pts[s.c1].x - g.pts[s.c0].x), (double)(g.pts[s.c1].y - g.pts[s.c0].y), 0.0, 0.0, 0 };
-    w.last_len = hypot(w.dlx, w.dly);
-    int c = s.c1;
-    for (int i = 0; i < gridn - 2; i++) { c = step(g, &w, c); cells[2 + i] = c; }
+    Walk w = { s.e0, 0.0, 0 };
+    for (int i = 0; i < gridn - 2; i++) cells[2 + i] = g.adj[step(g, &w)];
 }
 
 // find_grid.cc:776-822 (float32 throughout)
@@ -464,6 +490,7 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
     if (npoints <= 0 || gridn < 2 || !xy || !xy_out) return false;
     Graph g;
     if (!build_graph(&g, xy, npoints)) return false;
+    build_continuations(&g);
     Finder F = { g, gridn, {}, {}, {} };
 
     // every run of gridn cells, from every cell towards every neighbour (find_grid.cc:505-566)
@@ -473,18 +500,18 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
         for (int k = g.adj_off[c]; k < g.adj_off[c + 1]; k++)
         {
             const int c1 = g.adj[k];
-            Walk w = { g.adj_dx[k], g.adj_dy[k], g.adj_len[k], 0.0, 0 };
-            double mx = w.dlx, my = w.dly;
-            int cur = c1, clast = -1;
+            Walk w = { k, 0.0, 0 };
+            double mx = g.adj_dx[k], my = g.adj_dy[k];
+            int clast = -1;
             for (int i = 0; i < gridn - 2; i++)
             {
-                cur = step(g, &w, cur);
-                if (cur < 0) { clast = -1; break; }
-                mx += w.dlx; my += w.dly;
-                clast = cur;
+                const int e = step(g, &w);
+                if (e < 0) { clast = -1; break; }
+                mx += g.adj_dx[e]; my += g.adj_dy[e];
+                clast = g.adj[e];
             }
             if (clast < 0) continue;
-            const Sequence s = { c, c1, clast, mx / (double)(gridn - 1), my / (double)(gridn - 1) };
+            const Sequence s = { c, c1, clast, k, mx / (double)(gridn - 1), my / (double)(gridn - 1) };
             F.seq.push_back(s);
         }
     }
