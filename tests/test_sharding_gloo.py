@@ -74,3 +74,21 @@ def test_two_rank_gloo_shard_and_reduce():
     assert tmax == 11.0
     assert sizes == [32, 32]
     assert np.array_equal(gathered[:, 0], np.arange(nframes))
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: the reference's own CPU code on the host cores, one JSON line with the keys the
+    driver reads (same metric/unit/config as the GPU arm, impl, cpu_baseline, e2e with zero copies)"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--width", "640", "--height", "480", "--base-frames", "2"],
+                         check=True, capture_output=True, text=True, timeout=120).stdout.strip().split("\n")
+    line = json.loads(out[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mpix/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"] and "workload" in line["config"]
