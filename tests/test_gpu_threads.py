@@ -11,7 +11,7 @@ import pytest
 from mrgingham_b200 import api, synth
 from oracle import pyoracle as po
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]      # a deadlock must fail, not hang the run
 
 
 def _run_threads(n_threads, work):
