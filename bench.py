@@ -68,6 +68,12 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.t0 = self.t1 = None
+        # second source, for timed regions shorter than nvidia-smi's sampling period (small shards at 8 GPUs):
+        # NVML polled every 4 ms from a thread of this process
+        self.nvml_rows = []
+        self.nvml_max = None
+        self._nvml_stop = threading.Event()
+        self._nvml_thread = None
 
     def start(self):
         try:
@@ -78,6 +84,41 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+        try:
+            self._nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._nvml_thread.start()
+        except Exception:
+            self._nvml_thread = None
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._nvml_stop.is_set():
+                t = time.time()
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                except Exception:
+                    mask = 0
+                self.nvml_rows.append((t, mhz, mask))
+                time.sleep(0.004)
+        except Exception:
+            pass
+
+    def _nvml_result(self):
+        """clocks over the timed region from the NVML samples, or None if there are none inside it"""
+        if self.t0 is None or self.t1 is None:
+            return None
+        inside = [r for r in list(self.nvml_rows) if self.t0 <= r[0] <= self.t1]
+        if not inside:
+            return None
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        reasons = sorted({name for r in inside for name, bit in bits if r[2] & bit})
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": self.nvml_max, "samples": len(inside),
+                "scope": "timed region (NVML, 4 ms period)", "reasons": reasons}
 
     def _read(self):
         for line in self.proc.stdout:
@@ -91,8 +132,14 @@ class ClockSampler:
 
     def stop(self):
         import datetime
+        self._nvml_stop.set()
+        nvml = None
+        try:
+            nvml = self._nvml_result()
+        except Exception:
+            nvml = None
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return nvml or {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
         self.proc.terminate()
         try:
@@ -111,6 +158,8 @@ class ClockSampler:
                 continue
         inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
         scope = "timed region"
+        if len(inside) < 3 and nvml is not None:
+            return nvml          # the region was shorter than nvidia-smi's period: the NVML samples taken inside it
         if len(inside) < 3:
             inside = [r for r in rows if r[3] >= 50.0]
             scope = "warm-up + timed region (samples under load)"
