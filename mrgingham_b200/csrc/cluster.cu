@@ -352,7 +352,11 @@ cluster_find_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint32
         }
         __syncthreads();
         const int nstart = s_nstart;
-        for (int k = tid; k < nstart && !sequential; k += kClusterThreads)
+        // The floods and replays below diverge lane by lane, so a warp's time grows with the number of its lanes
+        // that have a starter: deal the starters to the warps round-robin (lane l of warp w takes starter
+        // l * nwarps + w, a bijection on 0..kClusterThreads-1) instead of filling warp after warp.
+        constexpr int kWarps = kClusterThreads / 32;
+        for (int k = (tid & 31) * kWarps + (tid >> 5); k < nstart && !sequential; k += kClusterThreads)
         {
             const int i0 = starters[k];
             const uint32_t key = cand_key(scand[i0]);
