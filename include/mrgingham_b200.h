@@ -17,7 +17,9 @@
 
   Conventions (same as the reference): 8-bit single-channel images, rows
   contiguous, `stride` in bytes; the caller owns every buffer; no exceptions cross this ABI;
-  diagnostics go to stderr as "file:line in func(): ... Sorry.". All functions are thread-safe.
+  diagnostics go to stderr as "file:line in func(): ... Sorry.". All functions are thread-safe, and none
+  changes the calling thread's current CUDA device. The one-image calls (sections A and B) run on the calling
+  thread's current device, each on a detector borrowed from a per-device pool, so concurrent callers overlap.
 */
 #ifndef MRGINGHAM_B200_H
 #define MRGINGHAM_B200_H
@@ -37,7 +39,9 @@ extern "C" {
 /* Replaces ChESS.c:55-106 (declared in ChESS.h:31-34).
    response: dense int16 [h][w] HOST buffer; image: uint8 HOST buffer with row pitch `stride`.
    Writes 7 <= x < w-7, 7 <= y < h-7 only; every other element of `response` is left untouched,
-   exactly as the reference does. */
+   exactly as the reference does. The signature has no way to report a failure: if the GPU path fails (no
+   device, CUDA error) a diagnostic goes to stderr and `response` is not (or only partly) written; the host
+   process is never aborted. */
 void mrgingham_ChESS_response_5(int16_t*       response,
                                 const uint8_t* image,
                                 int w, int h, int stride);
@@ -46,7 +50,8 @@ void mrgingham_ChESS_response_5(int16_t*       response,
    mrgingham_pywrap_cplusplus_bridge.h:10-23): the C bridge the reference's Python module binds.
    Returns false when nothing was found or on error (doblobs with a level other than 0 is one:
    ...bridge.cc:50-56); otherwise calls add_points(xy, N, 1/1000., cookie) once and returns its
-   result. doblobs selects the blob detector (find_blobs.cc:14-46) instead of the corner detector. */
+   result. A failure of the GPU path is NOT "nothing found": add_points(xy, 0, ...) is called and false
+   returned, which the reference's Python wrapper turns into RuntimeError (mrgingham_pywrap.c:203-219). doblobs selects the blob detector (find_blobs.cc:14-46) instead of the corner detector. */
 bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols,
                                                 int stride,
                                                 char* imagebuffer, /* const */
@@ -118,12 +123,14 @@ int mrg_b200_voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* 
    in turn until one yields a grid. refine != 0 (the reference: refinement_level != NULL): the grid's points
    are then refined level by level down to 0 (mrgingham.cc:81-99); levels_out (may be NULL) receives the level
    each point ended at. xy_out: gridn*gridn (x,y) doubles in full-resolution pixels.
-   Returns the level the grid was found at, or <0 (not found, or error). */
+   Returns the level the grid was found at, -1 if no grid was found (or on the reference's own error paths), -2 if
+   the GPU path failed (CUDA error, no device) -- a failure is never reported as "not found". */
 int mrg_b200_find_chessboard_from_image_array(const uint8_t* image, int Nrows, int Ncols, int stride,
                                               int gridn, int image_pyramid_level, int refine,
                                               double* xy_out, signed char* levels_out);
 
-/* mrgingham::find_circle_grid_from_image_array(), mrgingham.cc:10-21: blobs -> grid. Returns 1 or 0. */
+/* mrgingham::find_circle_grid_from_image_array(), mrgingham.cc:10-21: blobs -> grid. Returns 1 (found), 0 (not
+   found) or -2 (the GPU path failed). */
 int mrg_b200_find_circle_grid_from_image_array(const uint8_t* image, int Nrows, int Ncols, int stride,
                                                int gridn, double* xy_out);
 

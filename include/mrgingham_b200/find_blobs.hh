@@ -22,6 +22,7 @@ namespace mrgingham
             cap = n; xy.resize((size_t)2 * cap);
             n = mrg_b200_find_blobs(image.data, image.rows, image.cols, (int)image.step, xy.data(), cap);
         }
+        if (n < 0) throw std::runtime_error("mrgingham_b200: the GPU blob detector failed (see stderr)");
         for (int i = 0; i < n; i++)
         {
             if (dodump) printf("%f %f\n", xy[2*i] / 1000.0, xy[2*i + 1] / 1000.0);

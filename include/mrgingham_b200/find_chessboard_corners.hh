@@ -10,6 +10,7 @@
 #pragma once
 
 #include <vector>
+#include <stdexcept>
 #include <stdio.h>
 #include "../mrgingham_b200.h"
 
@@ -60,6 +61,9 @@ namespace mrgingham
             n = mrg_b200_find_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
                                                  image_pyramid_level, xy.data(), cap);
         }
+        // n < 0: the GPU path failed (CUDA error, no device). There is no CPU fallback and "no points" would be a lie:
+        // the failure is thrown (the reference's bool cannot carry it).
+        if (n < 0) throw std::runtime_error("mrgingham_b200: the GPU corner detector failed (see stderr)");
         for (int i = 0; i < n; i++) points_scaled_out->push_back(PointInt(xy[2*i], xy[2*i + 1]));
         return points_scaled_out->size() > 0;
     }
@@ -75,8 +79,11 @@ namespace mrgingham
         (void)debug; (void)debug_image_filename;
         static_assert(sizeof(PointDouble) == 2 * sizeof(double), "PointDouble must be 2 doubles");
         if (points->empty()) return 0;
-        return mrg_b200_refine_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
-                                                  image_pyramid_level, &(*points)[0].x, level, (int)points->size());
+        const int n = mrg_b200_refine_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
+                                                         image_pyramid_level, &(*points)[0].x, level, (int)points->size());
+        // callers stop refining on "<= 0 points refined" (mrgingham.cc:96): a GPU failure must not pass for that
+        if (n < 0) throw std::runtime_error("mrgingham_b200: the GPU corner refinement failed (see stderr)");
+        return n;
     }
 
     // Image files (find_chessboard_corners.cc:622-648, find_blobs.cc:48-64 go through cv::imread with

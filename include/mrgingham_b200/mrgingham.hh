@@ -41,7 +41,9 @@ namespace mrgingham
         (void)debug; (void)debug_sequence;
         if (gridn < 2) return false;
         std::vector<double> xy((size_t)2 * gridn * gridn);
-        if (mrg_b200_find_circle_grid_from_image_array(image.data, image.rows, image.cols, (int)image.step, gridn, xy.data()) != 1) return false;
+        const int rc = mrg_b200_find_circle_grid_from_image_array(image.data, image.rows, image.cols, (int)image.step, gridn, xy.data());
+        if (rc < 0) throw std::runtime_error("mrgingham_b200: the GPU circle-grid finder failed (see stderr)");
+        if (rc != 1) return false;
         for (int i = 0; i < gridn * gridn; i++) points_out.push_back(PointDouble(xy[2*i], xy[2*i + 1]));
         return true;
     }
@@ -59,6 +61,7 @@ namespace mrgingham
         std::vector<signed char> lv(N);
         const int level = mrg_b200_find_chessboard_from_image_array(image.data, image.rows, image.cols, (int)image.step, gridn,
                                                                     image_pyramid_level, refinement_level != NULL, xy.data(), lv.data());
+        if (level < -1) throw std::runtime_error("mrgingham_b200: the GPU board finder failed (see stderr)");   // -2: failure, not "no board"
         if (level < 0) return -1;
         const size_t first = points_out.size();
         for (int i = 0; i < N; i++) points_out.push_back(PointDouble(xy[2*i], xy[2*i + 1]));

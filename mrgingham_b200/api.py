@@ -185,8 +185,11 @@ def find_points(image, image_pyramid_level=0, blobs=False, debug=False):
     ok = lib().find_chessboard_corners_from_image_array_C(image.shape[0], image.shape[1], image.strides[0],
                                                           image.ctypes.data, int(image_pyramid_level),
                                                           bool(blobs), bool(debug), cb, None)
-    if not ok or "xy" not in result:
-        return np.zeros((0, 2), dtype=np.float64)
+    if not ok:
+        if "xy" in result:
+            # false WITH a result is the bridge's error return (mrgingham_pywrap.c:212-219): the GPU path failed
+            raise RuntimeError("find_chessboard_corners_from_image_array_C() failed")
+        return np.zeros((0, 2), dtype=np.float64)      # nothing found: an empty array, no error (:203-211)
     return result["xy"]
 
 
@@ -289,6 +292,8 @@ def find_chessboard_from_image_array(image, gridn=10, image_pyramid_level=-1, re
     lv = np.zeros(gridn * gridn, dtype=np.int8)
     r = lib().mrg_b200_find_chessboard_from_image_array(_ptr(image, _u8p), image.shape[0], image.shape[1], image.strides[0],
                                                         int(gridn), int(image_pyramid_level), int(bool(refine)), _ptr(xy, _f64p), _ptr(lv, _i8p))
+    if r < -1:
+        raise RuntimeError("mrg_b200_find_chessboard_from_image_array() failed on the GPU")
     if r < 0:
         return r, None, None
     return r, xy, (lv if refine else None)

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <condition_variable>
 
 #include "../../include/mrgingham_b200.h"
 #include "kernels.cuh"
@@ -89,6 +90,26 @@ struct KernelTimer
     }
     void release() { reset(); for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
 };
+
+// Makes `dev` the calling thread's current device for the lifetime of the guard and puts the caller's own
+// device back afterwards: no entry point of this library changes the caller's current device (the reference,
+// CPU code, has no such side effect).
+struct DeviceGuard
+{
+    int prev = -1; bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = prev == dev || cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;      // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_GUARD(det)                                                                \
+    DeviceGuard _dg((det)->device);                                                      \
+    if (!_dg.ok) { MSG("Could not select CUDA device %d.", (det)->device); return -1; }
 }
 
 struct mrg_b200_detector
@@ -115,6 +136,11 @@ struct mrg_b200_detector
     DeviceBuffer pts, lvls;
     // results of the batch in flight
     PinnedBuffer h_xy, h_counts, h_candcounts;
+    // detectors of the one-image pool: pageable caller memory goes through this pinned buffer (a plain memcpy, then
+    // one DMA on the detector's own stream), so concurrent callers do not queue on the driver's pageable-copy path
+    bool         stage_via_pinned = false;
+    PinnedBuffer h_stage;
+    cudaEvent_t  h_stage_free = nullptr;      // recorded after the last copy out of h_stage
 
     bool profiling = false;
     KernelTimer timers[3];
@@ -128,7 +154,7 @@ struct mrg_b200_detector
     struct Pending
     {
         bool active = false;
-        const uint8_t* images; int on_device, nframes, rows, cols, level; size_t pitch, fstride;
+        const uint8_t* images; int on_device, nframes, rows, cols, level, mp; size_t pitch, fstride;
         cudaStream_t stream;
     } pending;
 };
@@ -195,7 +221,19 @@ int stage_frames(mrg_b200_detector* det, mrg_b200_detector::Slot& S, const uint8
         const int spitch = round_up(cols, 16);
         const size_t sframe = (size_t)spitch * rows;
         if (S.stage.ensure(sframe * n)) return -1;
-        if (fstride == pitch * (size_t)rows && pitch == (size_t)spitch)
+        if (det->stage_via_pinned)
+        {
+            if (det->h_stage.ensure(sframe * n)) return -1;
+            if (!det->h_stage_free) CUDA_TRY(cudaEventCreateWithFlags(&det->h_stage_free, cudaEventDisableTiming));
+            else                    CUDA_TRY(cudaEventSynchronize(det->h_stage_free));
+            uint8_t* hp = (uint8_t*)det->h_stage.p;
+            for (int i = 0; i < n; i++)
+                if (pitch == (size_t)spitch) memcpy(hp + i * sframe, images + i * fstride, sframe);
+                else for (int y = 0; y < rows; y++) memcpy(hp + i * sframe + (size_t)y * spitch, images + i * fstride + (size_t)y * pitch, cols);
+            CUDA_TRY(cudaMemcpyAsync(S.stage.p, hp, sframe * n, cudaMemcpyHostToDevice, cstream));
+            CUDA_TRY(cudaEventRecord(det->h_stage_free, cstream));
+        }
+        else if (fstride == pitch * (size_t)rows && pitch == (size_t)spitch)
             // dense rows on both sides: one linear copy
             CUDA_TRY(cudaMemcpyAsync(S.stage.p, images, sframe * n, cudaMemcpyHostToDevice, cstream));
         else if (fstride == pitch * (size_t)rows)
@@ -243,9 +281,12 @@ int stage_frames(mrg_b200_detector* det, mrg_b200_detector::Slot& S, const uint8
     return 0;
 }
 
-int ensure_chunk_scratch(mrg_b200_detector* det, mrg_b200_detector::Slot& S, int n)
+// mp = per-frame output capacity of the call being served. It is an argument everywhere below and never written
+// back into det->cfg: the public batch calls pass the configured max_points (what the caller sized xy_out by),
+// the board finder and the one-image entry points grow a private value when a frame has more corners.
+int ensure_chunk_scratch(mrg_b200_detector* det, mrg_b200_detector::Slot& S, int n, int mp_)
 {
-    const size_t cap = det->cfg.candidate_capacity, mp = det->cfg.max_points;
+    const size_t cap = det->cfg.candidate_capacity, mp = (size_t)mp_;
     if (S.cand.ensure(sizeof(cand_t) * cap * n)) return -1;
     if (S.counts.ensure(sizeof(uint32_t) * n)) return -1;
     if (S.table.ensure(sizeof(uint32_t) * 2 * cap * n)) return -1;
@@ -259,19 +300,18 @@ int ensure_chunk_scratch(mrg_b200_detector* det, mrg_b200_detector::Slot& S, int
 // One frame whose candidate list (or component list) overflowed the chunk scratch: run it again
 // on the GPU with worst-case capacities.
 int rerun_big(mrg_b200_detector* det, const uint8_t* image, int on_device, int rows, int cols, size_t pitch,
-              int level, cudaStream_t stream, int32_t* xy_out, int32_t* count_out, int32_t* candcount_out)
+              int level, int mp, cudaStream_t stream, int32_t* xy_out, int32_t* count_out, int32_t* candcount_out)
 {
     mrg_b200_detector::Slot& S = det->slot[0];
     FrameSet fs;
     if (stage_frames(det, S, image, on_device, 1, rows, cols, pitch, pitch * rows, level, stream, stream, &fs, true)) return -1;
     const int cap = next_pow2((long long)fs.w * fs.h);
-    const int mp = det->cfg.max_points;
     const int reccap = cap / 2 + 1;
     if (det->big_cand.ensure(sizeof(cand_t) * cap)) return -1;
     if (det->big_table.ensure(sizeof(uint32_t) * 2 * cap)) return -1;
     if (det->big_dfs.ensure(sizeof(uint32_t) * cap)) return -1;
     if (det->big_records.ensure(cluster_record_bytes() * reccap)) return -1;
-    if (ensure_chunk_scratch(det, S, 1)) return -1;
+    if (ensure_chunk_scratch(det, S, 1, mp)) return -1;
     CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t), stream));
     if (chess_sparse(det, fs, (cand_t*)det->big_cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
     ClusterParams p; p.smem_cands = det->k2_smem_cands; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = reccap; p.records = det->big_records.p;
@@ -289,7 +329,7 @@ int rerun_big(mrg_b200_detector* det, const uint8_t* image, int on_device, int r
 }
 
 int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device, int nframes, int rows, int cols,
-                   size_t pitch, size_t fstride, int level, cudaStream_t stream)
+                   size_t pitch, size_t fstride, int level, int mp, cudaStream_t stream)
 {
     if (det->pending.active) { MSG("A batch is already in flight on this detector: collect it first."); return -1; }
     if (nframes < 0 || rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767 || pitch < (size_t)cols)
@@ -298,10 +338,10 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
     { MSG("Frame %dx%d exceeds the detector's configured maximum %dx%d.", cols, rows, det->cfg.max_cols, det->cfg.max_rows); return -1; }
     if (level < 0 || level > 10)
     { MSG("Got an unreasonable image_pyramid_level = %d.", level); return -1; }
-    CUDA_TRY(cudaSetDevice(det->device));
+    DEVICE_GUARD(det);
     for (auto& t : det->timers) t.reset();
 
-    const int mp = det->cfg.max_points, cap = det->cfg.candidate_capacity;
+    const int cap = det->cfg.candidate_capacity;
     if (det->h_xy.ensure(sizeof(int32_t) * 2 * mp * std::max(nframes, 1))) return -1;
     if (det->h_counts.ensure(sizeof(int32_t) * std::max(nframes, 1))) return -1;
     if (det->h_candcounts.ensure(sizeof(int32_t) * std::max(nframes, 1))) return -1;
@@ -332,7 +372,7 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
     {
         mrg_b200_detector::Slot& S = det->slot[b];
         const int n = std::min(chunk, nframes);
-        if (ensure_chunk_scratch(det, S, n)) return -1;
+        if (ensure_chunk_scratch(det, S, n, mp)) return -1;
         if (!on_device && S.stage.ensure((size_t)round_up(cols, 16) * rows * n)) return -1;
         if (level > 0 && S.level_img.ensure(level_geom(rows, cols, level).frame_bytes * n)) return -1;
         S.used = false;
@@ -369,13 +409,15 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
         CUDA_TRY(cudaEventRecord(S.k2done, aux));
         S.used = true;
     }
-    // join: everything this call enqueued is ordered before whatever the caller puts on `stream` next
-    for (int b = 0; b < 2; b++)
-        if (det->slot[b].used) CUDA_TRY(cudaStreamWaitEvent(stream, det->slot[b].k2done, 0));
+    // No join here: the clustering kernels and result copies of the last chunks run on the aux stream and
+    // collect() waits for THEM (their events), not for `stream`. Whatever the caller enqueues on `stream` next --
+    // another detector's batch over the same frames, as bench.py's overlapped passes do -- starts as soon as this
+    // batch's ChESS kernels are done, beside this batch's clustering tail. The frames must stay valid and
+    // unchanged until collect() returns.
     det->pending.active = true;
     det->pending.images = images; det->pending.on_device = on_device; det->pending.nframes = nframes;
     det->pending.rows = rows; det->pending.cols = cols; det->pending.level = level;
-    det->pending.pitch = pitch; det->pending.fstride = fstride; det->pending.stream = stream;
+    det->pending.pitch = pitch; det->pending.fstride = fstride; det->pending.stream = stream; det->pending.mp = mp;
     return 0;
 }
 
@@ -384,14 +426,16 @@ int collect_locked(mrg_b200_detector* det, int32_t* xy_out, int32_t* counts_out)
     if (!det->pending.active) { MSG("No batch in flight."); return -1; }
     auto& pd = det->pending;
     pd.active = false;
-    CUDA_TRY(cudaSetDevice(det->device));
-    CUDA_TRY(cudaStreamSynchronize(pd.stream));
+    DEVICE_GUARD(det);
+    // everything the batch enqueued ends in the k2done event of one of the two slots
+    for (int b = 0; b < 2; b++)
+        if (det->slot[b].used) CUDA_TRY(cudaEventSynchronize(det->slot[b].k2done));
     for (auto& t : det->timers) t.resolve();
-    const int mp = det->cfg.max_points;
+    const int mp = pd.mp;
     int32_t* hxy = (int32_t*)det->h_xy.p; int32_t* hc = (int32_t*)det->h_counts.p; int32_t* hcc = (int32_t*)det->h_candcounts.p;
     for (int f = 0; f < pd.nframes; f++)
         if (hc[f] < 0)
-            if (rerun_big(det, pd.images + (size_t)f * pd.fstride, pd.on_device, pd.rows, pd.cols, pd.pitch, pd.level, pd.stream,
+            if (rerun_big(det, pd.images + (size_t)f * pd.fstride, pd.on_device, pd.rows, pd.cols, pd.pitch, pd.level, mp, pd.stream,
                           hxy + (size_t)f * 2 * mp, hc + f, hcc + f)) return -1;
     if (xy_out)     memcpy(xy_out, hxy, sizeof(int32_t) * 2 * mp * pd.nframes);
     if (counts_out) memcpy(counts_out, hc, sizeof(int32_t) * pd.nframes);
@@ -433,7 +477,8 @@ API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detecto
     det->cfg.candidate_capacity = next_pow2(det->cfg.candidate_capacity);
     if (det->cfg.max_points <= 0) det->cfg.max_points = 1024;
     if (det->cfg.blur_radius < 0 || det->cfg.blur_radius > 4) { MSG("blur_radius must be in [0,4]; got %d.", det->cfg.blur_radius); delete det; return -1; }
-    bool ok = cudaSetDevice(det->device) == cudaSuccess &&
+    DeviceGuard dg(det->device);
+    bool ok = dg.ok &&
               cudaStreamCreateWithFlags(&det->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               // clustering runs at high priority so its few CTAs slot in as ChESS CTAs retire
               // (MRG_B200_K2_PRIORITY=0: A/B knob, default priority -- they then wait for the ChESS grid's tail)
@@ -457,9 +502,9 @@ API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detecto
 
 API void mrg_b200_detector_destroy(mrg_b200_detector* det)
 {
-    if (det && det->blobs) { cudaSetDevice(det->device); blob_workspace_destroy(det->blobs); det->blobs = nullptr; }
     if (!det) return;
-    cudaSetDevice(det->device);
+    DeviceGuard dg(det->device);
+    if (det->blobs) { blob_workspace_destroy(det->blobs); det->blobs = nullptr; }
     cudaDeviceSynchronize();
     for (auto& S : det->slot)
     {
@@ -471,10 +516,23 @@ API void mrg_b200_detector_destroy(mrg_b200_detector* det)
     if (det->ev_fork) cudaEventDestroy(det->ev_fork);
     if (det->aux_stream) cudaStreamDestroy(det->aux_stream);
     if (det->copy_stream) cudaStreamDestroy(det->copy_stream);
-    for (PinnedBuffer* b : { &det->h_xy, &det->h_counts, &det->h_candcounts }) b->release();
+    for (PinnedBuffer* b : { &det->h_xy, &det->h_counts, &det->h_candcounts, &det->h_stage }) b->release();
+    if (det->h_stage_free) cudaEventDestroy(det->h_stage_free);
     for (auto& t : det->timers) t.release();
     if (det->own_stream) cudaStreamDestroy(det->own_stream);
     delete det;
+}
+
+// mrg_b200_find_corners_batch() with an explicit per-frame output capacity (xy_out is [nframes][mp][2])
+static int corners_batch_mp(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                            int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                            int image_pyramid_level, int mp, int32_t* xy_out, int32_t* counts_out, void* stream)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (enqueue_locked(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, image_pyramid_level, mp,
+                       stream ? (cudaStream_t)stream : det->own_stream)) return -1;
+    return collect_locked(det, xy_out, counts_out);
 }
 
 API int mrg_b200_find_corners_batch_enqueue(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
@@ -484,7 +542,7 @@ API int mrg_b200_find_corners_batch_enqueue(mrg_b200_detector* det, const uint8_
     if (!det) return -1;
     std::lock_guard<std::mutex> g(det->mtx);
     return enqueue_locked(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, image_pyramid_level,
-                          stream ? (cudaStream_t)stream : det->own_stream);
+                          det->cfg.max_points, stream ? (cudaStream_t)stream : det->own_stream);
 }
 
 API int mrg_b200_find_corners_batch_collect(mrg_b200_detector* det, int32_t* xy_out, int32_t* counts_out)
@@ -499,10 +557,8 @@ API int mrg_b200_find_corners_batch(mrg_b200_detector* det, const uint8_t* image
                                     int image_pyramid_level, int32_t* xy_out, int32_t* counts_out, void* stream)
 {
     if (!det) return -1;
-    std::lock_guard<std::mutex> g(det->mtx);
-    if (enqueue_locked(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, image_pyramid_level,
-                       stream ? (cudaStream_t)stream : det->own_stream)) return -1;
-    return collect_locked(det, xy_out, counts_out);
+    return corners_batch_mp(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, image_pyramid_level,
+                            det->cfg.max_points, xy_out, counts_out, stream);
 }
 
 API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
@@ -514,7 +570,7 @@ API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* ima
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
     if (nframes <= 0 || rows <= 0 || cols <= 0 || row_pitch < (size_t)cols) { MSG("Bad batch geometry."); return -1; }
     if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
-    CUDA_TRY(cudaSetDevice(det->device));
+    DEVICE_GUARD(det);
     const size_t fe = (size_t)rows * cols;
     const int chunk = response_on_device ? nframes : std::max(1, det->cfg.max_frames);
     for (int f0 = 0; f0 < nframes; f0 += chunk)
@@ -560,7 +616,7 @@ static int preprocess_batch(mrg_b200_detector* det, const uint8_t* images, int i
     if (blur_radius < 0 || blur_radius > 4) { MSG("blur_radius must be in [0,4]; got %d.", blur_radius); return -1; }
     if (!clahe && blur_radius == 0) { MSG("Nothing to do: neither clahe nor a blur was asked for."); return -1; }
     if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
-    CUDA_TRY(cudaSetDevice(det->device));
+    DEVICE_GUARD(det);
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
     const size_t fe = (size_t)rows * cols;
     const int chunk = std::min(out_on_device && images_on_device ? std::max(nframes, 1) : std::max(1, det->cfg.max_frames), 65535);
@@ -618,7 +674,7 @@ API int mrg_b200_pyramid_level(mrg_b200_detector* det, const uint8_t* image, int
     std::lock_guard<std::mutex> g(det->mtx);
     if (level < 0 || level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); return -1; }
     if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
-    CUDA_TRY(cudaSetDevice(det->device));
+    DEVICE_GUARD(det);
     cudaStream_t stream = det->own_stream;
     FrameSet fs;
     if (stage_frames(det, det->slot[0], image, 0, 1, rows, cols, row_pitch, row_pitch * rows, level, stream, stream, &fs)) return -1;
@@ -657,23 +713,22 @@ API int mrg_b200_device_count(void)
     return ndev;
 }
 
-API int mrg_b200_find_blobs_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
-                                  int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
-                                  int32_t* xy_out, int32_t* counts_out, void* stream_)
+static int blobs_batch_mp(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                          int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                          int mp, int32_t* xy_out, int32_t* counts_out, void* stream_)
 {
     if (!det) return -1;
     std::lock_guard<std::mutex> g(det->mtx);
     if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
     if (nframes < 0 || rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767 || row_pitch < (size_t)cols)
     { MSG("Bad batch geometry (nframes=%d rows=%d cols=%d pitch=%zu).", nframes, rows, cols, row_pitch); return -1; }
-    CUDA_TRY(cudaSetDevice(det->device));
+    DEVICE_GUARD(det);
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
     if (!det->blobs) det->blobs = blob_workspace_create();
     det->blob_ms = 0;
     // One thread per (frame, threshold) follows borders, so throughput comes from frames in flight:
     // up to 256 frames per chunk (the scratch is ~70 MB per 4K frame, ~18 GB of the 180 GB at that size)
     const int chunk = std::max(1, std::min(det->cfg.max_frames, 256));
-    const int mp = det->cfg.max_points;
     for (int f0 = 0; f0 < nframes; f0 += chunk)
     {
         const int n = std::min(chunk, nframes - f0);
@@ -700,41 +755,108 @@ API int mrg_b200_find_blobs_batch(mrg_b200_detector* det, const uint8_t* images,
     return 0;
 }
 
+API int mrg_b200_find_blobs_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                  int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                  int32_t* xy_out, int32_t* counts_out, void* stream_)
+{
+    if (!det) return -1;
+    return blobs_batch_mp(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, det->cfg.max_points,
+                          xy_out, counts_out, stream_);
+}
+
 // =================================================================================================
 // A/B. single-image entry points on a process-wide default detector
 // =================================================================================================
-static std::mutex g_default_mtx;
-static mrg_b200_detector* g_default = nullptr;
-
-static mrg_b200_detector* default_detector()
+// A call borrows a private detector for its duration from a per-device pool (created on first use, at most
+// kPoolMax per device; further callers wait for one to come back). N host threads -- the reference CLI's -j N,
+// mrgingham-from-image.cc:374-379 -- therefore run on N streams with N sets of scratch, concurrently, and the
+// detector a call gets lives on the calling thread's CURRENT device (a thread working on cuda:1 stays there).
+namespace
 {
-    // callers hold g_default_mtx
-    if (g_default) return g_default;
-    mrg_b200_detector_config cfg; memset(&cfg, 0, sizeof(cfg));
-    cfg.device = -1; cfg.max_frames = 1; cfg.candidate_capacity = 65536; cfg.max_points = 4096;
-    if (mrg_b200_detector_create(&g_default, &cfg)) return nullptr;
-    return g_default;
+constexpr int kMaxDevices = 64, kPoolMax = 16;
+constexpr int kDefaultPoints = 4096;     // first guess at a frame's corner count; grown per call, never stored
+struct DefaultPool
+{
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<mrg_b200_detector*> idle[kMaxDevices];
+    int created[kMaxDevices] = {};
+};
+DefaultPool& default_pool()
+{
+    static DefaultPool* p = new DefaultPool;   // never destroyed: the CUDA runtime may be gone by static-destruction time
+    return *p;
+}
+struct DefaultLease
+{
+    mrg_b200_detector* det = nullptr;
+    int dev = -1;
+    DefaultLease()
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+        {
+            MSG("No usable CUDA device: this library has no CPU implementation.");
+            dev = -1;
+            return;
+        }
+        DefaultPool& P = default_pool();
+        {
+            std::unique_lock<std::mutex> lk(P.m);
+            for (;;)
+            {
+                if (!P.idle[dev].empty()) { det = P.idle[dev].back(); P.idle[dev].pop_back(); return; }
+                if (P.created[dev] < kPoolMax) { P.created[dev]++; break; }
+                P.cv.wait(lk);
+            }
+        }
+        mrg_b200_detector_config cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.device = dev; cfg.max_frames = 1; cfg.candidate_capacity = 65536; cfg.max_points = kDefaultPoints;
+        if (mrg_b200_detector_create(&det, &cfg))
+        {
+            det = nullptr;
+            std::lock_guard<std::mutex> lk(P.m);
+            P.created[dev]--;
+            P.cv.notify_one();
+            return;
+        }
+        // one-image calls hand over pageable host memory: stage it through the detector's own pinned buffer
+        static const bool pin = [] { const char* e = getenv("MRG_B200_PIN_STAGE"); return !e || atoi(e) != 0; }();
+        det->stage_via_pinned = pin;
+    }
+    ~DefaultLease()
+    {
+        if (!det) return;
+        DefaultPool& P = default_pool();
+        std::lock_guard<std::mutex> lk(P.m);
+        P.idle[dev].push_back(det);
+        P.cv.notify_one();
+    }
+    DefaultLease(const DefaultLease&) = delete;
+    DefaultLease& operator=(const DefaultLease&) = delete;
+};
 }
 
+// Return conventions of the one-image calls: 0 = nothing found (including the reference's own error paths, which
+// report "no points"), < 0 = the GPU path FAILED (CUDA error, no device). The two are kept apart all the way up:
+// the drop-in bridge symbols turn a failure into the reference's error return, never into "found nothing".
 API int mrg_b200_find_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride, int level,
                                          int* xy_out, int cap)
 {
     // the reference's error paths give "no points" (find_chessboard_corners.cc:433-441, :461-466)
     if (level < 0 || level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); return 0; }
     if (level == 0 && Nrows > 1 && stride != Ncols) { MSG("I can only handle continuous arrays (stride == width) currently."); return 0; }
-    std::lock_guard<std::mutex> g(g_default_mtx);
-    mrg_b200_detector* det = default_detector();
-    if (!det) return -1;
-    const int mp = det->cfg.max_points;
-    std::vector<int32_t> xy((size_t)2 * mp);
+    DefaultLease L;
+    if (!L.det) return -1;
+    int mp = kDefaultPoints;
+    std::vector<int32_t> xy;
     int32_t n = 0;
-    if (mrg_b200_find_corners_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, xy.data(), &n, nullptr)) return -1;
-    if (n > mp)
+    for (;;)
     {
-        // more corners than the default output capacity: grow it and run again
-        det->cfg.max_points = next_pow2(n);
-        xy.resize((size_t)2 * det->cfg.max_points);
-        if (mrg_b200_find_corners_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, xy.data(), &n, nullptr)) return -1;
+        xy.resize((size_t)2 * mp);
+        if (corners_batch_mp(L.det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level, mp, xy.data(), &n, nullptr)) return -1;
+        if (n <= mp) break;
+        mp = next_pow2(n);         // more corners than the first guess: look again with room for all of them
     }
     for (int i = 0; i < n && i < cap; i++) { xy_out[2*i] = xy[2*i]; xy_out[2*i + 1] = xy[2*i + 1]; }
     return n;
@@ -743,19 +865,20 @@ API int mrg_b200_find_chessboard_corners(const uint8_t* image, int Nrows, int Nc
 API int mrg_b200_find_blobs(const uint8_t* image, int Nrows, int Ncols, int stride, int* xy_out, int cap)
 {
     if (Nrows <= 0 || Ncols <= 0 || stride < Ncols) { MSG("Bad image geometry."); return 0; }
-    std::lock_guard<std::mutex> g(g_default_mtx);
-    mrg_b200_detector* det = default_detector();
-    if (!det) return -1;
+    DefaultLease L;
+    if (!L.det) return -1;
+    int mp = kDefaultPoints;
+    std::vector<int32_t> xy;
+    int32_t n = 0;
     for (;;)
     {
-        const int mp = det->cfg.max_points;
-        std::vector<int32_t> xy((size_t)2 * mp);
-        int32_t n = 0;
-        if (mrg_b200_find_blobs_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, xy.data(), &n, nullptr)) return -1;
-        if (n > mp) { det->cfg.max_points = next_pow2(n); continue; }
-        for (int i = 0; i < n && i < cap; i++) { xy_out[2*i] = xy[2*i]; xy_out[2*i + 1] = xy[2*i + 1]; }
-        return n;
+        xy.resize((size_t)2 * mp);
+        if (blobs_batch_mp(L.det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, mp, xy.data(), &n, nullptr)) return -1;
+        if (n <= mp) break;
+        mp = next_pow2(n);
     }
+    for (int i = 0; i < n && i < cap; i++) { xy_out[2*i] = xy[2*i]; xy_out[2*i + 1] = xy[2*i + 1]; }
+    return n;
 }
 
 API bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols, int stride, char* imagebuffer,
@@ -763,41 +886,39 @@ API bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols, int st
                                                     bool (*add_points)(int* xy, int N, double scale, void* cookie), void* cookie)
 {
     (void)debug; // the reference's debug mode only writes /tmp dumps
-    if (doblobs)
-    {
-        // mrgingham_pywrap_cplusplus_bridge.cc:50-56: blobs only at level 0, via find_blobs_from_image_array()
-        if (image_pyramid_level != 0) return false;
-        int bcap = 4096;
-        std::vector<int> bxy((size_t)2 * bcap);
-        int bn = mrg_b200_find_blobs((const uint8_t*)imagebuffer, Nrows, Ncols, stride, bxy.data(), bcap);
-        if (bn > bcap)
-        {
-            bcap = bn; bxy.resize((size_t)2 * bcap);
-            bn = mrg_b200_find_blobs((const uint8_t*)imagebuffer, Nrows, Ncols, stride, bxy.data(), bcap);
-        }
-        if (bn <= 0) return false;
-        return (*add_points)(bxy.data(), bn, 1.0 / kFindGridScale, cookie);
-    }
+    // mrgingham_pywrap_cplusplus_bridge.cc:50-56: blobs only at level 0, via find_blobs_from_image_array()
+    if (doblobs && image_pyramid_level != 0) return false;
     int cap = 4096;
     std::vector<int> xy((size_t)2 * cap);
-    int n = mrg_b200_find_chessboard_corners((const uint8_t*)imagebuffer, Nrows, Ncols, stride, image_pyramid_level, xy.data(), cap);
-    if (n > cap)
+    auto look = [&]() -> int
     {
-        cap = n; xy.resize((size_t)2 * cap);
-        n = mrg_b200_find_chessboard_corners((const uint8_t*)imagebuffer, Nrows, Ncols, stride, image_pyramid_level, xy.data(), cap);
+        return doblobs ? mrg_b200_find_blobs((const uint8_t*)imagebuffer, Nrows, Ncols, stride, xy.data(), cap)
+                       : mrg_b200_find_chessboard_corners((const uint8_t*)imagebuffer, Nrows, Ncols, stride, image_pyramid_level, xy.data(), cap);
+    };
+    int n = look();
+    if (n > cap) { cap = n; xy.resize((size_t)2 * cap); n = look(); }
+    if (n < 0)
+    {
+        // The GPU path failed. "false with nothing added" means "found nothing" to the caller (mrgingham_pywrap.c:
+        // 203-211 returns an empty array), so hand over an empty result first: false WITH a result is the bridge's
+        // error return (mrgingham_pywrap.c:212-219 raises RuntimeError).
+        MSG("The GPU corner detector failed; reporting an error, not 'no points'.");
+        (*add_points)(xy.data(), 0, 1.0 / kFindGridScale, cookie);
+        return false;
     }
-    if (n <= 0) return false;
+    if (n == 0) return false;
     return (*add_points)(xy.data(), n, 1.0 / kFindGridScale, cookie);
 }
 
+// A failure here cannot be returned (void, as ChESS.h:31-34 declares it): it is reported on stderr and `response` is
+// left untouched -- the host process is never taken down.
 API void mrgingham_ChESS_response_5(int16_t* response, const uint8_t* image, int w, int h, int stride)
 {
     if (w <= 2*kMargin || h <= 2*kMargin) return; // nothing is written for such sizes (ChESS.c:62-63)
-    std::lock_guard<std::mutex> g(g_default_mtx);
-    mrg_b200_detector* det = default_detector();
-    if (!det) { MSG("No CUDA device: response NOT computed."); abort(); }
-    if (mrg_b200_chess_response_batch(det, image, 0, 1, h, w, (size_t)stride, (size_t)stride * h, response, 0, nullptr))
-    { MSG("ChESS response failed on the GPU."); abort(); }
+    DefaultLease L;
+    if (!L.det) { MSG("No CUDA device: response NOT computed, the output buffer is untouched."); return; }
+    if (mrg_b200_chess_response_batch(L.det, image, 0, 1, h, w, (size_t)stride, (size_t)stride * h, response, 0, nullptr))
+        MSG("ChESS response failed on the GPU: response NOT computed, the output buffer may be partly written.");
 }
 
 // Refinement of `n` frames (n <= max_frames, or n == 1 with big == true for a frame whose candidate
@@ -811,7 +932,7 @@ static int refine_frames(mrg_b200_detector* det, cudaStream_t stream, const uint
     if (stage_frames(det, S, images, on_device, n, rows, cols, pitch, fstride, level, stream, stream, &fs, true)) return -1;
     if (det->pts.ensure(sizeof(double) * 2 * npoints * n)) return -1;
     if (det->lvls.ensure((size_t)npoints * n)) return -1;
-    if (ensure_chunk_scratch(det, S, n)) return -1;
+    if (ensure_chunk_scratch(det, S, n, det->cfg.max_points)) return -1;
     if (det->big_records.ensure(cluster_record_bytes() * (size_t)npoints * n)) return -1;
     int cap = det->cfg.candidate_capacity;
     cand_t* cand = (cand_t*)S.cand.p; uint32_t* table = (uint32_t*)S.table.p; uint32_t* dfs = (uint32_t*)S.dfs.p;
@@ -880,7 +1001,7 @@ API int mrg_b200_refine_corners_batch(mrg_b200_detector* det, const uint8_t* ima
     { MSG("Bad batch geometry."); return -1; }
     for (int i = 0; i < nframes; i++) nrefined_out[i] = 0;
     if (npoints == 0 || nframes == 0) return 0;
-    CUDA_TRY(cudaSetDevice(det->device));
+    DEVICE_GUARD(det);
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
     const int chunk = det->cfg.max_frames;
     for (int f0 = 0; f0 < nframes; f0 += chunk)
@@ -898,9 +1019,9 @@ API int mrg_b200_refine_chessboard_corners(const uint8_t* image, int Nrows, int 
     if (level < 0 || level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", level); return 0; }
     if (level == 0 && Nrows > 1 && stride != Ncols) { MSG("I can only handle continuous arrays (stride == width) currently."); return 0; }
     if (Npoints <= 0) return 0;
-    std::lock_guard<std::mutex> g(g_default_mtx);
-    mrg_b200_detector* det = default_detector();
-    if (!det) return -1;
+    DefaultLease L;
+    if (!L.det) return -1;
+    mrg_b200_detector* det = L.det;
     int32_t nref = 0;
     if (mrg_b200_refine_corners_batch(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, level,
                                       xy_inout, levels, Npoints, &nref, nullptr)) return -1;
@@ -957,6 +1078,7 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
     std::vector<int32_t> xy, counts(n);
     std::vector<int> todo;
     const uint8_t* base; size_t gp, gfs;
+    int mp = std::max(det->cfg.max_points, npts);      // output capacity of the corner passes below; grows here, never in det->cfg
     const int first_level = level < 0 ? 3 : level, last_level = level < 0 ? 0 : level;
     for (int L = first_level; L >= last_level; L--)
     {
@@ -970,17 +1092,15 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
         if (gather_frames(det, stream, d_images, rows, cols, pitch, fstride, todo, &base, &gp, &gfs)) return -1;
         for (;;)
         {
-            const int mp = det->cfg.max_points;
             xy.resize((size_t)2 * mp * cnt);
-            const int rc = doblobs ? mrg_b200_find_blobs_batch(det, base, 1, cnt, rows, cols, gp, gfs, xy.data(), counts.data(), stream)
-                                   : mrg_b200_find_corners_batch(det, base, 1, cnt, rows, cols, gp, gfs, L, xy.data(), counts.data(), stream);
+            const int rc = doblobs ? blobs_batch_mp(det, base, 1, cnt, rows, cols, gp, gfs, mp, xy.data(), counts.data(), stream)
+                                   : corners_batch_mp(det, base, 1, cnt, rows, cols, gp, gfs, L, mp, xy.data(), counts.data(), stream);
             if (rc) return -1;
             int most = 0;
             for (int k = 0; k < cnt; k++) most = std::max(most, (int)counts[k]);
             if (most <= mp) break;
-            det->cfg.max_points = next_pow2(most);     // more points than the output capacity: grow it and look again
+            mp = next_pow2(most);     // more points than room was made for: look again (a capacity private to this call)
         }
-        const int mp = det->cfg.max_points;
         parallel_for(cnt, [&](int k)
         {
             const int i = todo[k];
@@ -1045,12 +1165,23 @@ int find_boards(mrg_b200_detector* det, const uint8_t* images, int on_device, in
         if (!on_device)
         {
             // the frames go to the device once and stay there for every level and refinement pass
-            CUDA_TRY(cudaSetDevice(det->device));
+            DEVICE_GUARD(det);
             cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
             dpitch = pitch == (size_t)cols ? (size_t)cols : (size_t)round_up(cols, 16);
             dfstride = dpitch * rows;
             if (det->boards_frames.ensure(dfstride * n)) return -1;
-            if (dpitch == pitch && fstride == dfstride)
+            if (det->stage_via_pinned)
+            {
+                if (det->h_stage.ensure(dfstride * n)) return -1;
+                if (!det->h_stage_free) CUDA_TRY(cudaEventCreateWithFlags(&det->h_stage_free, cudaEventDisableTiming));
+                else                    CUDA_TRY(cudaEventSynchronize(det->h_stage_free));
+                uint8_t* hp = (uint8_t*)det->h_stage.p;
+                for (int i = 0; i < n; i++)
+                    for (int y = 0; y < rows; y++) memcpy(hp + i * dfstride + (size_t)y * dpitch, d + i * fstride + (size_t)y * pitch, cols);
+                CUDA_TRY(cudaMemcpyAsync(det->boards_frames.p, hp, dfstride * n, cudaMemcpyHostToDevice, stream));
+                CUDA_TRY(cudaEventRecord(det->h_stage_free, stream));
+            }
+            else if (dpitch == pitch && fstride == dfstride)
                 CUDA_TRY(cudaMemcpyAsync(det->boards_frames.p, d, dfstride * n, cudaMemcpyHostToDevice, stream));
             else
                 for (int i = 0; i < n; i++)
@@ -1087,17 +1218,18 @@ API int mrg_b200_find_boards_batch(mrg_b200_detector* det, const uint8_t* images
                        doblobs != 0, refine != 0, false, xy_out, levels_out, found_level_out, stream);
 }
 
+// Return values of the two one-image board calls: the reference's (level found / 1), "no grid" (-1 / 0), and,
+// kept apart from "no grid", -2 = the GPU path failed.
 API int mrg_b200_find_chessboard_from_image_array(const uint8_t* image, int Nrows, int Ncols, int stride,
                                                   int gridn, int image_pyramid_level, int refine,
                                                   double* xy_out, signed char* levels_out)
 {
     if (Nrows <= 0 || Ncols <= 0 || stride < Ncols) { MSG("Bad image geometry."); return -1; }
-    std::lock_guard<std::mutex> g(g_default_mtx);
-    mrg_b200_detector* det = default_detector();
-    if (!det) return -1;
+    DefaultLease L;
+    if (!L.det) return -2;
     int32_t found = -1;
-    if (find_boards(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, gridn, image_pyramid_level,
-                    false, refine != 0, true, xy_out, levels_out, &found, nullptr)) return -1;
+    if (find_boards(L.det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, gridn, image_pyramid_level,
+                    false, refine != 0, true, xy_out, levels_out, &found, nullptr)) return -2;
     return found;
 }
 
@@ -1105,12 +1237,11 @@ API int mrg_b200_find_circle_grid_from_image_array(const uint8_t* image, int Nro
                                                    int gridn, double* xy_out)
 {
     if (Nrows <= 0 || Ncols <= 0 || stride < Ncols) { MSG("Bad image geometry."); return 0; }
-    std::lock_guard<std::mutex> g(g_default_mtx);
-    mrg_b200_detector* det = default_detector();
-    if (!det) return 0;
+    DefaultLease L;
+    if (!L.det) return -2;
     int32_t found = -1;
-    if (find_boards(det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, gridn, 0,
-                    true, false, true, xy_out, nullptr, &found, nullptr)) return 0;
+    if (find_boards(L.det, image, 0, 1, Nrows, Ncols, (size_t)stride, (size_t)stride * Nrows, gridn, 0,
+                    true, false, true, xy_out, nullptr, &found, nullptr)) return -2;
     return found >= 0 ? 1 : 0;
 }
 
@@ -1123,12 +1254,25 @@ API bool find_chessboard_from_image_array_C(int Nrows, int Ncols, int stride, ch
     (void)debug; (void)debug_sequence_x; (void)debug_sequence_y;   // diagnostics only in the reference
     if (gridn < 2) return false;
     std::vector<double> xy((size_t)2 * gridn * gridn);
+    int rc;
     if (doblobs)
     {
         if (image_pyramid_level != 0) return false;
-        if (mrg_b200_find_circle_grid_from_image_array((const uint8_t*)imagebuffer, Nrows, Ncols, stride, gridn, xy.data()) != 1) return false;
+        rc = mrg_b200_find_circle_grid_from_image_array((const uint8_t*)imagebuffer, Nrows, Ncols, stride, gridn, xy.data());
+        if (rc == 0) return false;
     }
-    else if (mrg_b200_find_chessboard_from_image_array((const uint8_t*)imagebuffer, Nrows, Ncols, stride, gridn, image_pyramid_level, 1,
-                                                       xy.data(), nullptr) < 0) return false;
+    else
+    {
+        rc = mrg_b200_find_chessboard_from_image_array((const uint8_t*)imagebuffer, Nrows, Ncols, stride, gridn, image_pyramid_level, 1,
+                                                       xy.data(), nullptr);
+        if (rc == -1) return false;
+    }
+    if (rc < 0)
+    {
+        // The reference's Python wrapper reads any false as "no chessboard" (mrgingham_pywrap.c:300-310), so a GPU
+        // failure cannot be told apart through this symbol: it is made loud here instead of passing for "no board".
+        MSG("The GPU board finder FAILED (CUDA error or no device); this is NOT 'no chessboard found'.");
+        return false;
+    }
     return (*add_points)(xy.data(), gridn * gridn, cookie);
 }

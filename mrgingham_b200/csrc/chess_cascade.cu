@@ -464,8 +464,11 @@ bool make_cascade_map(CUtensorMap* map, const FrameSet& fs, int row_bytes)
     size_t fstride = fs.frame_stride;
     if (fs.nframes == 1) fstride = ((size_t)fs.pitch * fs.h + 15) & ~(size_t)15;
     if (fstride & 15) return false;
-    // the row is declared `pitch` bytes wide: padding bytes beyond w only ever feed pixels outside [7,w-7)
-    const cuuint64_t dims[3]    = { (cuuint64_t)(fs.pitch / 4), (cuuint64_t)fs.h, (cuuint64_t)fs.nframes };
+    // the row is declared ceil(w/4) words wide, not `pitch`: whatever lies beyond is zero-filled by TMA instead of
+    // fetched (a frame may be a crop of a larger allocation whose last row ends before base + h*pitch). The up to
+    // three bytes between w and the end of the last word are inside the row's pitch (pitch % 16 == 0 >= w) and only
+    // ever feed pixels outside [7,w-7).
+    const cuuint64_t dims[3]    = { (cuuint64_t)((fs.w + 3) / 4), (cuuint64_t)fs.h, (cuuint64_t)fs.nframes };
     const cuuint64_t strides[2] = { (cuuint64_t)fs.pitch, (cuuint64_t)fstride };
     const cuuint32_t box[3]     = { (cuuint32_t)(row_bytes / 4), kBlkRows, 1 };
     const cuuint32_t estr[3]    = { 1, 1, 1 };

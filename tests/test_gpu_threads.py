@@ -95,3 +95,36 @@ def test_detectors_of_their_own_per_thread():
         for xy, counts in res:
             for k, w in enumerate(want[t]):
                 assert counts[k] == len(w) and np.array_equal(xy[k, :counts[k]], w), (t, k)
+
+
+def test_one_image_calls_overlap_across_threads():
+    """The reference CLI's -j N (mrgingham-from-image.cc:374-379): N threads, one image each at a time. The one-image
+    entry points borrow a detector each from a per-device pool (own stream, own scratch, pinned staging), so eight
+    callers must get through clearly more images per second than one."""
+    import time
+    api._require_gpu()
+    images = [synth.board_frame(1920, 1080, 10, seed=70 + i) for i in range(8)]
+    want = [po.find_corners(im, 0) for im in images]
+    for im in images:                                   # warm the pool: one detector per future thread is created lazily
+        api.find_chessboard_corners_int(im, 0)
+
+    def rate(n_threads, seconds=1.5):
+        done = [0] * n_threads
+        stop = time.perf_counter() + seconds
+
+        def work(t):
+            while time.perf_counter() < stop:
+                got = api.find_chessboard_corners_int(images[t], 0)
+                assert np.array_equal(got, want[t])
+                done[t] += 1
+            return done[t]
+
+        t0 = time.perf_counter()
+        _run_threads(n_threads, work)
+        return sum(done) / (time.perf_counter() - t0)
+
+    rate(8, 0.5)                                        # all eight detectors exist after this
+    r1 = rate(1)
+    r8 = rate(8)
+    print(f"one-image 1080p calls: {r1:.0f}/s with 1 thread, {r8:.0f}/s with 8 threads ({r8 / r1:.2f}x)")
+    assert r8 >= 3.0 * r1, (r1, r8)
