@@ -237,6 +237,20 @@ int mrg_b200_chess_response_batch(mrg_b200_detector* det,
                                   int16_t* response, int response_on_device,
                                   void* stream);
 
+/* The sparse form of the response: per frame, every pixel of [7,w-7) x [7,h-7) whose ChESS response (at the given
+   pyramid level, after the detector's configured preprocessing) exceeds 15 -- what the reference's clamp + "r > 15"
+   membership test keeps (find_chessboard_corners.cc:527-529, :159-171) and all that the production ChESS kernel
+   writes. Only that kernel runs. cand_out: HOST uint64 [nframes][cand_cap] or NULL, entry = y << 32 | x << 16 | r, in no
+   particular order; counts_out: HOST int32 [nframes], the number found (entries beyond min(cand_cap, the detector's
+   candidate_capacity) are not stored). Synchronous. Returns 0 or <0. */
+int mrg_b200_chess_candidates_batch(mrg_b200_detector* det,
+                                    const uint8_t* images, int images_on_device,
+                                    int nframes, int rows, int cols,
+                                    size_t row_pitch, size_t frame_stride,
+                                    int image_pyramid_level,
+                                    uint64_t* cand_out, int cand_cap, int32_t* counts_out,
+                                    void* stream);
+
 /* The box blur the reference CLI applies before the detector by default (mrgingham-from-image.cc:
    106-111, --blur R with R = 1): cv::blur(image, image, Size(1+2R, 1+2R)), BORDER_REFLECT_101.
    out: uint8 [nframes][rows][cols] dense, HOST or DEVICE (out_on_device); it must not overlap the

@@ -25,7 +25,7 @@ EXPORTS = (
     "mrg_b200_preprocess_batch",
     "find_chessboard_from_image_array_C", "mrg_b200_find_grid_from_points", "mrg_b200_voronoi_neighbours",
     "mrg_b200_find_chessboard_from_image_array", "mrg_b200_find_circle_grid_from_image_array", "mrg_b200_find_boards_batch",
-    "mrg_b200_chess_response_batch", "mrg_b200_pyramid_level",
+    "mrg_b200_chess_response_batch", "mrg_b200_chess_candidates_batch", "mrg_b200_pyramid_level",
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
     "mrg_b200_device_count",
 )
@@ -107,6 +107,8 @@ def lib():
     L.mrg_b200_chess_response_batch.restype = ctypes.c_int
     L.mrg_b200_chess_response_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.mrg_b200_chess_candidates_batch.restype = ctypes.c_int
+    L.mrg_b200_chess_candidates_batch.argtypes = batch_args + [ctypes.c_void_p, ctypes.c_int, _i32p, ctypes.c_void_p]
     L.mrg_b200_pyramid_level.restype = ctypes.c_int
     L.mrg_b200_pyramid_level.argtypes = [ctypes.c_void_p, _u8p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_int,
                                          _u8p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
@@ -453,6 +455,19 @@ class Detector:
         if rc != 0:
             raise RuntimeError("mrg_b200_refine_corners_batch() failed")
         return nref, xy, levels
+
+    def chess_candidates(self, images, level=0, cand_cap=0, stream=None):
+        """K1 alone: (counts int32 [n], candidates uint64 [n, cand_cap] or None) -- the pixels with response > 15 as
+        y << 32 | x << 16 | r words, unordered (mrg_b200_chess_candidates_batch)"""
+        ptr, on_dev, n, rows, cols, pitch, fstride, keep = self._describe(images)
+        counts = np.zeros(n, dtype=np.int32)
+        cand = np.zeros((n, cand_cap), dtype=np.uint64) if cand_cap > 0 else None
+        rc = lib().mrg_b200_chess_candidates_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(level),
+                                                   cand.ctypes.data if cand is not None else None, int(cand_cap), _ptr(counts, _i32p),
+                                                   ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_chess_candidates_batch() failed")
+        return counts, cand
 
     def chess_response(self, images):
         """dense int16 response of host images [n, rows, cols] (border elements are 0)"""

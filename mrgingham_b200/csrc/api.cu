@@ -561,6 +561,50 @@ API int mrg_b200_find_corners_batch(mrg_b200_detector* det, const uint8_t* image
                             det->cfg.max_points, xy_out, counts_out, stream);
 }
 
+// The sparse form of the ChESS response: for every frame the list {(x, y, r) : r > 15} inside [7,w-7) x [7,h-7) that
+// the production ChESS kernel (K1) emits and the clustering kernel consumes -- K1 alone, nothing after it.
+API int mrg_b200_chess_candidates_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
+                                        int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                        int image_pyramid_level, uint64_t* cand_out, int cand_cap, int32_t* counts_out,
+                                        void* stream_)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    if (nframes < 0 || rows <= 0 || cols <= 0 || rows > 32767 || cols > 32767 || row_pitch < (size_t)cols || (cand_out && cand_cap <= 0))
+    { MSG("Bad batch geometry."); return -1; }
+    if (image_pyramid_level < 0 || image_pyramid_level > 10) { MSG("Got an unreasonable image_pyramid_level = %d.", image_pyramid_level); return -1; }
+    DEVICE_GUARD(det);
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+    for (auto& t : det->timers) t.reset();
+    const int cap = det->cfg.candidate_capacity;
+    const int chunk = std::max(1, det->cfg.max_frames);
+    std::vector<uint32_t> hc;
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        mrg_b200_detector::Slot& S = det->slot[0];
+        if (S.cand.ensure(sizeof(cand_t) * (size_t)cap * n) || S.counts.ensure(sizeof(uint32_t) * n)) return -1;
+        FrameSet fs;
+        if (stage_frames(det, S, images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride,
+                         image_pyramid_level, stream, stream, &fs, true)) return -1;
+        CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t) * n, stream));
+        if (chess_sparse(det, fs, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
+        hc.resize(n);
+        CUDA_TRY(cudaMemcpyAsync(hc.data(), S.counts.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int i = 0; i < n; i++)
+        {
+            if (counts_out) counts_out[f0 + i] = (int32_t)hc[i];           // may exceed the capacities: the list is then truncated
+            const size_t keep = std::min<size_t>(std::min<size_t>(hc[i], (size_t)cap), (size_t)std::max(cand_cap, 0));
+            if (cand_out && keep)
+                CUDA_TRY(cudaMemcpy(cand_out + (size_t)(f0 + i) * cand_cap, (cand_t*)S.cand.p + (size_t)i * cap, sizeof(cand_t) * keep, cudaMemcpyDeviceToHost));
+        }
+    }
+    for (auto& t : det->timers) t.resolve();
+    return 0;
+}
+
 API int mrg_b200_chess_response_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
                                       int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
                                       int16_t* response, int response_on_device, void* stream_)

@@ -51,10 +51,10 @@ namespace
 {
 constexpr int kLanePx   = 8;                   // pixels per lane
 constexpr int kWarpPx   = 32 * kLanePx;        // 256
-constexpr int kCHalo    = 16;                  // staged bytes left/right of the strip (ring needs 8; TMA boxes start 16-aligned)
+constexpr int kCHalo    = 8;                   // staged bytes left/right of the strip: the ring reaches 5 pixels, lanes read aligned 8-byte cells
 constexpr int kBlkRows  = 11;                  // rows per TMA stage == unroll of the row loop == register window
-constexpr int kL2QCap   = 512;                 // per-warp queue of flagged 8-pixel row cells (power of two, >= 31 + 352)
-constexpr int kL3QCap   = 512;                 // per-warp queue of pixels for the exact test (power of two, >= 31 + 256)
+constexpr int kL2QCap   = 384;                 // per-warp queue of flagged 8-pixel row cells (>= 31 carried + 352 of one block)
+constexpr int kL3QCap   = 288;                 // per-warp queue of pixels for the exact test (>= 31 waiting + 256 of one L2 batch)
 
 template<int NW> struct Geo
 {
@@ -69,8 +69,12 @@ struct CascadeParams
     int cap;
     int stages;                     // depth of the shared-memory ring (TMA stages of 11 rows)
     int nocarry;                    // 1: settle every flagged cell in its own block (2 stages held instead of 3)
+    uint32_t one;                   // the constant 1, opaque to the compiler: x*one + y is an integer add on the FMA pipe
 };
 
+// head/tail count entries since the CTA started (a CTA never queues anywhere near 2^32 of them); the slot of
+// entry p is p % cap. The capacities are not powers of two: every KB of shared memory per warp decides how many
+// CTAs fit a SM.
 struct WarpQueues
 {
     uint32_t l3q[kL3QCap];
@@ -96,6 +100,24 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity)
 }
 
 __device__ __forceinline__ uint32_t vabs4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+
+// a + b as IMAD (a*one + b, one == 1 at run time): the ALU pipe, which carries VABSDIFF4/PRMT/LOP3 at one warp
+// instruction per two cycles, is what binds L1; the FMA pipe has the room
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t b)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+// u0 + u1 + u2 + u3 + 0x78787878 in packed bytes. SUMS 0: two IADD3 (ALU pipe); 1: four IMAD (FMA pipe);
+// 2: one IADD3 + two IMAD
+template<int SUMS>
+__device__ __forceinline__ uint32_t packed_sum4(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t u3, uint32_t one)
+{
+    if (SUMS == 1) return add_fma(add_fma(u2, one, 0x78787878u), one, add_fma(u3, one, add_fma(u0, one, u1)));
+    if (SUMS == 2) return add_fma(u0 + u1 + 0x78787878u, one, add_fma(u2, one, u3));
+    return u0 + u1 + u2 + u3 + 0x78787878u;
+}
 
 // exact response of the pixel at c (ChESS.c:62-105), read straight from global memory
 __device__ __forceinline__ int chess_exact(const uint8_t* __restrict__ c, int pitch)
@@ -163,7 +185,7 @@ __device__ __forceinline__ void l3_phase(const StripCtx& c, WarpQueues* q, uint3
         int r = 0, x = 0, y = 0;
         if ((uint32_t)lane < n)
         {
-            const uint32_t ent = q->l3q[(l3_head + lane) & (kL3QCap - 1)];
+            const uint32_t ent = q->l3q[(l3_head + lane) % kL3QCap];
             x = ent & 0xFFFF; y = ent >> 16;
             r = chess_exact(c.img + (size_t)y * c.pitch + x, c.pitch);
         }
@@ -203,7 +225,7 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
 {
     if ((uint32_t)lane < n)
     {
-        const uint32_t u = q->l2q[(head + lane) & (kL2QCap - 1)];
+        const uint32_t u = q->l2q[(head + lane) % kL2QCap];
         const int col = u & 31, j = 31 - __clz(u >> 5);
         const bool cur = (int)(head + lane - L.mark) >= 0;
         const uint32_t sA = (cur ? L.off0 : L.off1) + c.cell_pitch * col, sB = (cur ? L.off1 : L.off2) + c.cell_pitch * col;
@@ -255,7 +277,7 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
                 if (x >= kMargin && x < c.w - kMargin)
                 {
                     const uint32_t pos = atomicAdd(&q->l3_tail, 1u);
-                    q->l3q[pos & (kL3QCap - 1)] = ((uint32_t)y << 16) | (uint32_t)x;
+                    q->l3q[pos % kL3QCap] = ((uint32_t)y << 16) | (uint32_t)x;
                 }
             }
         }
@@ -263,8 +285,11 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
     __syncwarp();
 }
 
-template<int NW>
-__global__ void __launch_bounds__(NW * 32, 5)     // shared memory already limits a SM to 5 CTAs of 3 warps; the hint lets ptxas keep ~96 registers for scheduling
+// MINB = CTAs per SM the register allocation aims at. The register file is per scheduler (16384 registers, i.e.
+// five warps of 96 registers): 3-warp CTAs reach 6 per SM (18 warps) at <= 96 registers and 7 per SM (21 warps,
+// one scheduler hosts six of them) only at <= 80.
+template<int NW, int SUMS, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, CascadeParams tp,
                      cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
 {
@@ -392,8 +417,8 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
             // lane can wrap, i.e. every chord <= 31 (4*31 + 0x78 < 256). That is what ha/hb guarantee: the
             // sum of all sixteen chord bytes of a word (IDP.4A against 1,1,1,1 -- FMA pipe, which idles
             // otherwise) is < 32. A word with ha >= 32 holds a chord sum >= 8 anyway and is flagged.
-            const uint32_t sa = u0a + u1a + u2a + u3a + 0x78787878u;
-            const uint32_t sb = u0b + u1b + u2b + u3b + 0x78787878u;
+            const uint32_t sa = packed_sum4<SUMS>(u0a, u1a, u2a, u3a, tp.one);
+            const uint32_t sb = packed_sum4<SUMS>(u0b, u1b, u2b, u3b, tp.one);
             const int ha = dp4a_us(u3a, 0x01010101, dp4a_us(u2a, 0x01010101, dp4a_us(u1a, 0x01010101, dp4a_us(u0a, 0x01010101, 0))));
             const int hb = dp4a_us(u3b, 0x01010101, dp4a_us(u2b, 0x01010101, dp4a_us(u1b, 0x01010101, dp4a_us(u0b, 0x01010101, 0))));
             if ((((sa | sb) & 0x80808080u) | ((uint32_t)(ha | hb) & ~31u)) != 0) flagbits |= 1u << j;
@@ -411,12 +436,13 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
         {
             // unit = one-hot row bit << 5 | lane column (the consumer finds the row; which block a unit
             // belongs to follows from its position in the queue)
-            uint32_t pos = atomicAdd(&q->l2_tail, (uint32_t)__popc(flagbits));
+            uint32_t pos = atomicAdd(&q->l2_tail, (uint32_t)__popc(flagbits)) % kL2QCap;
             do
             {
                 const uint32_t low = flagbits & (0u - flagbits);
                 flagbits ^= low;
-                q->l2q[pos++ & (kL2QCap - 1)] = (uint16_t)(low * 32u + (uint32_t)lane);
+                q->l2q[pos] = (uint16_t)(low * 32u + (uint32_t)lane);
+                if (++pos == kL2QCap) pos = 0;
             } while (flagbits);
         }
         __syncwarp();
@@ -478,7 +504,7 @@ bool make_cascade_map(CUtensorMap* map, const FrameSet& fs, int row_bytes)
     return r == CUDA_SUCCESS;
 }
 
-template<int NW>
+template<int NW, int SUMS, int MINB>
 cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32_t* counts, cudaStream_t stream, bool* ok)
 {
     using G = Geo<NW>;
@@ -490,12 +516,12 @@ cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32
     if (smem > 48 * 1024)
     {
         // per device, idempotent and cheap: set on every launch rather than tracking devices
-        cudaError_t e = cudaFuncSetAttribute(chess_cascade_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(chess_cascade_kernel<NW, SUMS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const long long items = (long long)fs.nframes * tp.nstrips * tp.nsegs;
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
-    chess_cascade_kernel<NW><<<(unsigned)items, NW * 32, smem, stream>>>(map, fs, tp, cand, counts);
+    chess_cascade_kernel<NW, SUMS, MINB><<<(unsigned)items, NW * 32, smem, stream>>>(map, fs, tp, cand, counts);
     return cudaGetLastError();
 }
 
@@ -548,11 +574,22 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     tp.seg_rows = seg_rows;
     tp.nsegs = (out_rows + seg_rows - 1) / seg_rows;
 
-    switch (nw)
+    tp.one = 1;
+    const int sums = env_int("MRG_B200_K1_SUMS", 0, 0, 2);
+    const int minb = env_int("MRG_B200_K1_MINB", 5, 5, 7);
+    if (nw == 1) return launch_nw<1, 0, 5>(fs, tp, cand, counts, stream, launched);
+    if (nw == 2) return launch_nw<2, 0, 5>(fs, tp, cand, counts, stream, launched);
+    switch (minb * 4 + sums)
     {
-    case 1:  return launch_nw<1>(fs, tp, cand, counts, stream, launched);
-    case 2:  return launch_nw<2>(fs, tp, cand, counts, stream, launched);
-    default: return launch_nw<3>(fs, tp, cand, counts, stream, launched);
+    case 21: return launch_nw<3, 1, 5>(fs, tp, cand, counts, stream, launched);
+    case 22: return launch_nw<3, 2, 5>(fs, tp, cand, counts, stream, launched);
+    case 24: return launch_nw<3, 0, 6>(fs, tp, cand, counts, stream, launched);
+    case 25: return launch_nw<3, 1, 6>(fs, tp, cand, counts, stream, launched);
+    case 26: return launch_nw<3, 2, 6>(fs, tp, cand, counts, stream, launched);
+    case 28: return launch_nw<3, 0, 7>(fs, tp, cand, counts, stream, launched);
+    case 29: return launch_nw<3, 1, 7>(fs, tp, cand, counts, stream, launched);
+    case 30: return launch_nw<3, 2, 7>(fs, tp, cand, counts, stream, launched);
+    default: return launch_nw<3, 0, 5>(fs, tp, cand, counts, stream, launched);
     }
 }
 

@@ -411,3 +411,24 @@ def test_full_size_symmetry_properties(api):
     a = np.sort(xy[0, :100, 0]); b = np.sort((3839 * 1000) - xy[1, :100, 0])
     assert np.abs(a - b).max() <= 100
     det.close()
+
+
+def test_candidate_lists_equal_the_oracles_dense_response(api, oracle):
+    """mrg_b200_chess_candidates_batch (the production ChESS kernel alone): the set {(x, y, r) : r > 15} of every
+    frame equals the one read off the oracle's dense response, at levels 0 and 1, on boards, noise and checkers."""
+    for (w, h) in ((640, 480), (1537, 70), (799, 150)):
+        frames = np.stack([synth.board_frame(w, h, 6, seed=7), synth.noise_frame(w, h, seed=8),
+                           synth.checker_frame(w, h, period=6, seed=9), synth.blurred_noise_frame(w, h, seed=10, passes=1)])
+        det = api.Detector(max_frames=3, candidate_capacity=1 << 18)          # two chunks
+        for level in (0, 1):
+            counts, cand = det.chess_candidates(frames, level, cand_cap=1 << 18)
+            for i, f in enumerate(frames):
+                img = f if level == 0 else oracle.pyramid(f, level)
+                r = oracle.chess_response_5(img, fill=0).astype(np.int64)
+                hh, ww = img.shape
+                ys, xs = np.nonzero(r[7:hh - 7, 7:ww - 7] > 15) if hh > 14 and ww > 14 else (np.zeros(0, int), np.zeros(0, int))
+                ys, xs = ys + 7, xs + 7
+                want = np.sort((ys.astype(np.uint64) << np.uint64(32)) | (xs.astype(np.uint64) << np.uint64(16)) | r[ys, xs].astype(np.uint64))
+                assert counts[i] == len(want), (w, h, level, i)
+                assert np.array_equal(np.sort(cand[i, :counts[i]]), want), (w, h, level, i)
+        det.close()

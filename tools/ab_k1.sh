@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 out=gpurun_out/ab_k1.txt
 : > $out
 for cfg in "$@"; do
-  line=$(env $cfg timeout 120 python bench.py --frames ${AB_FRAMES:-2048} --chunk ${AB_CHUNK:-512} --steps 6 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | tail -1)
+  line=$(env $cfg timeout 120 python bench.py --frames ${AB_FRAMES:-2048} --chunk ${AB_CHUNK:-512} --steps 6 --warmup 3 --no-e2e --no-cpu-baseline --no-content --sustain-seconds 0 --base-frames 8 --no-overlap 2>/dev/null | tail -1)
   echo "$line" | python -c "
 import sys, json
 cfg = sys.argv[1]

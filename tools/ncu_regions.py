@@ -29,3 +29,13 @@ for a in range(0, len(data), chunk):
     if e == 0 and s == 0: continue
     nv = sum(1 for d in ch if 'VABSDIFF4' in d[0]); nl = sum(1 for d in ch if 'LDG' in d[0]); ns = sum(1 for d in ch if 'SYNCS' in d[0])
     print(f"{a:5d} inst {e/tot*100:5.1f}% samples {s/tots*100:5.1f}% thr/inst {t/max(e,1):5.1f} vabs {nv} ldg {nl} syncs {ns}")
+# dynamic opcode histogram: executed warp-instructions per SASS opcode (which pipe the issue slots go to)
+import re, collections
+hist = collections.Counter(); samp = collections.Counter()
+for srcline, e, t, s in data:
+    m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", srcline)
+    op = m.group(2) if m else "?"
+    hist[op] += e; samp[op] += s
+print("opcode            warp-inst     share   stall-samples share")
+for op, e in hist.most_common(28):
+    print(f"{op:14s} {e:12d} {e/max(tot,1)*100:8.2f}% {samp[op]/max(tots,1)*100:10.2f}%")
