@@ -51,9 +51,11 @@ namespace
 {
 constexpr int kLanePx   = 8;                   // pixels per lane
 constexpr int kWarpPx   = 32 * kLanePx;        // 256
-constexpr int kCHalo    = 8;                   // staged bytes left/right of the strip: the ring reaches 5 pixels, lanes read aligned 8-byte cells
+constexpr int kCHalo    = 16;                  // staged bytes left/right of the strip: the ring needs 5 + the lanes' aligned 8-byte cells, and a
+                                               // TMA box must start on a 16-byte boundary of global memory (anything else is an illegal instruction)
 constexpr int kBlkRows  = 11;                  // rows per TMA stage == unroll of the row loop == register window
-constexpr int kL2QCap   = 384;                 // per-warp queue of flagged 8-pixel row cells (>= 31 carried + 352 of one block)
+constexpr int kL2QCarry = 384;                 // per-warp queue of flagged 8-pixel row cells: >= 31 carried over + 352 of one block ...
+constexpr int kL2QBlock = 352;                 // ... or one block's worth when nothing is carried (the queue then restarts at 0 every block)
 constexpr int kL3QCap   = 288;                 // per-warp queue of pixels for the exact test (>= 31 waiting + 256 of one L2 batch)
 
 template<int NW> struct Geo
@@ -68,19 +70,20 @@ struct CascadeParams
     int nstrips, nsegs, seg_rows;   // work decomposition: item = (frame, segment, strip)
     int cap;
     int stages;                     // depth of the shared-memory ring (TMA stages of 11 rows)
-    int nocarry;                    // 1: settle every flagged cell in its own block (2 stages held instead of 3)
     uint32_t one;                   // the constant 1, opaque to the compiler: x*one + y is an integer add on the FMA pipe
 };
 
 // head/tail count entries since the CTA started (a CTA never queues anywhere near 2^32 of them); the slot of
 // entry p is p % cap. The capacities are not powers of two: every KB of shared memory per warp decides how many
 // CTAs fit a SM.
-struct WarpQueues
+// CARRY: flagged cells that do not fill a batch of 32 wait for the next block's (three staged blocks are then held,
+// four stages needed); !CARRY: every block settles its own cells, the last batch partly empty (two held, three stages).
+template<bool CARRY> struct WarpQueues
 {
+    static constexpr int kL2QCap = CARRY ? kL2QCarry : kL2QBlock;
     uint32_t l3q[kL3QCap];
     uint16_t l2q[kL2QCap];
     uint32_t l2_tail, l3_tail;
-    uint32_t pad[2];
 };
 
 // mbarrier wait as a plain C loop around try_wait, executed by whole warps: no branch hidden from
@@ -175,7 +178,8 @@ struct StripCtx
 };
 
 // L3: exact test of queued pixels, 32 at a time (all of them when `final`).
-__device__ __forceinline__ void l3_phase(const StripCtx& c, WarpQueues* q, uint32_t& l3_head, bool final, int lane)
+template<class Q>
+__device__ __forceinline__ void l3_phase(const StripCtx& c, Q* q, uint32_t& l3_head, bool final, int lane)
 {
     __syncwarp();
     const uint32_t tail = *(volatile uint32_t*)&q->l3_tail;
@@ -221,11 +225,12 @@ struct L2Ctx
     int row_bytes;
 };
 
-__device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, WarpQueues* q, uint32_t head, uint32_t n, int lane)
+template<class Q>
+__device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Q* q, uint32_t head, uint32_t n, int lane)
 {
     if ((uint32_t)lane < n)
     {
-        const uint32_t u = q->l2q[(head + lane) % kL2QCap];
+        const uint32_t u = q->l2q[(head + lane) % Q::kL2QCap];
         const int col = u & 31, j = 31 - __clz(u >> 5);
         const bool cur = (int)(head + lane - L.mark) >= 0;
         const uint32_t sA = (cur ? L.off0 : L.off1) + c.cell_pitch * col, sB = (cur ? L.off1 : L.off2) + c.cell_pitch * col;
@@ -288,7 +293,7 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Warp
 // MINB = CTAs per SM the register allocation aims at. The register file is per scheduler (16384 registers, i.e.
 // five warps of 96 registers): 3-warp CTAs reach 6 per SM (18 warps) at <= 96 registers and 7 per SM (21 warps,
 // one scheduler hosts six of them) only at <= 80.
-template<int NW, int SUMS, int MINB>
+template<int NW, int SUMS, int MINB, bool CARRY>
 __global__ void __launch_bounds__(NW * 32, MINB)
 chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, CascadeParams tp,
                      cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
@@ -299,7 +304,8 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
     uint8_t*  ring      = smem;
     uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + (size_t)tp.stages * G::kStageBytes);
     uint32_t* released  = reinterpret_cast<uint32_t*>(full_bar + tp.stages);     // warps done with the stage's current block
-    WarpQueues* queues  = reinterpret_cast<WarpQueues*>(released + ((tp.stages + 3) & ~3));
+    using Q = WarpQueues<CARRY>;
+    Q* queues = reinterpret_cast<Q*>(released + ((tp.stages + 3) & ~3));
 
     const int tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
     const int nst = tp.stages;
@@ -308,7 +314,7 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
         for (int s = 0; s < nst; s++) { mbar_init(&full_bar[s], 1); released[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    WarpQueues* q = &queues[wi];
+    Q* q = &queues[wi];
     if (lane == 0) { q->l2_tail = 0; q->l3_tail = 0; }
     __syncthreads();
 
@@ -436,13 +442,14 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
         {
             // unit = one-hot row bit << 5 | lane column (the consumer finds the row; which block a unit
             // belongs to follows from its position in the queue)
-            uint32_t pos = atomicAdd(&q->l2_tail, (uint32_t)__popc(flagbits)) % kL2QCap;
+            uint32_t pos = atomicAdd(&q->l2_tail, (uint32_t)__popc(flagbits));
+            if (CARRY) pos %= Q::kL2QCap;          // (without carry the queue restarts at 0 every block: no wrap)
             do
             {
                 const uint32_t low = flagbits & (0u - flagbits);
                 flagbits ^= low;
                 q->l2q[pos] = (uint16_t)(low * 32u + (uint32_t)lane);
-                if (++pos == kL2QCap) pos = 0;
+                if (++pos == Q::kL2QCap) pos = 0;
             } while (flagbits);
         }
         __syncwarp();
@@ -456,16 +463,23 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
             q_head += 32u;
             l3_phase(c, q, l3_head, false, lane);
         }
-        if ((int)(prev_mark - q_head) > 0 || (tp.nocarry && tail != q_head))
+        if ((int)(prev_mark - q_head) > 0 || (!CARRY && tail != q_head))
         {
             l2_batch(c, L, q, q_head, tail - q_head, lane);
             q_head = tail;
             l3_phase(c, q, l3_head, false, lane);
         }
         prev_mark = tail;
+        if (!CARRY)
+        {
+            // the queue is empty: the next block's cells start at position 0 again
+            __syncwarp();
+            if (lane == 0) q->l2_tail = 0;
+            q_head = 0; prev_mark = 0;
+        }
         // every cell of block it-1 is settled: this warp is done with the stage of block it-2
         // (of block it-1 when cells are never carried over)
-        const int hold = tp.nocarry ? 1 : 2;
+        constexpr int hold = CARRY ? 2 : 1;
         if (it >= hold) { release(it - hold, s_rel); if (++s_rel == nst) s_rel = 0; }
         if (++s == nst) { s = 0; full_parity ^= 1; }
     }
@@ -504,7 +518,7 @@ bool make_cascade_map(CUtensorMap* map, const FrameSet& fs, int row_bytes)
     return r == CUDA_SUCCESS;
 }
 
-template<int NW, int SUMS, int MINB>
+template<int NW, int SUMS, int MINB, bool CARRY>
 cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32_t* counts, cudaStream_t stream, bool* ok)
 {
     using G = Geo<NW>;
@@ -512,16 +526,16 @@ cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32
     *ok = make_cascade_map(&map, fs, G::kRowBytes);
     if (!*ok) return cudaSuccess;
     const size_t smem = (size_t)tp.stages * G::kStageBytes + tp.stages * sizeof(uint64_t) + ((tp.stages + 3) & ~3) * sizeof(uint32_t) +
-                        NW * sizeof(WarpQueues);
+                        NW * sizeof(WarpQueues<CARRY>);
     if (smem > 48 * 1024)
     {
         // per device, idempotent and cheap: set on every launch rather than tracking devices
-        cudaError_t e = cudaFuncSetAttribute(chess_cascade_kernel<NW, SUMS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(chess_cascade_kernel<NW, SUMS, MINB, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const long long items = (long long)fs.nframes * tp.nstrips * tp.nsegs;
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
-    chess_cascade_kernel<NW, SUMS, MINB><<<(unsigned)items, NW * 32, smem, stream>>>(map, fs, tp, cand, counts);
+    chess_cascade_kernel<NW, SUMS, MINB, CARRY><<<(unsigned)items, NW * 32, smem, stream>>>(map, fs, tp, cand, counts);
     return cudaGetLastError();
 }
 
@@ -554,8 +568,8 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     tp.cap = cand_capacity;
     // a stage is handed back two blocks after it was consumed (L2 reads it), so 3 stages are always held
     // tuning knobs (defaults are what bench.py measures): MRG_B200_K1_NW, MRG_B200_K1_STAGES, MRG_B200_K1_NOCARRY
-    tp.nocarry = env_int("MRG_B200_K1_NOCARRY", 0, 0, 1);
-    tp.stages = env_int("MRG_B200_K1_STAGES", 4, tp.nocarry ? 3 : 4, 12);
+    const int nocarry = env_int("MRG_B200_K1_NOCARRY", 0, 0, 1);
+    tp.stages = env_int("MRG_B200_K1_STAGES", nocarry ? 3 : 4, nocarry ? 3 : 4, 12);
     const int sw = kWarpPx * nw;
     tp.nstrips = (fs.w - kMargin + sw - 1) / sw;
     const int out_rows = fs.h - 2*kMargin;
@@ -577,20 +591,20 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     tp.one = 1;
     const int sums = env_int("MRG_B200_K1_SUMS", 0, 0, 2);
     const int minb = env_int("MRG_B200_K1_MINB", 5, 5, 7);
-    if (nw == 1) return launch_nw<1, 0, 5>(fs, tp, cand, counts, stream, launched);
-    if (nw == 2) return launch_nw<2, 0, 5>(fs, tp, cand, counts, stream, launched);
+    // Variants (the defaults are what bench.py measures): carry / no carry (4 / 3 stages), where the packed sums of L1
+    // run, and the register target (5: 96 registers, 6: 88, 7: 80 -- CTAs per SM follow from shared memory)
+    if (nw == 1) return nocarry ? launch_nw<1, 0, 5, false>(fs, tp, cand, counts, stream, launched) : launch_nw<1, 0, 5, true>(fs, tp, cand, counts, stream, launched);
+    if (nw == 2) return nocarry ? launch_nw<2, 0, 5, false>(fs, tp, cand, counts, stream, launched) : launch_nw<2, 0, 5, true>(fs, tp, cand, counts, stream, launched);
+#define K1_CASE(S, M) case (M) * 4 + (S): return nocarry ? launch_nw<3, S, M, false>(fs, tp, cand, counts, stream, launched) \
+                                                         : launch_nw<3, S, M, true>(fs, tp, cand, counts, stream, launched);
     switch (minb * 4 + sums)
     {
-    case 21: return launch_nw<3, 1, 5>(fs, tp, cand, counts, stream, launched);
-    case 22: return launch_nw<3, 2, 5>(fs, tp, cand, counts, stream, launched);
-    case 24: return launch_nw<3, 0, 6>(fs, tp, cand, counts, stream, launched);
-    case 25: return launch_nw<3, 1, 6>(fs, tp, cand, counts, stream, launched);
-    case 26: return launch_nw<3, 2, 6>(fs, tp, cand, counts, stream, launched);
-    case 28: return launch_nw<3, 0, 7>(fs, tp, cand, counts, stream, launched);
-    case 29: return launch_nw<3, 1, 7>(fs, tp, cand, counts, stream, launched);
-    case 30: return launch_nw<3, 2, 7>(fs, tp, cand, counts, stream, launched);
-    default: return launch_nw<3, 0, 5>(fs, tp, cand, counts, stream, launched);
+    K1_CASE(1, 5) K1_CASE(2, 5)
+    K1_CASE(0, 6) K1_CASE(1, 6) K1_CASE(2, 6)
+    K1_CASE(0, 7) K1_CASE(1, 7) K1_CASE(2, 7)
+    default: return nocarry ? launch_nw<3, 0, 5, false>(fs, tp, cand, counts, stream, launched) : launch_nw<3, 0, 5, true>(fs, tp, cand, counts, stream, launched);
     }
+#undef K1_CASE
 }
 
 }
