@@ -9,403 +9,574 @@
 //   border following with a zero frame around the image; per contour: polygon moments, area /
 //   inertia / convexity / colour filters, centre, median radius; then grouping across thresholds.
 //
-// GPU decomposition (all 17 thresholds of all frames of a chunk in flight at once):
-//   B1 blob_binarize_kernel  gray -> 17 bit planes per frame (one pass over the frame, 1 B/px read)
-//   B2 blob_trace_kernel     one thread per (frame, threshold) replays OpenCV's raster scan and
-//                            border following on the bit plane. The scan visits only horizontal 0/1
-//                            transitions (32 pixels per word op); the pixel states of the original
-//                            (1 = untouched, 2 = visited, -126 = visited + "east neighbour examined
-//                            and zero") live in two more bit planes. While following a border it
-//                            accumulates the polygon moments as exact 64-bit integers (Green's
-//                            theorem terms are integers; order does not matter) and stores the
-//                            points; borders whose area is outside [20, 80000) are dropped at once.
-//   B3 blob_contour_kernel   one CTA per surviving border: convex-hull area from per-column
-//                            extremes (exact integers), colour test at the rounded centre, median
-//                            point distance by radix selection on the IEEE bit patterns.
-//   host                     the remaining double arithmetic (inertia, convexity ratio) and the
-//                            grouping across thresholds, a few hundred centres per frame, in the
-//                            reference's operation order (no FMA contraction: see build.py).
+// GPU decomposition (all 17 thresholds of all frames of a chunk in flight at once). Border following is
+// NOT replayed sequentially with pixel marks: blob_walk.cuh states (and tests/test_blob_walk_host.py
+// checks against the Suzuki-Abe restatement) the equivalent mark-free formulation -- borders are the
+// cycles of a successor function on (pixel, direction) states, and the raster scan discovers each cycle
+// at its raster-first state -- so every border is followed by its own lane:
+//   B1  blob_binarize_kernel   gray -> 17 bit planes per frame (one pass over the frame, 1 B/px read):
+//                              a thread bit-slices 32 pixels once, each plane is then a handful of word ops
+//   B2a blob_walk_kernel       persistent warps scan the planes tile by tile for candidate first pixels
+//                              of components / holes (word ops); each lane takes a candidate and sends two
+//                              walkers around its border in opposite directions, which either meet (the
+//                              candidate is where OpenCV's scan discovers that border: a record with the
+//                              border's length and exact area is emitted if the area passes the filter)
+//                              or run into a state the scan meets earlier (not the start: dropped).
+//                              Lanes refill from a per-warp list; no marks, no per-plane sequential pass.
+//   B2b blob_points_kernel     one lane per kept border walks it once more: stores its points and sums the
+//                              remaining Green's-theorem moments and the bounding box (exact integers).
+//   B3  blob_contour_warp_kernel  one warp per kept border: convex-hull area from per-column extremes,
+//                              centre, colour test, median point distance by radix selection on the IEEE
+//                              bit patterns, all in the warp's slice of shared memory;
+//       blob_contour_kernel    the same with one CTA and global scratch, for borders too long for that slice
+//   host                       the remaining double arithmetic (inertia, convexity ratio) and the
+//                              grouping across thresholds, a few hundred centres per frame, in the
+//                              reference's operation order (no FMA contraction: see build.py), frames
+//                              spread over host threads.
 #include <cuda_runtime.h>
 #include <float.h>
+#include <limits.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
+#include "blob_walk.cuh"
 
 namespace mrgb200
 {
 namespace
 {
+using namespace blobwalk;
+
 constexpr int kNThr = 17;                       // thresholds 50, 60, ..., 210 (min 50, max 220, step 10)
-__host__ __device__ inline int thr_value(int k) { return 50 + 10 * k; }
+__host__ __device__ constexpr int thr_value(int k) { return 50 + 10 * k; }
 
 struct BlobRecord
 {
-    int frame, thr, seq, n;                     // seq = discovery order among the survivors of (frame, thr)
-    unsigned pts_off;                           // first point, within the (frame, thr) point region
+    int frame, thr, seq, n;                     // seq = position y*w + x at which the raster scan discovers the border
+    unsigned pts_off;                           // first point, within the chunk's point region
+    int sx, sy, sk;                             // the state the border is followed from (blob_walk.cuh)
     int xmin, xmax, ymin, ymax;
     long long a00, a10, a01, a20, a11, a02;     // Green's-theorem sums over the directed border edges
     long long hull2;                            // twice the convex hull's area
     double cx, cy, radius;
-    int colour_ok, pad;
+    int colour_ok, big;                         // big: left to the CTA-per-border kernel
 };
 
 struct BlobGeom
 {
     int w, h, wpr;                              // pixels, 32-bit words per bit-plane row
     int nframes;
-    unsigned pts_cap;                           // points per (frame, thr) region
+    unsigned pts_cap;                           // points of the whole chunk
     unsigned rec_cap;
 };
 
+// device counters (uint32 each)
+enum { kCntRecords = 0, kCntStatus = 1, kCntPoints = 2, kCntTile = 3, kCntPointJob = 4, kCntWords = 8 };
+
 // ------------------------------------------------------------------------------------------------
 // B1: bit planes. plane(f,k)[y][wd] bit b = gray(f, y, 32*wd + b) > thr_k
+// A thread owns 32 pixels: two 128-bit loads, bytes regrouped so that word j holds pixels j, j+8, j+16,
+// j+24 (PRMT), then eight bit slices S_b (bit i = bit b of pixel i); "pixel > constant" on slices is one
+// AND or OR per bit of the constant, 32 pixels at a time.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t slices_gt(const uint32_t (&S)[8], int t)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) r = ((t >> b) & 1) ? (S[b] & r) : (S[b] | r);
+    return r;
+}
+
 __global__ void __launch_bounds__(128)
-blob_binarize_kernel(FrameSet fs, BlobGeom g, uint32_t* __restrict__ planes)
+blob_binarize_kernel(FrameSet fs, BlobGeom g, uint32_t* __restrict__ planes, int aligned)
 {
     const int wd = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
     if (wd >= g.wpr) return;
     const uint8_t* row = fs.base + (size_t)f * fs.frame_stride + (size_t)y * fs.pitch;
-    uint8_t v[32];
     const int x0 = wd * 32;
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = x0 + i < g.w ? row[x0 + i] : 0;
-    for (int k = 0; k < kNThr; k++)
+    uint32_t W[8];
+    if (aligned)
     {
-        const int t = thr_value(k);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int i = 0; i < 32; i++) bits |= (uint32_t)(v[i] > t) << i;
-        planes[(((size_t)f * kNThr + k) * g.h + y) * g.wpr + wd] = bits;
+        uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+        if (x0 < g.w)      a = *reinterpret_cast<const uint4*>(row + x0);          // rows are multiples of 16 bytes long:
+        if (x0 + 16 < g.w) b = *reinterpret_cast<const uint4*>(row + x0 + 16);     // a vector that starts inside ends inside
+        W[0] = a.x; W[1] = a.y; W[2] = a.z; W[3] = a.w; W[4] = b.x; W[5] = b.y; W[6] = b.z; W[7] = b.w;
     }
+    else
+    {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            uint32_t v = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (x0 + 4*j + i < g.w) v |= (uint32_t)row[x0 + 4*j + i] << (8 * i);
+            W[j] = v;
+        }
+    }
+    if (x0 + 32 > g.w)
+    {
+        // pixels beyond the width are background in every plane
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            const int valid = g.w - (x0 + 4*j);
+            W[j] &= valid >= 4 ? ~0u : (valid > 0 ? (1u << (8 * valid)) - 1u : 0u);
+        }
+    }
+    uint32_t S[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) S[b] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+    {
+        // U = pixels j, j+8, j+16, j+24 in bytes 0..3
+        const int a = j >> 2, bsel = j & 3;
+        const uint32_t t1 = __byte_perm(W[a], W[a + 2], bsel | ((4 + bsel) << 4));
+        const uint32_t t2 = __byte_perm(W[a + 4], W[a + 6], bsel | ((4 + bsel) << 4));
+        const uint32_t U = __byte_perm(t1, t2, 0x5410);
+#pragma unroll
+        for (int b = 0; b < 8; b++)
+        {
+            const uint32_t sh = j >= b ? U << (j - b) : U >> (b - j);               // bit b of byte i -> bit 8i + j
+            S[b] |= sh & (0x01010101u << j);
+        }
+    }
+    uint32_t* out = planes + ((size_t)f * kNThr * g.h + y) * g.wpr + wd;
+    const size_t plane_words = (size_t)g.h * g.wpr;
+#pragma unroll
+    for (int k = 0; k < kNThr; k++) out[(size_t)k * plane_words] = slices_gt(S, thr_value(k));
 }
 
 // ------------------------------------------------------------------------------------------------
-// B2: raster scan + border following, one thread per (frame, threshold)
+// B2a: candidate starts + verification walk (see blob_walk.cuh)
 // ------------------------------------------------------------------------------------------------
-__constant__ int kDx[8] = { 1, 1, 0, -1, -1, -1, 0, 1 };     // 0 = east, then counter-clockwise on the screen
-__constant__ int kDy[8] = { 0, -1, -1, -1, 0, 1, 1, 1 };
+constexpr int kTileRows  = 16;                  // a tile = 32 words (1024 pixels) x 16 rows of one plane
+constexpr int kListCap   = 2048;                // per-warp candidate list; a row adds at most 1024
+constexpr int kWalkWarps = 4;
+constexpr unsigned kFull = 0xffffffffu;
 
-// One thread's view of its bit planes. The thread keeps, in registers, the 3 x 3 words of B around
-// its position (rows cy-1..cy+1, words cwd-1..cwd+1) and the V/R words it is marking (written back
-// when it moves to another word): while a border is followed most steps need no load at all, a
-// vertical step needs one round of three independent loads.
-struct Plane
+__global__ void __launch_bounds__(kWalkWarps * 32)
+blob_walk_kernel(BlobGeom g, const uint32_t* __restrict__ planes, BlobRecord* __restrict__ recs,
+                 unsigned* __restrict__ counters, unsigned ntiles, int nstrips, int ncb)
 {
-    const uint32_t* B; uint32_t* V; uint32_t* R;
-    int w, h, wpr;
-    int cy, cwd; uint32_t b[3][3];
-    int my, mwd; uint32_t vword, rword; bool dirty;
+    __shared__ uint16_t s_list[kWalkWarps][kListCap];
+    const int lane = threadIdx.x & 31;
+    uint16_t* list = s_list[threadIdx.x >> 5];
+    const size_t plane_words = (size_t)g.h * g.wpr;
+    const long long max_steps = 4LL * g.w * g.h + 16;
 
-    __device__ __forceinline__ void init() { cy = -0x40000000; cwd = -2; my = -1; mwd = -1; vword = rword = 0; dirty = false; }
-    __device__ __forceinline__ void load_row(int slot, int y)
-    {
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-        {
-            const int wc = cwd - 1 + c;
-            b[slot][c] = ((unsigned)y < (unsigned)h && (unsigned)wc < (unsigned)wpr) ? B[(size_t)y * wpr + wc] : 0u;
-        }
-    }
-    __device__ __forceinline__ void seek(int x, int y)
-    {
-        const int wd = x >> 5;
-        if (wd == cwd && y == cy) return;
-        if (wd == cwd && y == cy + 1)
-        {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { b[0][c] = b[1][c]; b[1][c] = b[2][c]; }
-            cy = y; load_row(2, y + 1);
-        }
-        else if (wd == cwd && y == cy - 1)
-        {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { b[2][c] = b[1][c]; b[1][c] = b[0][c]; }
-            cy = y; load_row(0, y - 1);
-        }
-        else
-        {
-            cwd = wd; cy = y;
-            load_row(0, y - 1); load_row(1, y); load_row(2, y + 1);
-        }
-    }
-    // bits (x-1, x, x+1) of a cached row as bits 0..2
-    __device__ __forceinline__ uint32_t row3(int slot, int bpos) const
-    {
-        const unsigned long long w64 = ((unsigned long long)b[slot][1] << 32) | b[slot][0];
-        uint32_t v = (uint32_t)(w64 >> (31 + bpos)) & 7u;
-        if (bpos == 31) v |= (b[slot][2] & 1u) << 2;
-        return v;
-    }
-    // bit d = the neighbour of (x, y) in direction d (0 = E, 1 = NE, 2 = N, 3 = NW, 4 = W, 5 = SW, 6 = S, 7 = SE) is foreground
-    __device__ __forceinline__ uint32_t nbr8(int x, int y)
-    {
-        seek(x, y);
-        const int bpos = x & 31;
-        const uint32_t up = row3(0, bpos), mid = row3(1, bpos), dn = row3(2, bpos);
-        return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) |
-               ((mid & 1u) << 4) | ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
-    }
-    // mark words: write-back cache of one V word and one R word
-    __device__ __forceinline__ void flush_marks()
-    {
-        if (dirty) { V[(size_t)my * wpr + mwd] = vword; R[(size_t)my * wpr + mwd] = rword; dirty = false; }
-    }
-    __device__ __forceinline__ void seek_marks(int x, int y)
-    {
-        const int wd = x >> 5;
-        if (wd == mwd && y == my) return;
-        flush_marks();
-        my = y; mwd = wd;
-        vword = V[(size_t)y * wpr + wd]; rword = R[(size_t)y * wpr + wd];
-    }
-    __device__ __forceinline__ bool visited(int x, int y) { seek_marks(x, y); return (vword >> (x & 31)) & 1u; }
-    __device__ __forceinline__ bool rflag(int x, int y)   { seek_marks(x, y); return (rword >> (x & 31)) & 1u; }
-    __device__ __forceinline__ void set_visited(int x, int y) { seek_marks(x, y); vword |= 1u << (x & 31); dirty = true; }
-    __device__ __forceinline__ void set_rflag(int x, int y)   { seek_marks(x, y); rword |= 1u << (x & 31); dirty = true; }
-};
+    // the warp's candidate source (warp-uniform): a list of entries found in rows [.., tile_row) of the current tile
+    unsigned list_n = 0, list_head = 0;
+    int tile_row = 0, tile_rows = 0, tjob = 0, ty0 = 0, twd0 = 0;
+    bool src_done = false;
+    uint32_t up = 0, upl = 0, upr = 0;          // this lane's words of the row above the next one to scan
+    const uint32_t* TB = planes;                // plane of the current tile
 
-struct Tracer
-{
-    Plane P;
-    uint32_t* pts; unsigned npts, pts_cap;
-    BlobRecord* recs; unsigned* rec_count; unsigned rec_cap;
-    int* status;
-    int frame, thr, seq;
+    // the lane's border
+    bool active = false;
+    PlaneRef P; P.B = planes; P.w = g.w; P.h = g.h; P.wpr = g.wpr;
+    BitWindow F, Bk;
+    int fx = 0, fy = 0, fk = 0, bx = 0, by = 0, bk = 0, pos = 0, cnt = 0, sx = 0, sy = 0, sk = 0, job = 0;
+    long long a00 = 0;
 
-    // follow the border that starts at (x0, y0); false = out of space
-    __device__ __forceinline__ bool trace(int x0, int y0, bool is_hole)
+    for (;;)
     {
-        const unsigned start = npts;
-        // Only the area term is accumulated here (it decides at once whether the border is kept); the
-        // other moments and the bounding box are summed over the stored points, in parallel, by B3.
-        long long a00 = 0;
-        int fx = x0, fy = y0, px = x0, py = y0;          // first / previous emitted point
-        int n = 0;
-        auto emit = [&](int x, int y) -> bool
+        unsigned idle = __ballot_sync(kFull, !active);
+        while (idle && !src_done)
         {
-            if (npts >= pts_cap) return false;
-            pts[npts++] = (uint32_t)x | ((uint32_t)y << 16);
-            a00 += px * y - x * py;                      // coordinates < 2^15: the products fit 32 bits
-            px = x; py = y; n++;
-            return true;
-        };
-
-        // neighbour search on an 8-bit mask of the 3x3 neighbourhood (bit d = direction d is
-        // foreground): the three rows are fetched with independent loads, the rotation is bit math
-        int s_end = is_hole ? 0 : 4, s, x1, y1;
-        {
-            // first neighbour clockwise from s_end: directions s_end-1, s_end-2, ..., s_end (mod 8)
-            const uint32_t m = P.nbr8(x0, y0);
-            const uint32_t rot = ((m | (m << 8)) >> s_end) & 0xFFu;          // bit j = direction s_end + j
-            // clockwise order = j = 7, 6, ..., 1: the highest set bit (direction s_end itself, j = 0, is
-            // background at every start the scan can produce); none = isolated pixel
-            const int hb = rot ? 31 - __clz(rot) : 0;
-            s = (s_end + hb) & 7;
-            x1 = x0 + kDx[s]; y1 = y0 + kDy[s];
-        }
-        if (s == s_end)
-        {
-            P.set_visited(x0, y0); P.set_rflag(x0, y0);          // isolated pixel
-            if (!emit(x0, y0)) return false;
-        }
-        else
-        {
-            int x3 = x0, y3 = y0;
-            for (;;)
+            if (list_head == list_n)
             {
-                s_end = s;
-                // first neighbour counter-clockwise from s+1: directions s+1, s+2, ... (mod 8)
-                const uint32_t m = P.nbr8(x3, y3);
-                const uint32_t rot = ((m | (m << 8)) >> ((s + 1) & 7)) & 0xFFu;   // bit j = direction s + 1 + j
-                const int j = __ffs(rot) - 1;                                    // a neighbour always exists: we came from one
-                const int s_raw = s + 1 + j;                                     // what the original's ++s loop ends on (<= 15)
-                s = s_raw & 7;
-                const int x4 = x3 + kDx[s], y4 = y3 + kDy[s];
-                // marks of (x3, y3): one look-up of the cached mark words per step
+                list_head = list_n = 0;
+                int budget = kTileRows;
+                while (list_n == 0 && !src_done && (budget > 0 || idle == kFull))
                 {
-                    P.seek_marks(x3, y3);
-                    const uint32_t bit = 1u << (x3 & 31);
-                    if ((unsigned)(s - 1) < (unsigned)s_end) { P.vword |= bit; P.rword |= bit; P.dirty = true; }
-                    else if (!(P.vword & bit)) { P.vword |= bit; P.dirty = true; }
-                }
-                if (!emit(x3, y3)) return false;
-                if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
-                x3 = x4; y3 = y4;
-                s = (s + 4) & 7;
-            }
-        }
-        a00 += px * fy - fx * py;                        // closing edge: last point -> first point
-        // filterByArea: m00 = |a00| / 2 in [20, 80000) -- exact in integers. Everything else is dropped here.
-        const long long aa = a00 < 0 ? -a00 : a00;
-        if (aa < 40 || aa >= 160000) { npts = start; return true; }
-        const unsigned idx = atomicAdd(rec_count, 1u);
-        if (idx >= rec_cap) return false;
-        BlobRecord r;
-        r.frame = frame; r.thr = thr; r.seq = seq++; r.n = n; r.pts_off = start;
-        r.xmin = r.xmax = r.ymin = r.ymax = 0;
-        r.a00 = a00; r.a10 = r.a01 = r.a20 = r.a11 = r.a02 = 0;
-        r.hull2 = 0; r.cx = r.cy = r.radius = 0; r.colour_ok = 0; r.pad = 0;
-        recs[idx] = r;
-        return true;
-    }
-};
-
-__global__ void __launch_bounds__(32)
-blob_trace_kernel(BlobGeom g, const uint32_t* __restrict__ planes, uint32_t* marksV, uint32_t* marksR,
-                  uint32_t* pts, BlobRecord* recs, unsigned* rec_count, int* status)
-{
-    // One warp per (frame, threshold). The raster scan for 0/1 transitions is done by all 32 lanes
-    // (a lane looks at four words = 128 pixels; a 4K row is one coalesced 512-byte load); the groups that
-    // hold transitions are then handed, in raster order, to lane 0, which owns the mark planes and
-    // follows the borders exactly as the sequential original does.
-    const int lane = threadIdx.x;
-    const int job = blockIdx.x, f = job / kNThr, k = job % kNThr;
-    const size_t poff = ((size_t)f * kNThr + k) * g.h * g.wpr;
-    Tracer T;
-    T.P.B = planes + poff; T.P.V = marksV + poff; T.P.R = marksR + poff;
-    T.P.w = g.w; T.P.h = g.h; T.P.wpr = g.wpr; T.P.init();
-    T.pts = pts + (size_t)job * g.pts_cap; T.npts = 0; T.pts_cap = g.pts_cap;
-    T.recs = recs; T.rec_count = rec_count; T.rec_cap = g.rec_cap; T.status = status;
-    T.frame = f; T.thr = k; T.seq = 0;
-
-    const int groups = g.wpr / 4;                         // wpr is a multiple of 4, the planes are 16-byte aligned
-    for (int y = 0; y < g.h; y++)
-    {
-        const uint4* brow = reinterpret_cast<const uint4*>(T.P.B + (size_t)y * g.wpr);
-        uint32_t carry = 0;                               // last pixel of the previous 32 groups
-        for (int g0 = 0; g0 < groups; g0 += 32)
-        {
-            const int gi = g0 + lane;
-            const uint4 q = gi < groups ? brow[gi] : make_uint4(0, 0, 0, 0);
-            const uint32_t pw = __shfl_up_sync(0xffffffffu, q.w, 1);
-            const uint32_t prevbit = lane == 0 ? carry : pw >> 31;
-            carry = __shfl_sync(0xffffffffu, q.w, 31) >> 31;
-            // pixels that differ from their left neighbour
-            uint32_t e0 = q.x ^ ((q.x << 1) | prevbit), e1 = q.y ^ ((q.y << 1) | (q.x >> 31));
-            uint32_t e2 = q.z ^ ((q.z << 1) | (q.y >> 31)), e3 = q.w ^ ((q.w << 1) | (q.z >> 31));
-            const int left = g.w - gi * 128;              // only x < w is examined (the scan stops before the frame)
-            if (left < 128)
-            {
-                e0 &= left >= 32 ? ~0u : (left > 0 ? (1u << left) - 1 : 0u);
-                e1 &= left >= 64 ? ~0u : (left > 32 ? (1u << (left - 32)) - 1 : 0u);
-                e2 &= left >= 96 ? ~0u : (left > 64 ? (1u << (left - 64)) - 1 : 0u);
-                e3 &= left > 96 ? (1u << (left - 96)) - 1 : 0u;
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, (e0 | e1 | e2 | e3) != 0);
-            while (m)
-            {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t cx = __shfl_sync(0xffffffffu, q.x, src), cy = __shfl_sync(0xffffffffu, q.y, src);
-                const uint32_t cz = __shfl_sync(0xffffffffu, q.z, src), cw = __shfl_sync(0xffffffffu, q.w, src);
-                const uint32_t f0 = __shfl_sync(0xffffffffu, e0, src), f1 = __shfl_sync(0xffffffffu, e1, src);
-                const uint32_t f2 = __shfl_sync(0xffffffffu, e2, src), f3 = __shfl_sync(0xffffffffu, e3, src);
-                int failed = 0;
-                if (lane == 0)
-                {
-#pragma unroll 1
-                    for (int kk = 0; kk < 4 && !failed; kk++)
+                    budget--;
+                    if (tile_row >= tile_rows)
                     {
-                        uint32_t ev = kk == 0 ? f0 : kk == 1 ? f1 : kk == 2 ? f2 : f3;
-                        const uint32_t cur = kk == 0 ? cx : kk == 1 ? cy : kk == 2 ? cz : cw;
-                        while (ev)
+                        unsigned t = 0;
+                        if (lane == 0) t = atomicAdd(&counters[kCntTile], 1u);
+                        t = __shfl_sync(kFull, t, 0);
+                        if (t >= ntiles) { src_done = true; break; }
+                        // tile order: the first strip of every plane, then the second, ...: the longest borders (frame-
+                        // and board-sized outlines) start near the top of their planes and so start early
+                        const unsigned njobs = (unsigned)g.nframes * kNThr;
+                        tjob = (int)(t % njobs);
+                        const int cb = (int)((t / njobs) % (unsigned)ncb), st = (int)(t / (njobs * (unsigned)ncb));
+                        ty0 = st * kTileRows; twd0 = cb * 32;
+                        tile_rows = min(kTileRows, g.h - ty0); tile_row = 0;
+                        TB = planes + (size_t)tjob * plane_words;
+                        const int wd = twd0 + lane, yu = ty0 - 1;
+                        up = (yu >= 0 && wd < g.wpr) ? TB[(size_t)yu * g.wpr + wd] : 0u;
+                        upl = __shfl_up_sync(kFull, up, 1); upr = __shfl_down_sync(kFull, up, 1);
+                        if (lane == 0)  upl = (yu >= 0 && wd > 0) ? TB[(size_t)yu * g.wpr + wd - 1] : 0u;
+                        if (lane == 31) upr = (yu >= 0 && wd + 1 < g.wpr) ? TB[(size_t)yu * g.wpr + wd + 1] : 0u;
+                    }
+                    while (tile_row < tile_rows && list_n <= (unsigned)(kListCap - 1024))
+                    {
+                        const int wd = twd0 + lane, y = ty0 + tile_row;
+                        const uint32_t cur = wd < g.wpr ? TB[(size_t)y * g.wpr + wd] : 0u;
+                        uint32_t left = __shfl_up_sync(kFull, cur, 1), right = __shfl_down_sync(kFull, cur, 1);
+                        if (lane == 0)  left  = wd > 0 ? TB[(size_t)y * g.wpr + wd - 1] : 0u;
+                        if (lane == 31) right = wd + 1 < g.wpr ? TB[(size_t)y * g.wpr + wd + 1] : 0u;
+                        uint32_t outer, hole;
+                        candidate_masks(cur, left, up, upl, upr, &outer, &hole);
+                        up = cur; upl = left; upr = right;
+                        const unsigned c = __popc(outer) + __popc(hole);
+                        if (__ballot_sync(kFull, c != 0))
                         {
-                            const int bb = __ffs(ev) - 1;
-                            ev &= ev - 1;
-                            const int x = ((g0 + src) * 4 + kk) * 32 + bb;
-                            // 0 -> 1: an outer border starts here unless the pixel was already visited;
-                            // 1 -> 0: a hole border starts at x-1 unless that pixel carries the east flag
-                            const bool hole = !((cur >> bb) & 1u);
-                            const int sx = x - (hole ? 1 : 0);
-                            const bool start = hole ? !T.P.rflag(sx, y) : !T.P.visited(sx, y);
-                            if (start && !T.trace(sx, y, hole)) { failed = 1; break; }
+                            unsigned incl = c;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+                            unsigned at = list_n + incl - c;
+                            const unsigned rowbits = (unsigned)tile_row << 10 | (unsigned)lane << 5;
+                            while (outer) { const int b = __ffs(outer) - 1; outer &= outer - 1; list[at++] = (uint16_t)(rowbits | b); }
+                            while (hole)  { const int b = __ffs(hole) - 1;  hole &= hole - 1;   list[at++] = (uint16_t)(0x4000u | rowbits | b); }
+                            list_n += __shfl_sync(kFull, incl, 31);
+                        }
+                        tile_row++;
+                    }
+                }
+                __syncwarp();
+                if (list_n == 0) break;
+            }
+            // the list's next entries go to the idle lanes, in lane order
+            const unsigned avail = list_n - list_head, rank = __popc(idle & ((1u << lane) - 1u));
+            if (!active && rank < avail)
+            {
+                const unsigned e = list[list_head + rank];
+                const int x = twd0 * 32 + (int)(e & 1023u), y = ty0 + (int)((e >> 10) & 15u);
+                job = tjob; P.B = TB;
+                F.init(); Bk.init();
+                pos = y * g.w + x;
+                bool ok = true;
+                if (e & 0x4000u) { sx = x - 1; sy = y; sk = 1; }
+                else { sx = x; sy = y; ok = outer_start(P, F, x, y, &sk); }          // false: isolated pixel, area 0
+                if (ok) { fx = bx = sx; fy = by = sy; fk = bk = sk; a00 = 0; cnt = 0; active = true; }
+            }
+            list_head += min(avail, (unsigned)__popc(idle));
+            idle = __ballot_sync(kFull, !active);
+        }
+        if (!__any_sync(kFull, active)) { if (src_done) break; continue; }
+
+#pragma unroll 1
+        for (int it = 0; it < 16; it++)
+        {
+            if (active)
+            {
+                int disc;
+                { const int px = fx, py = fy; step_fwd(P, F, fx, fy, fk, &disc); a00 += (long long)(px * fy - fx * py); cnt++; }
+                bool drop = disc >= 0 && disc < pos;
+                bool met = !drop && fx == bx && fy == by && fk == bk;
+                if (!drop && !met)
+                {
+                    const int qx = bx, qy = by;
+                    step_bwd(P, Bk, bx, by, bk, &disc); a00 += (long long)(bx * qy - qx * by); cnt++;
+                    drop = disc >= 0 && disc < pos;
+                    met = !drop && fx == bx && fy == by && fk == bk;
+                }
+                if (!drop && !met && cnt > max_steps) { atomicExch(&counters[kCntStatus], 2u); drop = true; }   // cannot happen
+                if (drop) active = false;
+                else if (met)
+                {
+                    active = false;
+                    // filterByArea: m00 = |a00| / 2 in [20, 80000) -- exact in integers. Everything else is dropped here.
+                    const long long aa = a00 < 0 ? -a00 : a00;
+                    if (aa >= 40 && aa < 160000)
+                    {
+                        const unsigned idx = atomicAdd(&counters[kCntRecords], 1u);
+                        const unsigned off = atomicAdd(&counters[kCntPoints], (unsigned)cnt);
+                        if (idx >= g.rec_cap || off > g.pts_cap || (unsigned)cnt > g.pts_cap - off) atomicExch(&counters[kCntStatus], 1u);
+                        else
+                        {
+                            BlobRecord r;
+                            r.frame = job / kNThr; r.thr = job % kNThr; r.seq = pos; r.n = cnt; r.pts_off = off;
+                            r.sx = sx; r.sy = sy; r.sk = sk;
+                            r.xmin = r.xmax = r.ymin = r.ymax = 0;
+                            r.a00 = a00; r.a10 = r.a01 = r.a20 = r.a11 = r.a02 = 0;
+                            r.hull2 = 0; r.cx = r.cy = r.radius = 0; r.colour_ok = 0; r.big = 0;
+                            recs[idx] = r;
                         }
                     }
                 }
-                failed = __shfl_sync(0xffffffffu, failed, 0);
-                if (failed) { if (lane == 0) atomicExch(status, 1); return; }
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// B3: hull area, colour test, median radius of one surviving border per CTA
+// B2b: points, remaining moments and bounding box of the kept borders, one lane per border
 // ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+blob_points_kernel(BlobGeom g, const uint32_t* __restrict__ planes, BlobRecord* __restrict__ recs,
+                   unsigned* __restrict__ counters, uint32_t* __restrict__ pts)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned nrec = min(counters[kCntRecords], g.rec_cap);
+    if (counters[kCntStatus]) return;
+    const size_t plane_words = (size_t)g.h * g.wpr;
+    PlaneRef P; P.B = planes; P.w = g.w; P.h = g.h; P.wpr = g.wpr;
+    BitWindow F;
+    bool active = false, more = true;
+    unsigned ri = 0; int x = 0, y = 0, k = 0, i = 0, n = 0;
+    uint32_t* out = pts;
+    long long t10 = 0, t01 = 0, t20 = 0, t11 = 0, t02 = 0;
+    int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
+    for (;;)
+    {
+        const unsigned idle = __ballot_sync(kFull, !active);
+        if (idle && more)
+        {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&counters[kCntPointJob], (unsigned)__popc(idle));
+            base = __shfl_sync(kFull, base, 0);
+            more = base < nrec;
+            if (!active)
+            {
+                ri = base + __popc(idle & ((1u << lane) - 1u));
+                if (ri < nrec)
+                {
+                    const BlobRecord& r = recs[ri];
+                    P.B = planes + ((size_t)r.frame * kNThr + r.thr) * plane_words;
+                    F.init();
+                    x = r.sx; y = r.sy; k = r.sk; n = r.n; i = 0; out = pts + r.pts_off;
+                    t10 = t01 = t20 = t11 = t02 = 0;
+                    bx0 = INT_MAX; bx1 = INT_MIN; by0 = INT_MAX; by1 = INT_MIN;
+                    active = true;
+                }
+            }
+        }
+        if (!__any_sync(kFull, active)) { if (!more) break; continue; }
+#pragma unroll 1
+        for (int it = 0; it < 32; it++)
+        {
+            if (active)
+            {
+                out[i] = (uint32_t)x | ((uint32_t)y << 16);
+                bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y);
+                const long long xp = x, yp = y;
+                int disc;
+                step_fwd(P, F, x, y, k, &disc);
+                // edge (xp,yp) -> (x,y): the terms of cv::moments' contour sums, exact integers
+                const long long xc = x, yc = y;
+                const long long dxy = xp * yc - xc * yp, xs = xp + xc, ys2 = yp + yc;
+                t10 += dxy * xs; t01 += dxy * ys2;
+                t20 += dxy * (xp * xs + xc * xc);
+                t11 += dxy * (xp * (ys2 + yp) + xc * (ys2 + yc));
+                t02 += dxy * (yp * ys2 + yc * yc);
+                if (++i == n)
+                {
+                    BlobRecord& r = recs[ri];
+                    r.a10 = t10; r.a01 = t01; r.a20 = t20; r.a11 = t11; r.a02 = t02;
+                    r.xmin = bx0; r.xmax = bx1; r.ymin = by0; r.ymax = by1;
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// B3: hull area, colour test, median radius of one kept border
+// ------------------------------------------------------------------------------------------------
+// convex hull of the border = hull of the per-column extremes (every column of the box holds a border
+// point). Monotone chains over the columns; the area comes out as an exact integer: the polygon is the lower
+// chain left -> right, up the last column, the upper chain right -> left, down the first column.
+// One thread per chain (stk: 2 * bw ints each).
+__device__ long long hull_chain_sum(const int* ys, bool lower, int* stk, int bw)
+{
+    int k = 0;
+    for (int i = 0; i < bw; i++)
+    {
+        const long long x = i, y = ys[i];
+        while (k >= 2)
+        {
+            const long long ox = stk[2*(k-2)], oy = stk[2*(k-2)+1], ax = stk[2*(k-1)], ay = stk[2*(k-1)+1];
+            const long long cr = (ax - ox) * (y - oy) - (ay - oy) * (x - ox);
+            if (lower ? cr <= 0 : cr >= 0) k--; else break;
+        }
+        stk[2*k] = i; stk[2*k+1] = (int)y; k++;
+    }
+    long long s = 0;
+    for (int i = 0; i + 1 < k; i++)
+        s += (long long)stk[2*i] * stk[2*i+3] - (long long)stk[2*i+2] * stk[2*i+1];
+    return s;
+}
+__device__ __forceinline__ long long hull_area2_from_chains(long long sl, long long su, const int* ylo, const int* yhi, int bw)
+{
+    const long long xe = bw - 1;
+    const long long a2 = sl + xe * ((long long)yhi[bw-1] - ylo[bw-1]) - su;      // first column: x = 0 contributes nothing
+    return a2 < 0 ? -a2 : a2;
+}
+
+// centre with the rounding of cv::moments / SimpleBlobDetector (m = a * (+-1/2, +-1/6), c = m10 / m00) and the colour
+// filter (the binary image must be 0 at (cvRound(cy), cvRound(cx))). One thread. The host rejects a record whose
+// colour test fails whatever its hull is, so the hull (and the radius) are only worked out for the others.
+__device__ bool centre_and_colour(BlobRecord& r, const BlobGeom& g, const uint32_t* __restrict__ planes)
+{
+    const double sgn = r.a00 > 0 ? 1.0 : -1.0;
+    const double m00 = __dmul_rn((double)r.a00, sgn * 0.5);
+    const double m10 = __dmul_rn((double)r.a10, sgn * 0.16666666666666666666666666666667);
+    const double m01 = __dmul_rn((double)r.a01, sgn * 0.16666666666666666666666666666667);
+    const double cx = __ddiv_rn(m10, m00), cy = __ddiv_rn(m01, m00);
+    r.cx = cx; r.cy = cy;
+    const int rx = __double2int_rn(cx), ry = __double2int_rn(cy);
+    int ok = 0;
+    if (rx >= 0 && rx < g.w && ry >= 0 && ry < g.h)
+    {
+        const uint32_t* B = planes + ((size_t)r.frame * kNThr + r.thr) * g.h * g.wpr;
+        ok = !((B[(size_t)ry * g.wpr + (rx >> 5)] >> (rx & 31)) & 1u);
+    }
+    r.colour_ok = ok;
+    return ok != 0;
+}
+// The host also rejects the record if area / hullArea < 0.95f; where that is certain (a ratio below 0.94: far from
+// any rounding question) the median radius is not needed.
+__device__ __forceinline__ bool radius_needed(const BlobRecord& r)
+{
+    const long long aa = r.a00 < 0 ? -r.a00 : r.a00;
+    return aa * 100 >= r.hull2 * 94;
+}
+
+__device__ __forceinline__ unsigned long long dist2_key(double cx, double cy, uint32_t q)
+{
+    const double dx = __dsub_rn(cx, (double)(int)(q & 0xFFFF)), dy = __dsub_rn(cy, (double)(int)(q >> 16));
+    return (unsigned long long)__double_as_longlong(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+constexpr int kW3Keys = 1536, kW3Cols = 512, kW3Warps = 6;
+struct WarpScratch
+{
+    unsigned long long keys[kW3Keys];           // the hull's two chain stacks (2 * kW3Cols ints each) live here before the keys do
+    int ylo[kW3Cols], yhi[kW3Cols];
+    unsigned hist[256];
+};
+
+// One warp per border whose points (<= kW3Keys) and columns (<= kW3Cols) fit the warp's slice of shared memory.
+__global__ void __launch_bounds__(kW3Warps * 32)
+blob_contour_warp_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const uint32_t* __restrict__ pts,
+                         BlobRecord* recs, const unsigned* __restrict__ counters)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpScratch& S = reinterpret_cast<WarpScratch*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    if (counters[kCntStatus]) return;
+    const unsigned nrec = min(counters[kCntRecords], g.rec_cap);
+    const unsigned nwarps = gridDim.x * kW3Warps;
+    for (unsigned ri = blockIdx.x * kW3Warps + (threadIdx.x >> 5); ri < nrec; ri += nwarps)
+    {
+        BlobRecord& r = recs[ri];
+        const int n = r.n, bw = r.xmax - r.xmin + 1;
+        if (n > kW3Keys || bw > kW3Cols) { if (lane == 0) r.big = 1; continue; }
+        const uint32_t* p = pts + r.pts_off;
+        int need = 0;
+        if (lane == 0) need = centre_and_colour(r, g, planes);
+        need = __shfl_sync(kFull, need, 0);
+        if (!need) continue;
+        for (int i = lane; i < bw; i += 32) { S.ylo[i] = INT_MAX; S.yhi[i] = INT_MIN; }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32)
+        {
+            const uint32_t q = p[i];
+            const int x = (int)(q & 0xFFFF) - r.xmin, y = (int)(q >> 16);
+            atomicMin(&S.ylo[x], y); atomicMax(&S.yhi[x], y);
+        }
+        __syncwarp();
+        // lower chain on lane 0, upper chain on lane 1
+        long long cs = 0;
+        if (lane < 2) cs = hull_chain_sum(lane ? S.yhi : S.ylo, lane == 0, reinterpret_cast<int*>(S.keys) + lane * 2 * kW3Cols, bw);
+        const long long su = __shfl_sync(kFull, cs, 1);
+        if (lane == 0)
+        {
+            r.hull2 = hull_area2_from_chains(cs, su, S.ylo, S.yhi, bw);
+            need = radius_needed(r);
+        }
+        need = __shfl_sync(kFull, need, 0);
+        if (!need) continue;
+        const double cx = __shfl_sync(kFull, r.cx, 0), cy = __shfl_sync(kFull, r.cy, 0);   // (lane 0 wrote them; same value for all)
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) S.keys[i] = dist2_key(cx, cy, p[i]);
+        __syncwarp();
+        // median of the point distances to the centre: order statistics (n-1)/2 and n/2 of d2 = dx*dx + dy*dy,
+        // selected on the bit patterns (non-negative doubles order like integers), one byte per pass
+        double dsel[2];
+        for (int which = 0; which < 2; which++)
+        {
+            unsigned rank = which == 0 ? (unsigned)(n - 1) / 2 : (unsigned)n / 2;
+            if (which == 1 && rank == (unsigned)(n - 1) / 2) { dsel[1] = dsel[0]; break; }
+            unsigned long long prefix = 0;
+            for (int pass = 7; pass >= 0; pass--)
+            {
+                for (int i = lane; i < 256; i += 32) S.hist[i] = 0;
+                __syncwarp();
+                for (int i = lane; i < n; i += 32)
+                {
+                    const unsigned long long key = S.keys[i];
+                    if (pass == 7 || (key >> (8 * (pass + 1))) == (prefix >> (8 * (pass + 1))))
+                        atomicAdd(&S.hist[(key >> (8 * pass)) & 255], 1u);
+                }
+                __syncwarp();
+                // lane l owns bins 8l .. 8l+7
+                unsigned h[8], mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { h[j] = S.hist[8 * lane + j]; mine += h[j]; }
+                unsigned incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+                const unsigned excl = incl - mine;
+                const bool here = rank >= excl && rank < incl;
+                unsigned b = 0, rk = 0;
+                if (here)
+                {
+                    rk = rank - excl;
+                    bool found = false;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (!found) { if (rk < h[j]) { found = true; b = 8 * lane + j; } else rk -= h[j]; }
+                }
+                const int src = __ffs(__ballot_sync(kFull, here)) - 1;
+                b = __shfl_sync(kFull, b, src); rank = __shfl_sync(kFull, rk, src);
+                prefix |= (unsigned long long)b << (8 * pass);
+                __syncwarp();
+            }
+            dsel[which] = __dsqrt_rn(__longlong_as_double((long long)prefix));
+        }
+        if (lane == 0) r.radius = __ddiv_rn(__dadd_rn(dsel[0], dsel[1]), 2.0);
+        __syncwarp();
+    }
+}
+
+// The same for the borders the warp kernel left (big = 1): one CTA each, per-column extremes and the chain stack
+// in global scratch, keys recomputed in every pass.
 constexpr int kB3Threads = 128;
 
 __global__ void __launch_bounds__(kB3Threads)
 blob_contour_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const uint32_t* __restrict__ pts,
-                    BlobRecord* recs, const unsigned* __restrict__ rec_count, int* scratch, int scratch_stride)
+                    BlobRecord* recs, const unsigned* __restrict__ counters, int* scratch, int scratch_stride)
 {
     __shared__ unsigned hist[256];
     __shared__ unsigned long long sel_prefix;
     __shared__ unsigned sel_rank;
-    __shared__ double s_cx, s_cy;
-    __shared__ long long red_ll[kB3Threads / 32][5];
-    __shared__ int red_i[kB3Threads / 32][4];
     __shared__ int s_need_radius;
-    const unsigned nrec = min(*rec_count, g.rec_cap);
+    if (counters[kCntStatus]) return;
+    const unsigned nrec = min(counters[kCntRecords], g.rec_cap);
     int* ylo = scratch + (size_t)blockIdx.x * scratch_stride;       // per column of the bounding box
     int* yhi = ylo + g.w;
     int* stk = yhi + g.w;                                           // hull chain: (x, y) pairs
     for (unsigned ri = blockIdx.x; ri < nrec; ri += gridDim.x)
     {
         BlobRecord& r = recs[ri];
-        const uint32_t* p = pts + ((size_t)r.frame * kNThr + r.thr) * g.pts_cap + r.pts_off;
+        if (!r.big) continue;
+        const uint32_t* p = pts + r.pts_off;
         const int n = r.n;
-        // Green's-theorem sums over the directed edges (point i-1 -> point i, cyclically) and the
-        // bounding box: exact integers, any order
-        {
-            long long t10 = 0, t01 = 0, t20 = 0, t11 = 0, t02 = 0;
-            int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
-            for (int i = threadIdx.x; i < n; i += kB3Threads)
-            {
-                const uint32_t q = p[i], qp = p[i == 0 ? n - 1 : i - 1];
-                const long long x = q & 0xFFFF, y = q >> 16, xp = qp & 0xFFFF, yp = qp >> 16;
-                const long long dxy = xp * y - x * yp, xs = xp + x, ys2 = yp + y;
-                t10 += dxy * xs; t01 += dxy * ys2;
-                t20 += dxy * (xp * xs + x * x);
-                t11 += dxy * (xp * (ys2 + yp) + x * (ys2 + y));
-                t02 += dxy * (yp * ys2 + y * y);
-                bx0 = min(bx0, (int)x); bx1 = max(bx1, (int)x); by0 = min(by0, (int)y); by1 = max(by1, (int)y);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                t10 += __shfl_down_sync(0xffffffffu, t10, o); t01 += __shfl_down_sync(0xffffffffu, t01, o);
-                t20 += __shfl_down_sync(0xffffffffu, t20, o); t11 += __shfl_down_sync(0xffffffffu, t11, o);
-                t02 += __shfl_down_sync(0xffffffffu, t02, o);
-                bx0 = min(bx0, __shfl_down_sync(0xffffffffu, bx0, o)); bx1 = max(bx1, __shfl_down_sync(0xffffffffu, bx1, o));
-                by0 = min(by0, __shfl_down_sync(0xffffffffu, by0, o)); by1 = max(by1, __shfl_down_sync(0xffffffffu, by1, o));
-            }
-            if ((threadIdx.x & 31) == 0)
-            {
-                const int wi = threadIdx.x >> 5;
-                red_ll[wi][0] = t10; red_ll[wi][1] = t01; red_ll[wi][2] = t20; red_ll[wi][3] = t11; red_ll[wi][4] = t02;
-                red_i[wi][0] = bx0; red_i[wi][1] = bx1; red_i[wi][2] = by0; red_i[wi][3] = by1;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                long long u[5] = { 0, 0, 0, 0, 0 };
-                int c0 = INT_MAX, c1 = INT_MIN, c2 = INT_MAX, c3 = INT_MIN;
-                for (int wq = 0; wq < kB3Threads / 32; wq++)
-                {
-                    for (int k = 0; k < 5; k++) u[k] += red_ll[wq][k];
-                    c0 = min(c0, red_i[wq][0]); c1 = max(c1, red_i[wq][1]); c2 = min(c2, red_i[wq][2]); c3 = max(c3, red_i[wq][3]);
-                }
-                r.a10 = u[0]; r.a01 = u[1]; r.a20 = u[2]; r.a11 = u[3]; r.a02 = u[4];
-                r.xmin = c0; r.xmax = c1; r.ymin = c2; r.ymax = c3;
-            }
-            __syncthreads();
-        }
         const int bw = r.xmax - r.xmin + 1;
+        if (threadIdx.x == 0) s_need_radius = centre_and_colour(r, g, planes);
+        __syncthreads();
+        if (!s_need_radius) { __syncthreads(); continue; }
         for (int i = threadIdx.x; i < bw; i += kB3Threads) { ylo[i] = INT_MAX; yhi[i] = INT_MIN; }
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += kB3Threads)
@@ -417,59 +588,13 @@ blob_contour_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const uint3
         __syncthreads();
         if (threadIdx.x == 0)
         {
-            // convex hull of the border = hull of the per-column extremes (every column of the box holds
-            // a border point). Monotone chains over the columns; the area comes out as an exact integer.
-            auto chain_sum = [&](const int* ys, bool lower) -> long long
-            {
-                int k = 0;
-                for (int i = 0; i < bw; i++)
-                {
-                    const long long x = i, y = ys[i];
-                    while (k >= 2)
-                    {
-                        const long long ox = stk[2*(k-2)], oy = stk[2*(k-2)+1], ax = stk[2*(k-1)], ay = stk[2*(k-1)+1];
-                        const long long cr = (ax - ox) * (y - oy) - (ay - oy) * (x - ox);
-                        if (lower ? cr <= 0 : cr >= 0) k--; else break;
-                    }
-                    stk[2*k] = i; stk[2*k+1] = (int)y; k++;
-                }
-                long long s = 0;
-                for (int i = 0; i + 1 < k; i++)
-                    s += (long long)stk[2*i] * stk[2*i+3] - (long long)stk[2*i+2] * stk[2*i+1];
-                return s;
-            };
-            // polygon: lower chain left -> right, up the last column, upper chain right -> left, down the first
-            const long long sl = chain_sum(ylo, true), su = chain_sum(yhi, false);
-            const long long xe = bw - 1;
-            long long a2 = sl + xe * ((long long)yhi[bw-1] - ylo[bw-1]) - su;      // first column: x = 0 contributes nothing
-            r.hull2 = a2 < 0 ? -a2 : a2;
-
-            // centre, with the rounding of cv::moments / SimpleBlobDetector: m = a * (+-1/2, +-1/6), c = m10 / m00
-            const double sgn = r.a00 > 0 ? 1.0 : -1.0;
-            const double m00 = __dmul_rn((double)r.a00, sgn * 0.5);
-            const double m10 = __dmul_rn((double)r.a10, sgn * 0.16666666666666666666666666666667);
-            const double m01 = __dmul_rn((double)r.a01, sgn * 0.16666666666666666666666666666667);
-            const double cx = __ddiv_rn(m10, m00), cy = __ddiv_rn(m01, m00);
-            r.cx = cx; r.cy = cy; s_cx = cx; s_cy = cy;
-            // filterByColor: the binary image must be 0 at (cvRound(cy), cvRound(cx))
-            const int rx = __double2int_rn(cx), ry = __double2int_rn(cy);
-            int ok = 0;
-            if (rx >= 0 && rx < g.w && ry >= 0 && ry < g.h)
-            {
-                const uint32_t* B = planes + ((size_t)r.frame * kNThr + r.thr) * g.h * g.wpr;
-                ok = !((B[(size_t)ry * g.wpr + (rx >> 5)] >> (rx & 31)) & 1u);
-            }
-            r.colour_ok = ok;
-            // The host rejects the record if the colour test fails or area / hullArea < 0.95f. Where that is
-            // certain (colour, or a ratio below 0.94: far from any rounding question) the median is not needed.
-            const long long aa = r.a00 < 0 ? -r.a00 : r.a00;
-            s_need_radius = ok && aa * 100 >= r.hull2 * 94;
+            const long long sl = hull_chain_sum(ylo, true, stk, bw), su = hull_chain_sum(yhi, false, stk, bw);
+            r.hull2 = hull_area2_from_chains(sl, su, ylo, yhi, bw);
+            s_need_radius = radius_needed(r);
         }
         __syncthreads();
         if (!s_need_radius) { __syncthreads(); continue; }
-        // median of the point distances to the centre: order statistics (n-1)/2 and n/2 of
-        // d2 = dx*dx + dy*dy, selected on the bit patterns (non-negative doubles order like integers)
-        const double cx = s_cx, cy = s_cy;
+        const double cx = r.cx, cy = r.cy;
         double dsel[2];
         for (int which = 0; which < 2; which++)
         {
@@ -483,9 +608,7 @@ blob_contour_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const uint3
                 const unsigned long long prefix = sel_prefix;
                 for (int i = threadIdx.x; i < n; i += kB3Threads)
                 {
-                    const uint32_t q = p[i];
-                    const double dx = __dsub_rn(cx, (double)(int)(q & 0xFFFF)), dy = __dsub_rn(cy, (double)(int)(q >> 16));
-                    const unsigned long long key = (unsigned long long)__double_as_longlong(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    const unsigned long long key = dist2_key(cx, cy, p[i]);
                     if (pass == 7 || (key >> (8 * (pass + 1))) == (prefix >> (8 * (pass + 1))))
                         atomicAdd(&hist[(key >> (8 * pass)) & 255], 1u);
                 }
@@ -549,20 +672,20 @@ bool center_from_record(const BlobRecord& r, Center* c)
 }
 
 // SimpleBlobDetector::detect's grouping across thresholds + find_blobs.cc:40-41, for one frame.
-// recs: this frame's records sorted by (thr ascending, seq DESCENDING): OpenCV hands contours over
+// order: this frame's records sorted by (thr ascending, seq DESCENDING): OpenCV hands contours over
 // in reverse discovery order.
-int group_frame(const BlobRecord* recs, int nrec, int32_t* xy_out, int max_points)
+int group_frame(const BlobRecord* all, const unsigned* order, int nrec, int32_t* xy_out, int max_points)
 {
     std::vector<std::vector<Center>> centers;
     int i = 0;
     while (i < nrec)
     {
-        const int thr = recs[i].thr;
+        const int thr = all[order[i]].thr;
         std::vector<std::vector<Center>> fresh;
-        for (; i < nrec && recs[i].thr == thr; i++)
+        for (; i < nrec && all[order[i]].thr == thr; i++)
         {
             Center c;
-            if (!center_from_record(recs[i], &c)) continue;
+            if (!center_from_record(all[order[i]], &c)) continue;
             bool is_new = true;
             for (size_t j = 0; j < centers.size(); j++)
             {
@@ -604,19 +727,22 @@ int group_frame(const BlobRecord* recs, int nrec, int32_t* xy_out, int max_point
 
 struct BlobWorkspace
 {
-    void* planes = nullptr; void* marksV = nullptr; void* marksR = nullptr; void* pts = nullptr; void* recs = nullptr;
+    void* planes = nullptr; void* pts = nullptr; void* recs = nullptr;
     void* scratch = nullptr; void* counters = nullptr;
-    size_t planes_b = 0, marks_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0;
-    unsigned pts_cap = 1u << 18, rec_per_job = 512;
-    std::vector<BlobRecord> host_recs;
+    size_t planes_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0;
+    unsigned pts_per_frame = 1u << 21, rec_per_job = 512;
+    BlobRecord* host_recs = nullptr; size_t host_recs_cap = 0;      // pinned
+    std::vector<unsigned> order, first;
+    bool warp_smem_set = false;
 };
 
 BlobWorkspace* blob_workspace_create() { return new BlobWorkspace(); }
 void blob_workspace_destroy(BlobWorkspace* ws)
 {
     if (!ws) return;
-    cudaFree(ws->planes); cudaFree(ws->marksV); cudaFree(ws->marksR); cudaFree(ws->pts); cudaFree(ws->recs);
+    cudaFree(ws->planes); cudaFree(ws->pts); cudaFree(ws->recs);
     cudaFree(ws->scratch); cudaFree(ws->counters);
+    if (ws->host_recs) cudaFreeHost(ws->host_recs);
     delete ws;
 }
 
@@ -636,7 +762,7 @@ static cudaError_t grow(void** p, size_t* have, size_t want)
 // Blob detection over device-resident frames. xy_out: HOST [nframes][max_points][2] int32 (scaled
 // by 1000), counts_out: HOST [nframes]. Synchronous. Returns 0, -1 on a CUDA failure, or 1 when the
 // scratch of a multi-frame chunk overflowed (nothing was produced: run the frames one at a time).
-void blob_workspace_reset_capacity(BlobWorkspace* ws) { ws->pts_cap = 1u << 18; ws->rec_per_job = 512; }
+void blob_workspace_reset_capacity(BlobWorkspace* ws) { ws->pts_per_frame = 1u << 21; ws->rec_per_job = 512; }
 
 int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
                      cudaStream_t stream, float* ms_out)
@@ -648,70 +774,105 @@ int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int
     g.w = fs.w; g.h = fs.h; g.wpr = ((fs.w + 31) / 32 + 3) & ~3; g.nframes = n;      // rows of the planes: multiples of 16 bytes
     const size_t plane_words = (size_t)n * kNThr * g.h * g.wpr;
     BLOB_TRY(grow(&ws->planes, &ws->planes_b, plane_words * 4));
-    {
-        size_t have = ws->marks_b;
-        BLOB_TRY(grow(&ws->marksV, &have, plane_words * 4));
-        BLOB_TRY(grow(&ws->marksR, &ws->marks_b, plane_words * 4));
-    }
-    if (!ws->counters) BLOB_TRY(cudaMalloc(&ws->counters, 16));
+    if (!ws->counters) BLOB_TRY(cudaMalloc(&ws->counters, kCntWords * 4));
     const int b3_blocks = 148 * 4;
     const int scratch_stride = 4 * fs.w + 8;
     BLOB_TRY(grow(&ws->scratch, &ws->scratch_b, (size_t)b3_blocks * scratch_stride * sizeof(int)));
+    if (!ws->warp_smem_set)
+    {
+        BLOB_TRY(cudaFuncSetAttribute(blob_contour_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kW3Warps * sizeof(WarpScratch))));
+        ws->warp_smem_set = true;
+    }
+    const int aligned = ((uintptr_t)fs.base % 16 == 0) && (fs.pitch % 16 == 0) && (fs.frame_stride % 16 == 0 || n == 1);
+    // tiles of the candidate scan: 32 words x kTileRows rows
+    const int ncb = ((g.w + 31) / 32 + 31) / 32, nstrips = (g.h + kTileRows - 1) / kTileRows;
+    const unsigned long long ntiles64 = (unsigned long long)n * kNThr * nstrips * ncb;
+    if (ntiles64 >= 0xFFFFFFFFull) { fprintf(stderr, "%s:%d in %s(): too many frames in one blob chunk. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); *ms_out = 0; }
+    unsigned nrec = 0;
     for (int attempt = 0; ; attempt++)
     {
-        g.pts_cap = ws->pts_cap; g.rec_cap = ws->rec_per_job * (unsigned)n * kNThr;
-        BLOB_TRY(grow(&ws->pts, &ws->pts_b, (size_t)n * kNThr * g.pts_cap * 4));
+        const unsigned long long want_pts = (unsigned long long)ws->pts_per_frame * n;
+        g.pts_cap = (unsigned)std::min<unsigned long long>(want_pts, 0xFFFFFFF0ull);
+        g.rec_cap = (unsigned)std::min<unsigned long long>((unsigned long long)ws->rec_per_job * n * kNThr, 0x7FFFFFFFull);
+        BLOB_TRY(grow(&ws->pts, &ws->pts_b, (size_t)g.pts_cap * 4));
         BLOB_TRY(grow(&ws->recs, &ws->recs_b, (size_t)g.rec_cap * sizeof(BlobRecord)));
-        unsigned* rec_count = (unsigned*)ws->counters; int* status = (int*)ws->counters + 1;
-        BLOB_TRY(cudaMemsetAsync(ws->counters, 0, 16, stream));
-        BLOB_TRY(cudaMemsetAsync(ws->marksV, 0, plane_words * 4, stream));
-        BLOB_TRY(cudaMemsetAsync(ws->marksR, 0, plane_words * 4, stream));
+        unsigned* counters = (unsigned*)ws->counters;
+        BLOB_TRY(cudaMemsetAsync(ws->counters, 0, kCntWords * 4, stream));
         if (e0) cudaEventRecord(e0, stream);
-        blob_binarize_kernel<<<dim3((g.wpr + 127) / 128, g.h, n), 128, 0, stream>>>(fs, g, (uint32_t*)ws->planes);
-        blob_trace_kernel<<<n * kNThr, 32, 0, stream>>>(g, (const uint32_t*)ws->planes, (uint32_t*)ws->marksV, (uint32_t*)ws->marksR,
-                                                       (uint32_t*)ws->pts, (BlobRecord*)ws->recs, rec_count, status);
+        blob_binarize_kernel<<<dim3((g.wpr + 127) / 128, g.h, n), 128, 0, stream>>>(fs, g, (uint32_t*)ws->planes, aligned);
+        blob_walk_kernel<<<148 * 4, kWalkWarps * 32, 0, stream>>>(g, (const uint32_t*)ws->planes, (BlobRecord*)ws->recs, counters,
+                                                                 (unsigned)ntiles64, nstrips, ncb);
+        blob_points_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (BlobRecord*)ws->recs, counters, (uint32_t*)ws->pts);
+        blob_contour_warp_kernel<<<148 * 2, kW3Warps * 32, kW3Warps * sizeof(WarpScratch), stream>>>(
+            g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts, (BlobRecord*)ws->recs, counters);
         blob_contour_kernel<<<b3_blocks, kB3Threads, 0, stream>>>(g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts,
-                                                                  (BlobRecord*)ws->recs, rec_count, (int*)ws->scratch, scratch_stride);
+                                                                  (BlobRecord*)ws->recs, counters, (int*)ws->scratch, scratch_stride);
         if (e1) cudaEventRecord(e1, stream);
         BLOB_TRY(cudaGetLastError());
-        unsigned hc[4];
-        BLOB_TRY(cudaMemcpyAsync(hc, ws->counters, 16, cudaMemcpyDeviceToHost, stream));
+        unsigned hc[kCntWords];
+        BLOB_TRY(cudaMemcpyAsync(hc, ws->counters, kCntWords * 4, cudaMemcpyDeviceToHost, stream));
         BLOB_TRY(cudaStreamSynchronize(stream));
         if (e0) { float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms_out += t; }
-        const bool overflow = hc[1] != 0 || hc[0] > g.rec_cap;
-        if (!overflow)
-        {
-            ws->host_recs.resize(hc[0]);
-            if (hc[0]) BLOB_TRY(cudaMemcpy(ws->host_recs.data(), ws->recs, sizeof(BlobRecord) * hc[0], cudaMemcpyDeviceToHost));
-            break;
-        }
-        // A point region or the record list overflowed. A single frame is run again with four times the
+        if (hc[kCntStatus] == 2) { fprintf(stderr, "%s:%d in %s(): a border walk did not close. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
+        const bool overflow = hc[kCntStatus] != 0 || hc[kCntRecords] > g.rec_cap;
+        if (!overflow) { nrec = hc[kCntRecords]; break; }
+        // The point region or the record list overflowed. A single frame is run again with four times the
         // space; a chunk of several frames is handed back to the caller, who runs its frames one by one
         // (growing the scratch for a whole chunk could ask for tens of GB because of one busy frame).
         if (n > 1) { if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return 1; }
         if (attempt >= 6) { fprintf(stderr, "%s:%d in %s(): blob scratch still overflows after growing it 4096x. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
-        ws->pts_cap *= 4; ws->rec_per_job *= 4;
+        ws->pts_per_frame = ws->pts_per_frame >= (1u << 29) ? ws->pts_per_frame : ws->pts_per_frame * 4; ws->rec_per_job *= 4;
     }
     if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    if (!nrec) return 0;
 
-    std::vector<BlobRecord>& R = ws->host_recs;
-    std::sort(R.begin(), R.end(), [](const BlobRecord& a, const BlobRecord& b)
+    if (ws->host_recs_cap < nrec)
     {
-        if (a.frame != b.frame) return a.frame < b.frame;
-        if (a.thr != b.thr) return a.thr < b.thr;
-        return a.seq > b.seq;
-    });
-    size_t i = 0;
-    while (i < R.size())
+        if (ws->host_recs) cudaFreeHost(ws->host_recs);
+        ws->host_recs = nullptr; ws->host_recs_cap = 0;
+        const size_t cap = (size_t)nrec + nrec / 2 + 1024;
+        BLOB_TRY(cudaMallocHost((void**)&ws->host_recs, cap * sizeof(BlobRecord)));
+        ws->host_recs_cap = cap;
+    }
+    BLOB_TRY(cudaMemcpyAsync(ws->host_recs, ws->recs, sizeof(BlobRecord) * nrec, cudaMemcpyDeviceToHost, stream));
+    BLOB_TRY(cudaStreamSynchronize(stream));
+    const BlobRecord* R = ws->host_recs;
+    // records by frame (counting sort of indices), then each frame ordered and grouped on its own: frames are
+    // independent, so they are spread over host threads
+    std::vector<unsigned>& first = ws->first; std::vector<unsigned>& order = ws->order;
+    first.assign((size_t)n + 1, 0u); order.resize(nrec);
+    for (unsigned i = 0; i < nrec; i++) first[R[i].frame + 1]++;
+    for (int f = 0; f < n; f++) first[f + 1] += first[f];
     {
-        size_t j = i;
-        while (j < R.size() && R[j].frame == R[i].frame) j++;
-        const int f = R[i].frame;
-        counts_out[f] = group_frame(&R[i], (int)(j - i), xy_out + (size_t)f * 2 * max_points, max_points);
-        i = j;
+        std::vector<unsigned> at(first.begin(), first.end() - 1);
+        for (unsigned i = 0; i < nrec; i++) order[at[R[i].frame]++] = i;
+    }
+    auto do_frames = [&](int f0, int f1)
+    {
+        for (int f = f0; f < f1; f++)
+        {
+            unsigned* o = order.data() + first[f];
+            const int m = (int)(first[f + 1] - first[f]);
+            if (!m) continue;
+            std::sort(o, o + m, [&](unsigned a, unsigned b)
+            {
+                if (R[a].thr != R[b].thr) return R[a].thr < R[b].thr;
+                return R[a].seq > R[b].seq;
+            });
+            counts_out[f] = group_frame(R, o, m, xy_out + (size_t)f * 2 * max_points, max_points);
+        }
+    };
+    const int nthreads = std::max(1, std::min({ n / 4, 16, (int)std::thread::hardware_concurrency() }));
+    if (nthreads <= 1) do_frames(0, n);
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++)
+            pool.emplace_back(do_frames, (int)((long long)n * t / nthreads), (int)((long long)n * (t + 1) / nthreads));
+        for (auto& th : pool) th.join();
     }
     return 0;
 }
