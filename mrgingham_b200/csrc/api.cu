@@ -145,7 +145,10 @@ struct mrg_b200_detector
     bool profiling = false;
     KernelTimer timers[3];
     int k2_smem_cands = kClusterSmemCands;   // adapted to the candidate counts of the previous batch (collect_locked)
-    BlobWorkspace* blobs = nullptr;
+    static constexpr int kBlobDepth = 4;       // chunks of the blob path kept in flight
+    BlobWorkspace* blobs[kBlobDepth] = {};
+    Slot blob_slot[kBlobDepth];                // their staged frames (host input)
+    cudaStream_t blob_stream[kBlobDepth] = {};
     float blob_ms = 0;
     // board finder: the frames of the chunk being worked on, kept on the device across the level loop
     std::mutex   boards_mtx;
@@ -504,7 +507,12 @@ API void mrg_b200_detector_destroy(mrg_b200_detector* det)
 {
     if (!det) return;
     DeviceGuard dg(det->device);
-    if (det->blobs) { blob_workspace_destroy(det->blobs); det->blobs = nullptr; }
+    for (int k = 0; k < mrg_b200_detector::kBlobDepth; k++)
+    {
+        if (det->blobs[k]) { blob_workspace_destroy(det->blobs[k]); det->blobs[k] = nullptr; }
+        if (det->blob_stream[k]) { cudaStreamDestroy(det->blob_stream[k]); det->blob_stream[k] = nullptr; }
+        det->blob_slot[k].stage.release();
+    }
     cudaDeviceSynchronize();
     for (auto& S : det->slot)
     {
@@ -768,35 +776,59 @@ static int blobs_batch_mp(mrg_b200_detector* det, const uint8_t* images, int ima
     { MSG("Bad batch geometry (nframes=%d rows=%d cols=%d pitch=%zu).", nframes, rows, cols, row_pitch); return -1; }
     DEVICE_GUARD(det);
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
-    if (!det->blobs) det->blobs = blob_workspace_create();
-    det->blob_ms = 0;
-    // One thread per (frame, threshold) follows borders, so throughput comes from frames in flight:
-    // up to 256 frames per chunk (the scratch is ~70 MB per 4K frame, ~18 GB of the 180 GB at that size)
-    const int chunk = std::max(1, std::min(det->cfg.max_frames, 256));
-    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    constexpr int D = mrg_b200_detector::kBlobDepth;
+    for (int k = 0; k < D; k++)
     {
-        const int n = std::min(chunk, nframes - f0);
-        FrameSet fs;
-        if (stage_frames(det, det->slot[0], images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride,
-                         0, stream, stream, &fs)) return -1;
-        float ms = 0;
-        const int rc = blob_find_frames(det->blobs, fs, xy_out + (size_t)f0 * 2 * mp, counts_out + f0, mp, stream, det->profiling ? &ms : nullptr);
+        if (!det->blobs[k]) det->blobs[k] = blob_workspace_create();
+        if (!det->blob_stream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&det->blob_stream[k], cudaStreamNonBlocking));
+    }
+    det->blob_ms = 0;
+    // Every border is followed by its own lane, but a frame-sized outline still takes one lane a few milliseconds,
+    // during which most of the GPU has nothing left to do for that chunk: D chunks are kept in flight, each on its
+    // own stream and workspace, so that the tails of some chunks' border walks run beside other chunks' kernels,
+    // and the host-side grouping of a finished chunk beside all of them.
+    int chunk = std::max(1, std::min(det->cfg.max_frames, 64));
+    if (const char* e = getenv("MRG_B200_BLOB_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 256) chunk = std::min(v, det->cfg.max_frames); }
+    CUDA_TRY(cudaEventRecord(det->ev_fork, stream));
+    for (int k = 0; k < D; k++) CUDA_TRY(cudaStreamWaitEvent(det->blob_stream[k], det->ev_fork, 0));   // the frames may come from work queued on `stream`
+    struct InFlight { FrameSet fs; int f0 = 0, n = 0; bool live = false; } fl[D];
+    float ms = 0;
+    auto finish = [&](int k) -> int
+    {
+        InFlight& c = fl[k];
+        if (!c.live) return 0;
+        c.live = false;
+        const int rc = blob_finish(det->blobs[k], xy_out + (size_t)c.f0 * 2 * mp, counts_out + c.f0, mp, det->profiling ? &ms : nullptr);
         if (rc < 0) return -1;
-        det->blob_ms += ms;
         if (rc == 1)
         {
             // some frame of the chunk needs more scratch than the default: frame by frame, on the GPU
-            for (int i = 0; i < n; i++)
+            for (int i = 0; i < c.n; i++)
             {
-                FrameSet one = fs; one.base = fs.base + (size_t)i * fs.frame_stride; one.nframes = 1;
-                if (blob_find_frames(det->blobs, one, xy_out + (size_t)(f0 + i) * 2 * mp, counts_out + f0 + i, mp, stream,
-                                     det->profiling ? &ms : nullptr)) return -1;
-                det->blob_ms += ms;
-                blob_workspace_reset_capacity(det->blobs);
+                FrameSet one = c.fs; one.base = c.fs.base + (size_t)i * c.fs.frame_stride; one.nframes = 1;
+                float ms1 = 0;
+                if (blob_find_frames(det->blobs[k], one, xy_out + (size_t)(c.f0 + i) * 2 * mp, counts_out + c.f0 + i, mp, det->blob_stream[k],
+                                     det->profiling ? &ms1 : nullptr)) return -1;
+                ms += ms1;
+                blob_workspace_reset_capacity(det->blobs[k]);
             }
         }
+        return 0;
+    };
+    int rc = 0, ci = 0;
+    for (int f0 = 0; f0 < nframes && !rc; f0 += chunk, ci++)
+    {
+        const int k = ci % D, n = std::min(chunk, nframes - f0);
+        if (finish(k)) { rc = -1; break; }
+        if (stage_frames(det, det->blob_slot[k], images + (size_t)f0 * frame_stride, images_on_device, n, rows, cols, row_pitch, frame_stride,
+                         0, det->blob_stream[k], det->blob_stream[k], &fl[k].fs)) { rc = -1; break; }
+        if (blob_enqueue(det->blobs[k], fl[k].fs, det->blob_stream[k])) { rc = -1; break; }
+        fl[k].f0 = f0; fl[k].n = n; fl[k].live = true;
     }
-    return 0;
+    // (after a failure the chunks still in flight are waited for, their results dropped)
+    for (int j = 0; j < D; j++) { const int k = (ci + j) % D; if (finish(k)) rc = -1; }
+    det->blob_ms = ms;
+    return rc;
 }
 
 API int mrg_b200_find_blobs_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,

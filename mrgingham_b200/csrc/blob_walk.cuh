@@ -59,11 +59,22 @@ BW_HD int dir_dy(int d) { return (int)((0xA901u >> (2 * d)) & 3u) - 1; }
 // outside the w x h image are background). The lane keeps the 3 x 3 words around its position in
 // registers: while a border is followed most steps need no load at all, a vertical step needs one round
 // of three independent loads.
+// A bit plane as the walkers see it: B[y * wpr + wd], bit b = pixel (32*wd + b, y) is foreground. The storage
+// carries a frame of background around the image, so that B may be read for y in [-1, h] and wd in [-1, words]
+// (words = ceil(w / 32)) without any bounds test: B points at the image's first word, one row and one word into
+// the storage, and bits at x >= w are 0.
 struct PlaneRef
 {
     const uint32_t* B;
     int w, h, wpr;
 };
+// storage words per row / rows of a plane holding a w x h image
+BW_HD int plane_wpr(int w)  { return ((w + 31) / 32 + 2 + 3) & ~3; }
+BW_HD int plane_rows(int h) { return h + 2; }
+BW_HD int plane_origin(int w) { return plane_wpr(w) + 1; }           // word offset of pixel (0,0) in the storage
+
+// One lane's view of a bit plane: the 3 x 3 words around its position, in registers. While a border is followed
+// most steps need no load at all, a vertical step needs one round of three independent loads.
 struct BitWindow
 {
     int cy, cwd;
@@ -72,12 +83,8 @@ struct BitWindow
     BW_HD void init() { cy = -0x40000000; cwd = -2; }
     BW_HD void load_row(const PlaneRef& P, int slot, int y)
     {
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-        {
-            const int wc = cwd - 1 + c;
-            b[slot][c] = ((unsigned)y < (unsigned)P.h && (unsigned)wc < (unsigned)P.wpr) ? P.B[(size_t)y * P.wpr + wc] : 0u;
-        }
+        const uint32_t* r = P.B + (y * P.wpr + cwd);
+        b[slot][0] = r[-1]; b[slot][1] = r[0]; b[slot][2] = r[1];
     }
     BW_HD void seek(const PlaneRef& P, int x, int y)
     {

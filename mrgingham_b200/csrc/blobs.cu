@@ -69,14 +69,21 @@ struct BlobRecord
 
 struct BlobGeom
 {
-    int w, h, wpr;                              // pixels, 32-bit words per bit-plane row
+    int w, h, wpr;                              // pixels; storage words per bit-plane row (blobwalk::plane_wpr)
     int nframes;
     unsigned pts_cap;                           // points of the whole chunk
     unsigned rec_cap;
+    unsigned queue_cap;                         // candidate starts of the whole chunk
+    size_t plane_words;                         // storage words of one plane: (h + 2) rows of wpr words
+    int origin;                                 // word offset of pixel (0,0) in a plane's storage
 };
+__device__ __forceinline__ const uint32_t* plane_ptr(const BlobGeom& g, const uint32_t* planes, int job)
+{
+    return planes + (size_t)job * g.plane_words + g.origin;
+}
 
 // device counters (uint32 each)
-enum { kCntRecords = 0, kCntStatus = 1, kCntPoints = 2, kCntTile = 3, kCntPointJob = 4, kCntWords = 8 };
+enum { kCntRecords = 0, kCntStatus = 1, kCntPoints = 2, kCntQueue = 3, kCntPointJob = 4, kCntQueueHead = 5, kCntWords = 8 };
 
 // ------------------------------------------------------------------------------------------------
 // B1: bit planes. plane(f,k)[y][wd] bit b = gray(f, y, 32*wd + b) > thr_k
@@ -95,8 +102,17 @@ __device__ __forceinline__ uint32_t slices_gt(const uint32_t (&S)[8], int t)
 __global__ void __launch_bounds__(128)
 blob_binarize_kernel(FrameSet fs, BlobGeom g, uint32_t* __restrict__ planes, int aligned)
 {
-    const int wd = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (wd >= g.wpr) return;
+    // one thread per storage word: the frame of background words around the image is written here too
+    const int ws = blockIdx.x * blockDim.x + threadIdx.x, ys = blockIdx.y, f = blockIdx.z;
+    if (ws >= g.wpr) return;
+    uint32_t* out = planes + (size_t)f * kNThr * g.plane_words + (size_t)ys * g.wpr + ws;
+    const int wd = ws - 1, y = ys - 1;
+    if (y < 0 || y >= g.h || wd < 0 || wd * 32 >= g.w)
+    {
+#pragma unroll
+        for (int k = 0; k < kNThr; k++) out[(size_t)k * g.plane_words] = 0u;
+        return;
+    }
     const uint8_t* row = fs.base + (size_t)f * fs.frame_stride + (size_t)y * fs.pitch;
     const int x0 = wd * 32;
     uint32_t W[8];
@@ -146,39 +162,94 @@ blob_binarize_kernel(FrameSet fs, BlobGeom g, uint32_t* __restrict__ planes, int
             S[b] |= sh & (0x01010101u << j);
         }
     }
-    uint32_t* out = planes + ((size_t)f * kNThr * g.h + y) * g.wpr + wd;
-    const size_t plane_words = (size_t)g.h * g.wpr;
 #pragma unroll
-    for (int k = 0; k < kNThr; k++) out[(size_t)k * plane_words] = slices_gt(S, thr_value(k));
+    for (int k = 0; k < kNThr; k++) out[(size_t)k * g.plane_words] = slices_gt(S, thr_value(k));
 }
 
 // ------------------------------------------------------------------------------------------------
-// B2a: candidate starts + verification walk (see blob_walk.cuh)
+// B2a: candidate starts (blob_scan_kernel) and their verification walks (blob_walk_kernel); see blob_walk.cuh
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileRows  = 16;                  // a tile = 32 words (1024 pixels) x 16 rows of one plane
-constexpr int kListCap   = 2048;                // per-warp candidate list; a row adds at most 1024
-constexpr int kWalkWarps = 4;
+constexpr int kTileRows  = 16;                  // a tile = 32 words (1024 pixels) x 16 rows of one plane, one warp
 constexpr unsigned kFull = 0xffffffffu;
+// queue entry: job << 32 | kind << 30 | y << 15 | x   (kind 0: first pixel of a component, 1: first pixel of a hole)
 
-__global__ void __launch_bounds__(kWalkWarps * 32)
-blob_walk_kernel(BlobGeom g, const uint32_t* __restrict__ planes, BlobRecord* __restrict__ recs,
+__global__ void __launch_bounds__(256)
+blob_scan_kernel(BlobGeom g, const uint32_t* __restrict__ planes, unsigned long long* __restrict__ queue,
                  unsigned* __restrict__ counters, unsigned ntiles, int nstrips, int ncb)
 {
-    __shared__ uint16_t s_list[kWalkWarps][kListCap];
     const int lane = threadIdx.x & 31;
-    uint16_t* list = s_list[threadIdx.x >> 5];
-    const size_t plane_words = (size_t)g.h * g.wpr;
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const unsigned njobs = (unsigned)g.nframes * kNThr;
+    // tile order: the first strip of every plane, then the second, ...: the longest borders (frame- and board-sized
+    // outlines) start near the top of their planes, so they are at the head of the queue and are walked first
+    for (unsigned t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ntiles; t += nwarps)
+    {
+        const int job = (int)(t % njobs);
+        const int cb = (int)((t / njobs) % (unsigned)ncb), st = (int)(t / (njobs * (unsigned)ncb));
+        const int y0 = st * kTileRows, rows = min(kTileRows, g.h - y0), wd = cb * 32 + lane;
+        const uint32_t* B = plane_ptr(g, planes, job);
+        const bool in = wd * 32 < g.w;                      // (words past the image are background; so are rows -1 and h)
+        // the tile's rows -1 .. rows-1 of this lane's word column, all loads in flight at once; the words of the
+        // neighbouring columns come from the neighbouring lanes (lanes 0 and 31 load theirs)
+        uint32_t c[kTileRows + 1], el[kTileRows + 1], er[kTileRows + 1];
+#pragma unroll
+        for (int r = 0; r <= kTileRows; r++) c[r] = (in && r <= rows) ? B[(y0 + r - 1) * g.wpr + wd] : 0u;
+        if (lane == 0 || lane == 31)
+        {
+            const int wn = lane == 0 ? wd - 1 : wd + 1;
+#pragma unroll
+            for (int r = 0; r <= kTileRows; r++) el[r] = (in && r <= rows) ? B[(y0 + r - 1) * g.wpr + wn] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r <= kTileRows; r++)
+        {
+            const uint32_t l = __shfl_up_sync(kFull, c[r], 1), rr = __shfl_down_sync(kFull, c[r], 1);
+            er[r] = lane == 31 ? el[r] : rr;
+            el[r] = lane == 0 ? el[r] : l;
+        }
+        uint32_t outer[kTileRows], hole[kTileRows];
+        unsigned cnt = 0;
+#pragma unroll
+        for (int r = 0; r < kTileRows; r++)
+        {
+            candidate_masks(c[r + 1], el[r + 1], c[r], el[r], er[r], &outer[r], &hole[r]);
+            if (r >= rows) { outer[r] = 0; hole[r] = 0; }
+            cnt += __popc(outer[r]) + __popc(hole[r]);
+        }
+        if (__ballot_sync(kFull, cnt != 0))
+        {
+            unsigned incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+            unsigned base = 0;
+            if (lane == 31) base = atomicAdd(&counters[kCntQueue], incl);
+            base = __shfl_sync(kFull, base, 31);
+            unsigned at = base + incl - cnt;
+#pragma unroll
+            for (int r = 0; r < kTileRows; r++)
+            {
+                if ((outer[r] | hole[r]) == 0) continue;
+                const unsigned long long hi = (unsigned long long)job << 32 | (unsigned)(y0 + r) << 15 | (unsigned)(wd * 32);
+                uint32_t m = outer[r];
+                while (m) { const int bb = __ffs(m) - 1; m &= m - 1; if (at < g.queue_cap) queue[at] = hi | (unsigned)bb; at++; }
+                m = hole[r];
+                while (m) { const int bb = __ffs(m) - 1; m &= m - 1; if (at < g.queue_cap) queue[at] = hi | 1ull << 30 | (unsigned)bb; at++; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+blob_walk_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsigned long long* __restrict__ queue,
+                 BlobRecord* __restrict__ recs, unsigned* __restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned qn_all = counters[kCntQueue];
+    if (qn_all > g.queue_cap) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(&counters[kCntStatus], 1u); return; }
+    const unsigned qn = qn_all;
     const long long max_steps = 4LL * g.w * g.h + 16;
 
-    // the warp's candidate source (warp-uniform): a list of entries found in rows [.., tile_row) of the current tile
-    unsigned list_n = 0, list_head = 0;
-    int tile_row = 0, tile_rows = 0, tjob = 0, ty0 = 0, twd0 = 0;
-    bool src_done = false;
-    uint32_t up = 0, upl = 0, upr = 0;          // this lane's words of the row above the next one to scan
-    const uint32_t* TB = planes;                // plane of the current tile
-
-    // the lane's border
-    bool active = false;
+    bool active = false, more = true;
     PlaneRef P; P.B = planes; P.w = g.w; P.h = g.h; P.wpr = g.wpr;
     BitWindow F, Bk;
     int fx = 0, fy = 0, fk = 0, bx = 0, by = 0, bk = 0, pos = 0, cnt = 0, sx = 0, sy = 0, sk = 0, job = 0;
@@ -186,97 +257,48 @@ blob_walk_kernel(BlobGeom g, const uint32_t* __restrict__ planes, BlobRecord* __
 
     for (;;)
     {
-        unsigned idle = __ballot_sync(kFull, !active);
-        while (idle && !src_done)
+        // idle lanes take the queue's next candidates
+        const unsigned idle = __ballot_sync(kFull, !active);
+        if (idle && more)
         {
-            if (list_head == list_n)
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&counters[kCntQueueHead], (unsigned)__popc(idle));
+            base = __shfl_sync(kFull, base, 0);
+            more = base < qn;
+            const unsigned my = base + __popc(idle & ((1u << lane) - 1u));
+            if (!active && my < qn)
             {
-                list_head = list_n = 0;
-                int budget = kTileRows;
-                while (list_n == 0 && !src_done && (budget > 0 || idle == kFull))
-                {
-                    budget--;
-                    if (tile_row >= tile_rows)
-                    {
-                        unsigned t = 0;
-                        if (lane == 0) t = atomicAdd(&counters[kCntTile], 1u);
-                        t = __shfl_sync(kFull, t, 0);
-                        if (t >= ntiles) { src_done = true; break; }
-                        // tile order: the first strip of every plane, then the second, ...: the longest borders (frame-
-                        // and board-sized outlines) start near the top of their planes and so start early
-                        const unsigned njobs = (unsigned)g.nframes * kNThr;
-                        tjob = (int)(t % njobs);
-                        const int cb = (int)((t / njobs) % (unsigned)ncb), st = (int)(t / (njobs * (unsigned)ncb));
-                        ty0 = st * kTileRows; twd0 = cb * 32;
-                        tile_rows = min(kTileRows, g.h - ty0); tile_row = 0;
-                        TB = planes + (size_t)tjob * plane_words;
-                        const int wd = twd0 + lane, yu = ty0 - 1;
-                        up = (yu >= 0 && wd < g.wpr) ? TB[(size_t)yu * g.wpr + wd] : 0u;
-                        upl = __shfl_up_sync(kFull, up, 1); upr = __shfl_down_sync(kFull, up, 1);
-                        if (lane == 0)  upl = (yu >= 0 && wd > 0) ? TB[(size_t)yu * g.wpr + wd - 1] : 0u;
-                        if (lane == 31) upr = (yu >= 0 && wd + 1 < g.wpr) ? TB[(size_t)yu * g.wpr + wd + 1] : 0u;
-                    }
-                    while (tile_row < tile_rows && list_n <= (unsigned)(kListCap - 1024))
-                    {
-                        const int wd = twd0 + lane, y = ty0 + tile_row;
-                        const uint32_t cur = wd < g.wpr ? TB[(size_t)y * g.wpr + wd] : 0u;
-                        uint32_t left = __shfl_up_sync(kFull, cur, 1), right = __shfl_down_sync(kFull, cur, 1);
-                        if (lane == 0)  left  = wd > 0 ? TB[(size_t)y * g.wpr + wd - 1] : 0u;
-                        if (lane == 31) right = wd + 1 < g.wpr ? TB[(size_t)y * g.wpr + wd + 1] : 0u;
-                        uint32_t outer, hole;
-                        candidate_masks(cur, left, up, upl, upr, &outer, &hole);
-                        up = cur; upl = left; upr = right;
-                        const unsigned c = __popc(outer) + __popc(hole);
-                        if (__ballot_sync(kFull, c != 0))
-                        {
-                            unsigned incl = c;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-                            unsigned at = list_n + incl - c;
-                            const unsigned rowbits = (unsigned)tile_row << 10 | (unsigned)lane << 5;
-                            while (outer) { const int b = __ffs(outer) - 1; outer &= outer - 1; list[at++] = (uint16_t)(rowbits | b); }
-                            while (hole)  { const int b = __ffs(hole) - 1;  hole &= hole - 1;   list[at++] = (uint16_t)(0x4000u | rowbits | b); }
-                            list_n += __shfl_sync(kFull, incl, 31);
-                        }
-                        tile_row++;
-                    }
-                }
-                __syncwarp();
-                if (list_n == 0) break;
-            }
-            // the list's next entries go to the idle lanes, in lane order
-            const unsigned avail = list_n - list_head, rank = __popc(idle & ((1u << lane) - 1u));
-            if (!active && rank < avail)
-            {
-                const unsigned e = list[list_head + rank];
-                const int x = twd0 * 32 + (int)(e & 1023u), y = ty0 + (int)((e >> 10) & 15u);
-                job = tjob; P.B = TB;
+                const unsigned long long e = queue[my];
+                const int x = (int)(e & 0x7FFFu), y = (int)((e >> 15) & 0x7FFFu);
+                job = (int)(e >> 32); P.B = plane_ptr(g, planes, job);
                 F.init(); Bk.init();
                 pos = y * g.w + x;
                 bool ok = true;
-                if (e & 0x4000u) { sx = x - 1; sy = y; sk = 1; }
+                if ((e >> 30) & 1u) { sx = x - 1; sy = y; sk = 1; }
                 else { sx = x; sy = y; ok = outer_start(P, F, x, y, &sk); }          // false: isolated pixel, area 0
                 if (ok) { fx = bx = sx; fy = by = sy; fk = bk = sk; a00 = 0; cnt = 0; active = true; }
             }
-            list_head += min(avail, (unsigned)__popc(idle));
-            idle = __ballot_sync(kFull, !active);
         }
-        if (!__any_sync(kFull, active)) { if (src_done) break; continue; }
+        if (!__any_sync(kFull, active)) { if (!more) break; continue; }
 
 #pragma unroll 1
-        for (int it = 0; it < 16; it++)
+        for (int it = 0; it < 8; it++)
         {
             if (active)
             {
-                int disc;
-                { const int px = fx, py = fy; step_fwd(P, F, fx, fy, fk, &disc); a00 += (long long)(px * fy - fx * py); cnt++; }
-                bool drop = disc >= 0 && disc < pos;
-                bool met = !drop && fx == bx && fy == by && fk == bk;
+                // Both walkers step every time, as two independent dependency chains; the backward step is thrown
+                // away when the forward one already decided (order of the tests as in blobwalk::verify_start).
+                int discf, discb;
+                const int px = fx, py = fy, qx = bx, qy = by, qk = bk;
+                step_fwd(P, F, fx, fy, fk, &discf);
+                step_bwd(P, Bk, bx, by, bk, &discb);
+                a00 += (long long)(px * fy - fx * py); cnt++;
+                bool drop = discf >= 0 && discf < pos;
+                bool met = !drop && fx == qx && fy == qy && fk == qk;
                 if (!drop && !met)
                 {
-                    const int qx = bx, qy = by;
-                    step_bwd(P, Bk, bx, by, bk, &disc); a00 += (long long)(bx * qy - qx * by); cnt++;
-                    drop = disc >= 0 && disc < pos;
+                    a00 += (long long)(bx * qy - qx * by); cnt++;
+                    drop = discb >= 0 && discb < pos;
                     met = !drop && fx == bx && fy == by && fk == bk;
                 }
                 if (!drop && !met && cnt > max_steps) { atomicExch(&counters[kCntStatus], 2u); drop = true; }   // cannot happen
@@ -318,7 +340,6 @@ blob_points_kernel(BlobGeom g, const uint32_t* __restrict__ planes, BlobRecord* 
     const int lane = threadIdx.x & 31;
     const unsigned nrec = min(counters[kCntRecords], g.rec_cap);
     if (counters[kCntStatus]) return;
-    const size_t plane_words = (size_t)g.h * g.wpr;
     PlaneRef P; P.B = planes; P.w = g.w; P.h = g.h; P.wpr = g.wpr;
     BitWindow F;
     bool active = false, more = true;
@@ -341,7 +362,7 @@ blob_points_kernel(BlobGeom g, const uint32_t* __restrict__ planes, BlobRecord* 
                 if (ri < nrec)
                 {
                     const BlobRecord& r = recs[ri];
-                    P.B = planes + ((size_t)r.frame * kNThr + r.thr) * plane_words;
+                    P.B = plane_ptr(g, planes, r.frame * kNThr + r.thr);
                     F.init();
                     x = r.sx; y = r.sy; k = r.sk; n = r.n; i = 0; out = pts + r.pts_off;
                     t10 = t01 = t20 = t11 = t02 = 0;
@@ -428,8 +449,8 @@ __device__ bool centre_and_colour(BlobRecord& r, const BlobGeom& g, const uint32
     int ok = 0;
     if (rx >= 0 && rx < g.w && ry >= 0 && ry < g.h)
     {
-        const uint32_t* B = planes + ((size_t)r.frame * kNThr + r.thr) * g.h * g.wpr;
-        ok = !((B[(size_t)ry * g.wpr + (rx >> 5)] >> (rx & 31)) & 1u);
+        const uint32_t* B = plane_ptr(g, planes, r.frame * kNThr + r.thr);
+        ok = !((B[ry * g.wpr + (rx >> 5)] >> (rx & 31)) & 1u);
     }
     r.colour_ok = ok;
     return ok != 0;
@@ -728,12 +749,17 @@ int group_frame(const BlobRecord* all, const unsigned* order, int nrec, int32_t*
 struct BlobWorkspace
 {
     void* planes = nullptr; void* pts = nullptr; void* recs = nullptr;
-    void* scratch = nullptr; void* counters = nullptr;
-    size_t planes_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0;
-    unsigned pts_per_frame = 1u << 21, rec_per_job = 512;
+    void* scratch = nullptr; void* counters = nullptr; void* queue = nullptr;
+    size_t planes_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0, queue_b = 0;
+    unsigned pts_per_frame = 1u << 21, rec_per_job = 512, queue_per_frame = 1u << 18;
     BlobRecord* host_recs = nullptr; size_t host_recs_cap = 0;      // pinned
+    unsigned* host_counters = nullptr;                              // pinned
     std::vector<unsigned> order, first;
     bool warp_smem_set = false;
+    // the chunk in flight (blob_enqueue .. blob_finish)
+    bool pending = false;
+    BlobGeom g; cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, done = nullptr;
 };
 
 BlobWorkspace* blob_workspace_create() { return new BlobWorkspace(); }
@@ -741,8 +767,12 @@ void blob_workspace_destroy(BlobWorkspace* ws)
 {
     if (!ws) return;
     cudaFree(ws->planes); cudaFree(ws->pts); cudaFree(ws->recs);
-    cudaFree(ws->scratch); cudaFree(ws->counters);
+    cudaFree(ws->scratch); cudaFree(ws->counters); cudaFree(ws->queue);
     if (ws->host_recs) cudaFreeHost(ws->host_recs);
+    if (ws->host_counters) cudaFreeHost(ws->host_counters);
+    if (ws->e0) cudaEventDestroy(ws->e0);
+    if (ws->e1) cudaEventDestroy(ws->e1);
+    if (ws->done) cudaEventDestroy(ws->done);
     delete ws;
 }
 
@@ -759,22 +789,27 @@ static cudaError_t grow(void** p, size_t* have, size_t want)
 #define BLOB_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
     fprintf(stderr, "%s:%d in %s(): CUDA failure '%s' in " #expr ". Sorry.\n", __FILE__, __LINE__, __func__, cudaGetErrorString(_e)); return -1; } } while (0)
 
-// Blob detection over device-resident frames. xy_out: HOST [nframes][max_points][2] int32 (scaled
-// by 1000), counts_out: HOST [nframes]. Synchronous. Returns 0, -1 on a CUDA failure, or 1 when the
-// scratch of a multi-frame chunk overflowed (nothing was produced: run the frames one at a time).
-void blob_workspace_reset_capacity(BlobWorkspace* ws) { ws->pts_per_frame = 1u << 21; ws->rec_per_job = 512; }
+void blob_workspace_reset_capacity(BlobWorkspace* ws) { ws->pts_per_frame = 1u << 21; ws->rec_per_job = 512; ws->queue_per_frame = 1u << 18; }
 
-int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
-                     cudaStream_t stream, float* ms_out)
+// Enqueues the kernels of one chunk of device-resident frames on `stream` (nothing is waited for; the frames may
+// be overwritten once the first kernel has run, i.e. after whatever is enqueued next on `stream`). Returns 0 / -1.
+int blob_enqueue(BlobWorkspace* ws, const FrameSet& fs, cudaStream_t stream)
 {
+    if (ws->pending) { fprintf(stderr, "%s:%d in %s(): a chunk is already in flight on this workspace. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
     const int n = fs.nframes;
-    for (int i = 0; i < n; i++) counts_out[i] = 0;
-    if (n <= 0 || fs.w <= 0 || fs.h <= 0) return 0;
-    BlobGeom g;
-    g.w = fs.w; g.h = fs.h; g.wpr = ((fs.w + 31) / 32 + 3) & ~3; g.nframes = n;      // rows of the planes: multiples of 16 bytes
-    const size_t plane_words = (size_t)n * kNThr * g.h * g.wpr;
-    BLOB_TRY(grow(&ws->planes, &ws->planes_b, plane_words * 4));
+    BlobGeom& g = ws->g;
+    g.w = fs.w; g.h = fs.h; g.wpr = plane_wpr(fs.w); g.nframes = n;
+    g.plane_words = (size_t)plane_rows(fs.h) * g.wpr; g.origin = plane_origin(fs.w);
+    ws->stream = stream;
+    if (n <= 0 || fs.w <= 0 || fs.h <= 0) { g.nframes = 0; ws->pending = true; return 0; }
+    BLOB_TRY(grow(&ws->planes, &ws->planes_b, (size_t)n * kNThr * g.plane_words * 4));
     if (!ws->counters) BLOB_TRY(cudaMalloc(&ws->counters, kCntWords * 4));
+    if (!ws->host_counters) BLOB_TRY(cudaMallocHost((void**)&ws->host_counters, kCntWords * 4));
+    if (!ws->e0)
+    {
+        BLOB_TRY(cudaEventCreate(&ws->e0)); BLOB_TRY(cudaEventCreate(&ws->e1));
+        BLOB_TRY(cudaEventCreateWithFlags(&ws->done, cudaEventDisableTiming));
+    }
     const int b3_blocks = 148 * 4;
     const int scratch_stride = 4 * fs.w + 8;
     BLOB_TRY(grow(&ws->scratch, &ws->scratch_b, (size_t)b3_blocks * scratch_stride * sizeof(int)));
@@ -789,44 +824,51 @@ int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int
     const unsigned long long ntiles64 = (unsigned long long)n * kNThr * nstrips * ncb;
     if (ntiles64 >= 0xFFFFFFFFull) { fprintf(stderr, "%s:%d in %s(): too many frames in one blob chunk. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
 
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ms_out) { cudaEventCreate(&e0); cudaEventCreate(&e1); *ms_out = 0; }
-    unsigned nrec = 0;
-    for (int attempt = 0; ; attempt++)
-    {
-        const unsigned long long want_pts = (unsigned long long)ws->pts_per_frame * n;
-        g.pts_cap = (unsigned)std::min<unsigned long long>(want_pts, 0xFFFFFFF0ull);
-        g.rec_cap = (unsigned)std::min<unsigned long long>((unsigned long long)ws->rec_per_job * n * kNThr, 0x7FFFFFFFull);
-        BLOB_TRY(grow(&ws->pts, &ws->pts_b, (size_t)g.pts_cap * 4));
-        BLOB_TRY(grow(&ws->recs, &ws->recs_b, (size_t)g.rec_cap * sizeof(BlobRecord)));
-        unsigned* counters = (unsigned*)ws->counters;
-        BLOB_TRY(cudaMemsetAsync(ws->counters, 0, kCntWords * 4, stream));
-        if (e0) cudaEventRecord(e0, stream);
-        blob_binarize_kernel<<<dim3((g.wpr + 127) / 128, g.h, n), 128, 0, stream>>>(fs, g, (uint32_t*)ws->planes, aligned);
-        blob_walk_kernel<<<148 * 4, kWalkWarps * 32, 0, stream>>>(g, (const uint32_t*)ws->planes, (BlobRecord*)ws->recs, counters,
-                                                                 (unsigned)ntiles64, nstrips, ncb);
-        blob_points_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (BlobRecord*)ws->recs, counters, (uint32_t*)ws->pts);
-        blob_contour_warp_kernel<<<148 * 2, kW3Warps * 32, kW3Warps * sizeof(WarpScratch), stream>>>(
-            g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts, (BlobRecord*)ws->recs, counters);
-        blob_contour_kernel<<<b3_blocks, kB3Threads, 0, stream>>>(g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts,
-                                                                  (BlobRecord*)ws->recs, counters, (int*)ws->scratch, scratch_stride);
-        if (e1) cudaEventRecord(e1, stream);
-        BLOB_TRY(cudaGetLastError());
-        unsigned hc[kCntWords];
-        BLOB_TRY(cudaMemcpyAsync(hc, ws->counters, kCntWords * 4, cudaMemcpyDeviceToHost, stream));
-        BLOB_TRY(cudaStreamSynchronize(stream));
-        if (e0) { float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms_out += t; }
-        if (hc[kCntStatus] == 2) { fprintf(stderr, "%s:%d in %s(): a border walk did not close. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
-        const bool overflow = hc[kCntStatus] != 0 || hc[kCntRecords] > g.rec_cap;
-        if (!overflow) { nrec = hc[kCntRecords]; break; }
-        // The point region or the record list overflowed. A single frame is run again with four times the
-        // space; a chunk of several frames is handed back to the caller, who runs its frames one by one
-        // (growing the scratch for a whole chunk could ask for tens of GB because of one busy frame).
-        if (n > 1) { if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return 1; }
-        if (attempt >= 6) { fprintf(stderr, "%s:%d in %s(): blob scratch still overflows after growing it 4096x. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
-        ws->pts_per_frame = ws->pts_per_frame >= (1u << 29) ? ws->pts_per_frame : ws->pts_per_frame * 4; ws->rec_per_job *= 4;
-    }
-    if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    const unsigned long long want_pts = (unsigned long long)ws->pts_per_frame * n;
+    g.pts_cap = (unsigned)std::min<unsigned long long>(want_pts, 0xFFFFFFF0ull);
+    g.rec_cap = (unsigned)std::min<unsigned long long>((unsigned long long)ws->rec_per_job * n * kNThr, 0x7FFFFFFFull);
+    g.queue_cap = (unsigned)std::min<unsigned long long>((unsigned long long)ws->queue_per_frame * n, 0x7FFFFFFFull);
+    BLOB_TRY(grow(&ws->queue, &ws->queue_b, (size_t)g.queue_cap * 8));
+    BLOB_TRY(grow(&ws->pts, &ws->pts_b, (size_t)g.pts_cap * 4));
+    BLOB_TRY(grow(&ws->recs, &ws->recs_b, (size_t)g.rec_cap * sizeof(BlobRecord)));
+    unsigned* counters = (unsigned*)ws->counters;
+    BLOB_TRY(cudaMemsetAsync(ws->counters, 0, kCntWords * 4, stream));
+    BLOB_TRY(cudaEventRecord(ws->e0, stream));
+    blob_binarize_kernel<<<dim3((g.wpr + 127) / 128, plane_rows(g.h), n), 128, 0, stream>>>(fs, g, (uint32_t*)ws->planes, aligned);
+    blob_scan_kernel<<<148 * 8, 256, 0, stream>>>(g, (const uint32_t*)ws->planes, (unsigned long long*)ws->queue, counters,
+                                                  (unsigned)ntiles64, nstrips, ncb);
+    blob_walk_kernel<<<148 * 6, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (const unsigned long long*)ws->queue,
+                                                  (BlobRecord*)ws->recs, counters);
+    blob_points_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (BlobRecord*)ws->recs, counters, (uint32_t*)ws->pts);
+    blob_contour_warp_kernel<<<148 * 2, kW3Warps * 32, kW3Warps * sizeof(WarpScratch), stream>>>(
+        g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts, (BlobRecord*)ws->recs, counters);
+    blob_contour_kernel<<<b3_blocks, kB3Threads, 0, stream>>>(g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts,
+                                                              (BlobRecord*)ws->recs, counters, (int*)ws->scratch, scratch_stride);
+    BLOB_TRY(cudaEventRecord(ws->e1, stream));
+    BLOB_TRY(cudaGetLastError());
+    BLOB_TRY(cudaMemcpyAsync(ws->host_counters, ws->counters, kCntWords * 4, cudaMemcpyDeviceToHost, stream));
+    BLOB_TRY(cudaEventRecord(ws->done, stream));
+    ws->pending = true;
+    return 0;
+}
+
+// Waits for the chunk enqueued last, then groups its records on the host. xy_out: HOST [nframes][max_points][2]
+// int32 (scaled by 1000), counts_out: HOST [nframes]. ms_out (optional): device time of the kernels is ADDED.
+// Returns 0, -1 on a CUDA failure, or 1 when the chunk's scratch overflowed (nothing was produced).
+int blob_finish(BlobWorkspace* ws, int32_t* xy_out, int32_t* counts_out, int max_points, float* ms_out)
+{
+    if (!ws->pending) return -1;
+    ws->pending = false;
+    const BlobGeom& g = ws->g;
+    const int n = g.nframes;
+    for (int i = 0; i < n; i++) counts_out[i] = 0;
+    if (n <= 0) return 0;
+    BLOB_TRY(cudaEventSynchronize(ws->done));
+    if (ms_out) { float t = 0; cudaEventElapsedTime(&t, ws->e0, ws->e1); *ms_out += t; }
+    const unsigned* hc = ws->host_counters;
+    if (hc[kCntStatus] == 2) { fprintf(stderr, "%s:%d in %s(): a border walk did not close. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
+    if (hc[kCntStatus] != 0 || hc[kCntRecords] > g.rec_cap) return 1;
+    const unsigned nrec = hc[kCntRecords];
     if (!nrec) return 0;
 
     if (ws->host_recs_cap < nrec)
@@ -837,8 +879,8 @@ int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int
         BLOB_TRY(cudaMallocHost((void**)&ws->host_recs, cap * sizeof(BlobRecord)));
         ws->host_recs_cap = cap;
     }
-    BLOB_TRY(cudaMemcpyAsync(ws->host_recs, ws->recs, sizeof(BlobRecord) * nrec, cudaMemcpyDeviceToHost, stream));
-    BLOB_TRY(cudaStreamSynchronize(stream));
+    BLOB_TRY(cudaMemcpyAsync(ws->host_recs, ws->recs, sizeof(BlobRecord) * nrec, cudaMemcpyDeviceToHost, ws->stream));
+    BLOB_TRY(cudaStreamSynchronize(ws->stream));
     const BlobRecord* R = ws->host_recs;
     // records by frame (counting sort of indices), then each frame ordered and grouped on its own: frames are
     // independent, so they are spread over host threads
@@ -875,6 +917,25 @@ int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int
         for (auto& th : pool) th.join();
     }
     return 0;
+}
+
+// One chunk, synchronously. A single frame whose scratch overflows is run again with four times the space; a chunk
+// of several frames that overflows is handed back to the caller (return 1), who runs its frames one by one (growing
+// the scratch for a whole chunk could ask for tens of GB because of one busy frame).
+int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
+                     cudaStream_t stream, float* ms_out)
+{
+    if (ms_out) *ms_out = 0;
+    for (int attempt = 0; ; attempt++)
+    {
+        if (blob_enqueue(ws, fs, stream)) return -1;
+        const int rc = blob_finish(ws, xy_out, counts_out, max_points, ms_out);
+        if (rc <= 0) return rc;
+        if (fs.nframes > 1) return 1;
+        if (attempt >= 6) { fprintf(stderr, "%s:%d in %s(): blob scratch still overflows after growing it 4096x. Sorry.\n", __FILE__, __LINE__, __func__); return -1; }
+        ws->pts_per_frame = ws->pts_per_frame >= (1u << 29) ? ws->pts_per_frame : ws->pts_per_frame * 4; ws->rec_per_job *= 4;
+        ws->queue_per_frame = ws->queue_per_frame >= (1u << 28) ? ws->queue_per_frame : ws->queue_per_frame * 4;
+    }
 }
 
 }

@@ -118,6 +118,11 @@ void           blob_workspace_destroy(BlobWorkspace* ws);
 // Returns 0; -1 on a CUDA failure; 1 if the scratch of a multi-frame chunk overflowed (nothing was
 // produced: call again frame by frame, then blob_workspace_reset_capacity()).
 void blob_workspace_reset_capacity(BlobWorkspace* ws);
+// The two halves of blob_find_frames for callers that keep two chunks in flight (one workspace each): enqueue the
+// kernels of a chunk on a stream; later wait for it and group its records on the host (same return values; ms is
+// added to *ms_out).
+int blob_enqueue(BlobWorkspace* ws, const FrameSet& fs, cudaStream_t stream);
+int blob_finish(BlobWorkspace* ws, int32_t* xy_out, int32_t* counts_out, int max_points, float* ms_out);
 int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
                      cudaStream_t stream, float* ms_out);
 

@@ -18,18 +18,19 @@ struct Found { int pos, x, y, k, n; long long a00; };
 extern "C" int blob_walk_host_contours(const uint8_t* bin, int w, int h, int stride, int32_t* xy, int max_pts,
                                        int32_t* lens, long long* area2, int max_cont)
 {
-    const int wpr = ((w + 31) / 32 + 3) & ~3;
-    std::vector<uint32_t> plane((size_t)wpr * h, 0u);
+    const int wpr = plane_wpr(w), words = (w + 31) / 32;
+    std::vector<uint32_t> storage((size_t)wpr * plane_rows(h), 0u);
+    uint32_t* plane = storage.data() + plane_origin(w);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++)
             if (bin[(size_t)y * stride + x]) plane[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
-    PlaneRef P{ plane.data(), w, h, wpr };
+    PlaneRef P{ plane, w, h, wpr };
     BitWindow F, Bk;
     F.init(); Bk.init();
     std::vector<Found> found;
-    auto word = [&](int y, int wd) -> uint32_t { return (y >= 0 && y < h && wd >= 0 && wd < wpr) ? plane[(size_t)y * wpr + wd] : 0u; };
+    auto word = [&](int y, int wd) -> uint32_t { return plane[y * wpr + wd]; };       // y in [-1, h], wd in [-1, words]
     for (int y = 0; y < h; y++)
-        for (int wd = 0; wd < wpr; wd++)
+        for (int wd = 0; wd < words; wd++)
         {
             uint32_t outer, hole;
             candidate_masks(word(y, wd), word(y, wd - 1), word(y - 1, wd), word(y - 1, wd - 1), word(y - 1, wd + 1), &outer, &hole);
