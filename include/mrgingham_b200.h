@@ -179,6 +179,24 @@ int mrg_b200_find_corners_batch(mrg_b200_detector* det,
                                 int32_t* xy_out, int32_t* counts_out,
                                 void* stream);
 
+/* The same over images of ANY sizes in one call: what the reference CLI does with a glob of images of whatever
+   sizes, one per worker iteration (mrgingham-from-image.cc:50-54, 374-379). Images are grouped by size inside;
+   each group goes through the batch path above (device images that lie at a fixed stride are read in place).
+     images           HOST array of nimages descriptors; `data` is host or device memory per images_on_device
+     xy_out           HOST int32 [nimages][max_points][2] (x, y scaled by 1000), in the order of `images`
+     counts_out       HOST int32 [nimages]
+   Every image must fit the detector's max_rows x max_cols. Synchronous. Returns 0 or <0. */
+typedef struct mrg_b200_image_desc
+{
+    const uint8_t* data;
+    int            rows, cols;
+    size_t         row_pitch;    /* bytes between rows, >= cols */
+} mrg_b200_image_desc;
+int mrg_b200_find_corners_mixed_batch(mrg_b200_detector* det,
+                                      const mrg_b200_image_desc* images, int nimages, int images_on_device,
+                                      int image_pyramid_level,
+                                      int32_t* xy_out, int32_t* counts_out, void* stream);
+
 /* Same work, split so a caller can time the device part with its own CUDA events:
    enqueue() only enqueues (copies, kernels, result copies into the detector's pinned buffers) on
    `stream`; collect() synchronises that stream, handles overflowed frames and fills the outputs. */

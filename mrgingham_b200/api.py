@@ -21,6 +21,7 @@ EXPORTS = (
     "mrg_b200_find_chessboard_corners", "mrg_b200_refine_chessboard_corners",
     "mrg_b200_detector_create", "mrg_b200_detector_destroy",
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
+    "mrg_b200_find_corners_mixed_batch",
     "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch", "mrg_b200_box_blur_batch",
     "mrg_b200_preprocess_batch",
     "find_chessboard_from_image_array_C", "mrg_b200_find_grid_from_points", "mrg_b200_voronoi_neighbours",
@@ -29,6 +30,11 @@ EXPORTS = (
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
     "mrg_b200_device_count",
 )
+
+
+class ImageDesc(ctypes.Structure):
+    """mrg_b200_image_desc: one image of a mixed-size batch"""
+    _fields_ = [("data", ctypes.c_void_p), ("rows", ctypes.c_int), ("cols", ctypes.c_int), ("row_pitch", ctypes.c_size_t)]
 
 
 class DetectorConfig(ctypes.Structure):
@@ -88,6 +94,9 @@ def lib():
     L.mrg_b200_find_corners_batch.argtypes = batch_args + [_i32p, _i32p, ctypes.c_void_p]
     L.mrg_b200_find_corners_batch_enqueue.restype = ctypes.c_int
     L.mrg_b200_find_corners_batch_enqueue.argtypes = batch_args + [ctypes.c_void_p]
+    L.mrg_b200_find_corners_mixed_batch.restype = ctypes.c_int
+    L.mrg_b200_find_corners_mixed_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(ImageDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    _i32p, _i32p, ctypes.c_void_p]
     L.mrg_b200_find_corners_batch_collect.restype = ctypes.c_int
     L.mrg_b200_find_corners_batch_collect.argtypes = [ctypes.c_void_p, _i32p, _i32p]
     L.mrg_b200_refine_corners_batch.restype = ctypes.c_int
@@ -388,6 +397,31 @@ class Detector:
         """returns (xy int32 [n, max_points, 2] scaled by 1000, counts int32 [n])"""
         self.enqueue(images, level, stream)
         return self.collect()
+
+    def find_corners_mixed(self, images, level=0, stream=None):
+        """One call over a list of images of ANY sizes (each a 2-D uint8 numpy array, or each a 2-D CUDA torch tensor),
+        as the reference CLI takes a glob of images (mrgingham-from-image.cc:50-54):
+        returns (xy int32 [n, max_points, 2] scaled by 1000, counts int32 [n]) in the order of `images`."""
+        n = len(images)
+        descs = (ImageDesc * max(n, 1))()
+        on_dev = None
+        for i, im in enumerate(images):
+            if isinstance(im, np.ndarray):
+                assert im.ndim == 2 and im.dtype == np.uint8 and (im.shape[1] == 1 or im.strides[1] == 1)
+                dev, ptr, pitch = 0, im.ctypes.data, im.strides[0]
+            else:
+                assert im.dim() == 2 and im.element_size() == 1 and im.stride(1) == 1
+                dev, ptr, pitch = (1 if im.is_cuda else 0), im.data_ptr(), im.stride(0)
+            assert on_dev in (None, dev), "host and device images cannot be mixed in one call"
+            on_dev = dev
+            descs[i] = ImageDesc(ptr, im.shape[0], im.shape[1], pitch)
+        xy = np.empty((n, self.max_points, 2), dtype=np.int32)
+        counts = np.zeros(n, dtype=np.int32)
+        rc = lib().mrg_b200_find_corners_mixed_batch(self._h, descs, n, on_dev or 0, int(level), _ptr(xy, _i32p), _ptr(counts, _i32p),
+                                                     ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_find_corners_mixed_batch() failed")
+        return xy, counts
 
     def find_blobs(self, images, stream=None):
         """batched blob detector: returns (xy int32 [n, max_points, 2] scaled by 1000, counts int32 [n])"""

@@ -153,6 +153,7 @@ struct mrg_b200_detector
     // board finder: the frames of the chunk being worked on, kept on the device across the level loop
     std::mutex   boards_mtx;
     DeviceBuffer boards_frames, boards_gather;
+    DeviceBuffer mixed_stage, mixed_srcs;     // mrg_b200_find_corners_mixed_batch(): one size group, contiguous; its sources
 
     struct Pending
     {
@@ -520,7 +521,7 @@ API void mrg_b200_detector_destroy(mrg_b200_detector* det)
         for (cudaEvent_t e : { S.staged, S.k1done, S.k2done }) if (e) cudaEventDestroy(e);
     }
     for (DeviceBuffer* b : { &det->big_cand, &det->big_table, &det->big_dfs, &det->big_records, &det->pts, &det->lvls, &det->boards_frames,
-                             &det->boards_gather }) b->release();
+                             &det->boards_gather, &det->mixed_stage, &det->mixed_srcs }) b->release();
     if (det->ev_fork) cudaEventDestroy(det->ev_fork);
     if (det->aux_stream) cudaStreamDestroy(det->aux_stream);
     if (det->copy_stream) cudaStreamDestroy(det->copy_stream);
@@ -567,6 +568,97 @@ API int mrg_b200_find_corners_batch(mrg_b200_detector* det, const uint8_t* image
     if (!det) return -1;
     return corners_batch_mp(det, images, images_on_device, nframes, rows, cols, row_pitch, frame_stride, image_pyramid_level,
                             det->cfg.max_points, xy_out, counts_out, stream);
+}
+
+// One call over images of ANY sizes (the reference CLI takes a glob of images and hands them to its workers one by
+// one, whatever their sizes: mrgingham-from-image.cc:50-54, 374-379). The images are grouped by (rows, cols); each
+// group is laid out contiguously on the device (host images: one copy each, straight into the group's staging
+// buffer; device images that already lie at a fixed stride are read in place) and goes through the batch path.
+API int mrg_b200_find_corners_mixed_batch(mrg_b200_detector* det, const mrg_b200_image_desc* images, int nimages,
+                                          int images_on_device, int image_pyramid_level,
+                                          int32_t* xy_out, int32_t* counts_out, void* stream_)
+{
+    if (!det || nimages < 0 || (nimages > 0 && (!images || !counts_out))) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    const int mp = det->cfg.max_points;
+    for (int i = 0; i < nimages; i++)
+    {
+        const mrg_b200_image_desc& d = images[i];
+        if (!d.data || d.rows <= 0 || d.cols <= 0 || d.row_pitch < (size_t)d.cols)
+        { MSG("Bad image %d (data=%p rows=%d cols=%d pitch=%zu).", i, (const void*)d.data, d.rows, d.cols, d.row_pitch); return -1; }
+        counts_out[i] = 0;
+    }
+    DEVICE_GUARD(det);
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+    std::vector<int> order(nimages);
+    for (int i = 0; i < nimages; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b)
+    {
+        if (images[a].rows != images[b].rows) return images[a].rows < images[b].rows;
+        if (images[a].cols != images[b].cols) return images[a].cols < images[b].cols;
+        return images[a].data < images[b].data;         // frames cut from one allocation end up at a fixed stride
+    });
+    std::vector<int32_t> txy, tcounts;
+    std::vector<GatherSrc> srcs;
+    const int super = std::max(1, 2 * det->cfg.max_frames);
+    for (int g0 = 0; g0 < nimages; )
+    {
+        const int rows = images[order[g0]].rows, cols = images[order[g0]].cols;
+        int g1 = g0;
+        while (g1 < nimages && images[order[g1]].rows == rows && images[order[g1]].cols == cols) g1++;
+        for (int c0 = g0; c0 < g1; c0 += super)
+        {
+            const int n = std::min(super, g1 - c0);
+            const mrg_b200_image_desc& first = images[order[c0]];
+            // device images at a fixed stride, in this order, with rows TMA can address: read in place
+            bool in_place = images_on_device != 0;
+            size_t fstride = n > 1 ? (size_t)(images[order[c0 + 1]].data - first.data) : first.row_pitch * rows;
+            for (int i = 0; i < n && in_place; i++)
+            {
+                const mrg_b200_image_desc& d = images[order[c0 + i]];
+                in_place = d.row_pitch == first.row_pitch && d.data == first.data + (size_t)i * fstride;
+            }
+            if (in_place && n > 1 && (images[order[c0 + 1]].data < first.data || fstride < first.row_pitch * rows)) in_place = false;
+            const uint8_t* base; size_t pitch;
+            if (in_place) { base = first.data; pitch = first.row_pitch; }
+            else
+            {
+                pitch = (size_t)round_up(cols, 16);
+                fstride = pitch * rows;
+                if (det->mixed_stage.ensure(fstride * n)) return -1;
+                if (images_on_device)
+                {
+                    // one gather kernel for the whole group (a copy call per image would cost more than the detector)
+                    srcs.resize(n);
+                    for (int i = 0; i < n; i++) { srcs[i].data = images[order[c0 + i]].data; srcs[i].pitch = images[order[c0 + i]].row_pitch; }
+                    if (det->mixed_srcs.ensure(sizeof(GatherSrc) * n)) return -1;
+                    CUDA_TRY(cudaMemcpyAsync(det->mixed_srcs.p, srcs.data(), sizeof(GatherSrc) * n, cudaMemcpyHostToDevice, stream));
+                    CUDA_TRY(cudaStreamSynchronize(stream));       // (srcs is reused by the next group)
+                    CUDA_TRY(launch_gather_frames((const GatherSrc*)det->mixed_srcs.p, n, rows, cols, (uint8_t*)det->mixed_stage.p, pitch, fstride, stream));
+                }
+                else
+                    for (int i = 0; i < n; i++)
+                    {
+                        const mrg_b200_image_desc& d = images[order[c0 + i]];
+                        CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)det->mixed_stage.p + (size_t)i * fstride, pitch, d.data, d.row_pitch, cols, rows,
+                                                   cudaMemcpyHostToDevice, stream));
+                    }
+                base = (const uint8_t*)det->mixed_stage.p;
+            }
+            if (enqueue_locked(det, base, 1, n, rows, cols, pitch, fstride, image_pyramid_level, mp, stream)) return -1;
+            txy.resize((size_t)n * 2 * mp); tcounts.resize(n);
+            if (collect_locked(det, txy.data(), tcounts.data())) return -1;
+            for (int i = 0; i < n; i++)
+            {
+                const int dst = order[c0 + i];
+                counts_out[dst] = tcounts[i];
+                if (xy_out) memcpy(xy_out + (size_t)dst * 2 * mp, txy.data() + (size_t)i * 2 * mp, sizeof(int32_t) * 2 * mp);
+            }
+        }
+        g0 = g1;
+    }
+    return 0;
 }
 
 // The sparse form of the ChESS response: for every frame the list {(x, y, r) : r > 15} inside [7,w-7) x [7,h-7) that

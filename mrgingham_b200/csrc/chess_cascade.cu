@@ -70,7 +70,6 @@ struct CascadeParams
     int nstrips, nsegs, seg_rows;   // work decomposition: item = (frame, segment, strip)
     int cap;
     int stages;                     // depth of the shared-memory ring (TMA stages of 11 rows)
-    uint32_t one;                   // the constant 1, opaque to the compiler: x*one + y is an integer add on the FMA pipe
 };
 
 // head/tail count entries since the CTA started (a CTA never queues anywhere near 2^32 of them); the slot of
@@ -104,21 +103,11 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity)
 
 __device__ __forceinline__ uint32_t vabs4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
 
-// a + b as IMAD (a*one + b, one == 1 at run time): the ALU pipe, which carries VABSDIFF4/PRMT/LOP3 at one warp
-// instruction per two cycles, is what binds L1; the FMA pipe has the room
-__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t b)
+// u0 + u1 + u2 + u3 + 0x78787878 in packed bytes: two IADD3. (Moving these sums to the FMA pipe as IMADs by an
+// opaque 1, and register targets of 88 / 80 for 6 / 7 CTAs per SM, were measured and lost 0-4 %:
+// profiles/r02_k1_ab_knobs.txt.)
+__device__ __forceinline__ uint32_t packed_sum4(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t u3)
 {
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
-    return d;
-}
-// u0 + u1 + u2 + u3 + 0x78787878 in packed bytes. SUMS 0: two IADD3 (ALU pipe); 1: four IMAD (FMA pipe);
-// 2: one IADD3 + two IMAD
-template<int SUMS>
-__device__ __forceinline__ uint32_t packed_sum4(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t u3, uint32_t one)
-{
-    if (SUMS == 1) return add_fma(add_fma(u2, one, 0x78787878u), one, add_fma(u3, one, add_fma(u0, one, u1)));
-    if (SUMS == 2) return add_fma(u0 + u1 + 0x78787878u, one, add_fma(u2, one, u3));
     return u0 + u1 + u2 + u3 + 0x78787878u;
 }
 
@@ -290,11 +279,8 @@ __device__ __forceinline__ void l2_batch(const StripCtx& c, const L2Ctx& L, Q* q
     __syncwarp();
 }
 
-// MINB = CTAs per SM the register allocation aims at. The register file is per scheduler (16384 registers, i.e.
-// five warps of 96 registers): 3-warp CTAs reach 6 per SM (18 warps) at <= 96 registers and 7 per SM (21 warps,
-// one scheduler hosts six of them) only at <= 80.
-template<int NW, int SUMS, int MINB, bool CARRY>
-__global__ void __launch_bounds__(NW * 32, MINB)
+template<int NW, bool CARRY>
+__global__ void __launch_bounds__(NW * 32, 5)
 chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, CascadeParams tp,
                      cand_t* __restrict__ cand, uint32_t* __restrict__ counts)
 {
@@ -423,8 +409,8 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
             // lane can wrap, i.e. every chord <= 31 (4*31 + 0x78 < 256). That is what ha/hb guarantee: the
             // sum of all sixteen chord bytes of a word (IDP.4A against 1,1,1,1 -- FMA pipe, which idles
             // otherwise) is < 32. A word with ha >= 32 holds a chord sum >= 8 anyway and is flagged.
-            const uint32_t sa = packed_sum4<SUMS>(u0a, u1a, u2a, u3a, tp.one);
-            const uint32_t sb = packed_sum4<SUMS>(u0b, u1b, u2b, u3b, tp.one);
+            const uint32_t sa = packed_sum4(u0a, u1a, u2a, u3a);
+            const uint32_t sb = packed_sum4(u0b, u1b, u2b, u3b);
             const int ha = dp4a_us(u3a, 0x01010101, dp4a_us(u2a, 0x01010101, dp4a_us(u1a, 0x01010101, dp4a_us(u0a, 0x01010101, 0))));
             const int hb = dp4a_us(u3b, 0x01010101, dp4a_us(u2b, 0x01010101, dp4a_us(u1b, 0x01010101, dp4a_us(u0b, 0x01010101, 0))));
             if ((((sa | sb) & 0x80808080u) | ((uint32_t)(ha | hb) & ~31u)) != 0) flagbits |= 1u << j;
@@ -518,7 +504,7 @@ bool make_cascade_map(CUtensorMap* map, const FrameSet& fs, int row_bytes)
     return r == CUDA_SUCCESS;
 }
 
-template<int NW, int SUMS, int MINB, bool CARRY>
+template<int NW, bool CARRY>
 cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32_t* counts, cudaStream_t stream, bool* ok)
 {
     using G = Geo<NW>;
@@ -530,12 +516,12 @@ cudaError_t launch_nw(const FrameSet& fs, CascadeParams tp, cand_t* cand, uint32
     if (smem > 48 * 1024)
     {
         // per device, idempotent and cheap: set on every launch rather than tracking devices
-        cudaError_t e = cudaFuncSetAttribute(chess_cascade_kernel<NW, SUMS, MINB, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(chess_cascade_kernel<NW, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const long long items = (long long)fs.nframes * tp.nstrips * tp.nsegs;
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
-    chess_cascade_kernel<NW, SUMS, MINB, CARRY><<<(unsigned)items, NW * 32, smem, stream>>>(map, fs, tp, cand, counts);
+    chess_cascade_kernel<NW, CARRY><<<(unsigned)items, NW * 32, smem, stream>>>(map, fs, tp, cand, counts);
     return cudaGetLastError();
 }
 
@@ -588,23 +574,9 @@ cudaError_t launch_chess_sparse_cascade(const FrameSet& fs, cand_t* cand, uint32
     tp.seg_rows = seg_rows;
     tp.nsegs = (out_rows + seg_rows - 1) / seg_rows;
 
-    tp.one = 1;
-    const int sums = env_int("MRG_B200_K1_SUMS", 0, 0, 2);
-    const int minb = env_int("MRG_B200_K1_MINB", 5, 5, 7);
-    // Variants (the defaults are what bench.py measures): carry / no carry (4 / 3 stages), where the packed sums of L1
-    // run, and the register target (5: 96 registers, 6: 88, 7: 80 -- CTAs per SM follow from shared memory)
-    if (nw == 1) return nocarry ? launch_nw<1, 0, 5, false>(fs, tp, cand, counts, stream, launched) : launch_nw<1, 0, 5, true>(fs, tp, cand, counts, stream, launched);
-    if (nw == 2) return nocarry ? launch_nw<2, 0, 5, false>(fs, tp, cand, counts, stream, launched) : launch_nw<2, 0, 5, true>(fs, tp, cand, counts, stream, launched);
-#define K1_CASE(S, M) case (M) * 4 + (S): return nocarry ? launch_nw<3, S, M, false>(fs, tp, cand, counts, stream, launched) \
-                                                         : launch_nw<3, S, M, true>(fs, tp, cand, counts, stream, launched);
-    switch (minb * 4 + sums)
-    {
-    K1_CASE(1, 5) K1_CASE(2, 5)
-    K1_CASE(0, 6) K1_CASE(1, 6) K1_CASE(2, 6)
-    K1_CASE(0, 7) K1_CASE(1, 7) K1_CASE(2, 7)
-    default: return nocarry ? launch_nw<3, 0, 5, false>(fs, tp, cand, counts, stream, launched) : launch_nw<3, 0, 5, true>(fs, tp, cand, counts, stream, launched);
-    }
-#undef K1_CASE
+    if (nw == 1) return nocarry ? launch_nw<1, false>(fs, tp, cand, counts, stream, launched) : launch_nw<1, true>(fs, tp, cand, counts, stream, launched);
+    if (nw == 2) return nocarry ? launch_nw<2, false>(fs, tp, cand, counts, stream, launched) : launch_nw<2, true>(fs, tp, cand, counts, stream, launched);
+    return nocarry ? launch_nw<3, false>(fs, tp, cand, counts, stream, launched) : launch_nw<3, true>(fs, tp, cand, counts, stream, launched);
 }
 
 }

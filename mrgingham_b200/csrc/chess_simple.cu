@@ -339,4 +339,34 @@ cudaError_t launch_pyramid(const FrameSet& src, int level, uint8_t* dst, int dst
     return cudaGetLastError();
 }
 
+
+// ---- gather of scattered, equally-sized device images into one batch (mrg_b200_find_corners_mixed_batch) ----
+__global__ void __launch_bounds__(256)
+gather_frames_kernel(const GatherSrc* __restrict__ srcs, int rows, int cols, uint8_t* __restrict__ dst, size_t dst_pitch, size_t dst_frame_stride)
+{
+    const int f = blockIdx.z, y = blockIdx.y;
+    const GatherSrc s = srcs[f];
+    const uint8_t* in = s.data + (size_t)y * s.pitch;
+    uint8_t* out = dst + (size_t)f * dst_frame_stride + (size_t)y * dst_pitch;
+    const int x16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x16 >= cols) return;
+    if ((((uintptr_t)in | s.pitch) & 15) == 0 && x16 + 16 <= cols)
+        *reinterpret_cast<uint4*>(out + x16) = *reinterpret_cast<const uint4*>(in + x16);      // dst rows are 16-byte aligned
+    else
+        for (int i = 0; i < 16 && x16 + i < cols; i++) out[x16 + i] = in[x16 + i];
+}
+
+cudaError_t launch_gather_frames(const GatherSrc* srcs, int n, int rows, int cols, uint8_t* dst, size_t dst_pitch,
+                                 size_t dst_frame_stride, cudaStream_t stream)
+{
+    if (n <= 0 || rows <= 0 || cols <= 0) return cudaSuccess;
+    const int per_row = (cols + 15) / 16;
+    for (int f0 = 0; f0 < n; f0 += 65535)
+    {
+        const int m = std::min(65535, n - f0);
+        gather_frames_kernel<<<dim3((per_row + 255) / 256, rows, m), 256, 0, stream>>>(srcs + f0, rows, cols, dst + (size_t)f0 * dst_frame_stride,
+                                                                                        dst_pitch, dst_frame_stride);
+    }
+    return cudaGetLastError();
+}
 }

@@ -66,6 +66,11 @@ size_t clahe_scratch_bytes(int nframes);
 cudaError_t launch_normalize_clahe(const FrameSet& fs, bool normalize, double clip_limit, uint8_t* dst, int dst_pitch,
                                    size_t dst_frame_stride, void* scratch, cudaStream_t stream);
 
+// device-to-device gather of n equally-sized images lying anywhere into one contiguous, pitched batch
+struct GatherSrc { const uint8_t* data; size_t pitch; };
+cudaError_t launch_gather_frames(const GatherSrc* srcs, int n, int rows, int cols, uint8_t* dst, size_t dst_pitch,
+                                 size_t dst_frame_stride, cudaStream_t stream);
+
 // K1 (simple variant): ChESS response, one thread per pixel, emits candidates
 cudaError_t launch_chess_sparse_simple(const FrameSet& fs, cand_t* cand, uint32_t* counts,
                                        int cand_capacity, cudaStream_t stream);
