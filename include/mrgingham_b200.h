@@ -293,6 +293,17 @@ int mrg_b200_preprocess_batch(mrg_b200_detector* det,
                               uint8_t* out, int out_on_device,
                               void* stream);
 
+/* The same for 16-bit frames, as the reference CLI treats them (mrgingham-from-image.cc:83-93): with clahe,
+   cv::normalize(0, 65535, NORM_MINMAX) and CLAHE(clipLimit 8) on the 16-bit data; then convertTo(CV_8U, 255./65535.);
+   then the blur (blur_radius 0 = none). images: uint16 [nframes][rows][row_pitch / 2]; row_pitch and frame_stride
+   in BYTES. out: uint8 [nframes][rows][cols], dense: the image the detector is then given. Returns 0 or <0. */
+int mrg_b200_preprocess16_batch(mrg_b200_detector* det,
+                                const uint16_t* images, int images_on_device,
+                                int nframes, int rows, int cols,
+                                size_t row_pitch, size_t frame_stride,
+                                int clahe, int blur_radius,
+                                uint8_t* out, int out_on_device, void* stream);
+
 /* Pyramid level image (what the reference gets from cv::resize, find_chessboard_corners.cc:449-450).
    out: HOST uint8 [orows][ocols] dense; returns 0 and the size, or <0. */
 int mrg_b200_pyramid_level(mrg_b200_detector* det,

@@ -23,7 +23,7 @@ EXPORTS = (
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
     "mrg_b200_find_corners_mixed_batch",
     "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch", "mrg_b200_box_blur_batch",
-    "mrg_b200_preprocess_batch",
+    "mrg_b200_preprocess_batch", "mrg_b200_preprocess16_batch",
     "find_chessboard_from_image_array_C", "mrg_b200_find_grid_from_points", "mrg_b200_voronoi_neighbours",
     "mrg_b200_find_chessboard_from_image_array", "mrg_b200_find_circle_grid_from_image_array", "mrg_b200_find_boards_batch",
     "mrg_b200_chess_response_batch", "mrg_b200_chess_candidates_batch", "mrg_b200_pyramid_level",
@@ -106,6 +106,9 @@ def lib():
     L.mrg_b200_find_blobs_batch.restype = ctypes.c_int
     L.mrg_b200_find_blobs_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_size_t, ctypes.c_size_t, _i32p, _i32p, ctypes.c_void_p]
+    L.mrg_b200_preprocess16_batch.restype = ctypes.c_int
+    L.mrg_b200_preprocess16_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.mrg_b200_box_blur_batch.restype = ctypes.c_int
     L.mrg_b200_box_blur_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
@@ -459,6 +462,36 @@ class Detector:
                                              optr, on_dev, ctypes.c_void_p(stream) if stream else None)
         if rc != 0:
             raise RuntimeError("mrg_b200_preprocess_batch() failed")
+        return out
+
+    def preprocess16(self, images, clahe=False, blur_radius=1, out=None, stream=None):
+        """The reference CLI's chain for 16-bit images (mrgingham-from-image.cc:83-111): with clahe, normalize to
+        [0,65535] + CLAHE(clipLimit 8) on the 16-bit data; convertTo 8 bits (x 255/65535); blur of the given radius.
+        images: uint16 [n, rows, cols] numpy array or CUDA torch tensor (int16 storage is read as uint16).
+        Host images -> numpy uint8 result; CUDA tensor -> a new CUDA uint8 tensor (or `out`)."""
+        if isinstance(images, np.ndarray):
+            a = images if images.ndim == 3 else images[None]
+            assert a.dtype == np.uint16 and (a.shape[2] == 1 or a.strides[2] == 2)
+            n, rows, cols = a.shape
+            ptr, on_dev, pitch = a.ctypes.data, 0, a.strides[1]
+            fstride = a.strides[0] if n > 1 else pitch * rows
+            out = np.empty((n, rows, cols), dtype=np.uint8)
+            optr = out.ctypes.data
+        else:
+            import torch
+            t = images if images.dim() == 3 else images[None]
+            assert t.is_cuda and t.element_size() == 2 and t.stride(2) == 1
+            n, rows, cols = t.shape
+            ptr, on_dev, pitch = t.data_ptr(), 1, t.stride(1) * 2
+            fstride = t.stride(0) * 2 if n > 1 else pitch * rows
+            if out is None:
+                out = torch.empty((n, rows, cols), dtype=torch.uint8, device=t.device)
+            assert out.is_contiguous() and tuple(out.shape) == (n, rows, cols)
+            optr = out.data_ptr()
+        rc = lib().mrg_b200_preprocess16_batch(self._h, ptr, on_dev, n, rows, cols, pitch, fstride, int(bool(clahe)), int(blur_radius),
+                                               optr, on_dev, ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise RuntimeError("mrg_b200_preprocess16_batch() failed")
         return out
 
     def find_boards(self, images, gridn=10, level=-1, blobs=False, refine=True, stream=None):

@@ -796,6 +796,63 @@ static int preprocess_batch(mrg_b200_detector* det, const uint8_t* images, int i
     return 0;
 }
 
+// The reference CLI's handling of 16-bit images (mrgingham-from-image.cc:83-93), then its blur: 16 bits in, the 8-bit
+// image the detector would be given out.
+API int mrg_b200_preprocess16_batch(mrg_b200_detector* det, const uint16_t* images, int images_on_device,
+                                    int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
+                                    int clahe, int blur_radius, uint8_t* out, int out_on_device, void* stream_)
+{
+    if (!det) return -1;
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (nframes < 0 || rows <= 0 || cols <= 0 || row_pitch < 2 * (size_t)cols || (row_pitch & 1) || (frame_stride & 1) || ((uintptr_t)images & 1))
+    { MSG("Bad batch geometry (16-bit frames: pitch and stride in bytes, even, pitch >= 2*cols)."); return -1; }
+    if (blur_radius < 0 || blur_radius > 4) { MSG("blur_radius must be in [0,4]; got %d.", blur_radius); return -1; }
+    if (det->pending.active) { MSG("A batch is in flight on this detector: collect it first."); return -1; }
+    DEVICE_GUARD(det);
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
+    const size_t fe = (size_t)rows * cols;
+    // the 65536-bin histograms and tables of the 16-bit CLAHE take 24 MB per frame: modest chunks
+    const int chunk = std::max(1, std::min(clahe ? 32 : 65535, out_on_device && images_on_device ? std::max(nframes, 1) : std::max(1, det->cfg.max_frames)));
+    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    {
+        const int n = std::min(chunk, nframes - f0);
+        mrg_b200_detector::Slot& S = det->slot[0];
+        const uint16_t* src = (const uint16_t*)((const uint8_t*)images + (size_t)f0 * frame_stride);
+        size_t src_stride = frame_stride / 2; int src_pitch = (int)(row_pitch / 2);
+        if (!images_on_device)
+        {
+            if (S.stage.ensure(fe * 2 * n)) return -1;
+            for (int i = 0; i < n; i++)
+                CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)S.stage.p + (size_t)i * fe * 2, (size_t)cols * 2, (const uint8_t*)src + (size_t)i * frame_stride, row_pitch,
+                                           (size_t)cols * 2, rows, cudaMemcpyHostToDevice, stream));
+            src = (const uint16_t*)S.stage.p; src_stride = fe; src_pitch = cols;
+        }
+        uint8_t* d = out + (size_t)f0 * fe;
+        if (!out_on_device)
+        {
+            if (S.level_img.ensure(fe * n)) return -1;
+            d = (uint8_t*)S.level_img.p;
+        }
+        uint8_t* e = d; int epitch = cols; size_t eframe = fe;
+        if (blur_radius > 0)
+        {
+            epitch = round_up(cols, 16); eframe = (size_t)epitch * rows;
+            if (S.equalized.ensure(eframe * n)) return -1;
+            e = (uint8_t*)S.equalized.p;
+        }
+        if (clahe && S.pre_scratch.ensure(preproc16_scratch_bytes(n))) return -1;
+        CUDA_TRY(launch_preprocess16(src, src_stride, src_pitch, cols, rows, n, clahe != 0, e, epitch, eframe, S.pre_scratch.p, stream));
+        if (blur_radius > 0)
+        {
+            FrameSet fs; fs.base = e; fs.pitch = epitch; fs.frame_stride = eframe; fs.w = cols; fs.h = rows; fs.nframes = n;
+            CUDA_TRY(launch_box_blur(fs, blur_radius, d, cols, fe, stream));
+        }
+        if (!out_on_device) CUDA_TRY(cudaMemcpyAsync(out + (size_t)f0 * fe, d, fe * n, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
 API int mrg_b200_box_blur_batch(mrg_b200_detector* det, const uint8_t* images, int images_on_device,
                                 int nframes, int rows, int cols, size_t row_pitch, size_t frame_stride,
                                 int blur_radius, uint8_t* out, int out_on_device, void* stream_)

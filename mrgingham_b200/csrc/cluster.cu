@@ -26,6 +26,8 @@ namespace mrgb200
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kRoot  = 0x1FFFFFFFu;
 constexpr int      kClusterThreads = 256;
+constexpr int      kRefineMaxPoints = 1024;   // refine: points per frame the parallel path groups (more: one thread, as before)
+constexpr int      kRefineStack = 192;         // refine: stack of one point's region flood
 
 struct Component
 {
@@ -111,6 +113,65 @@ __device__ void grow_component(Component& c, cand_t* cand, const uint32_t* table
             }
             if (!found) break;
         }
+    }
+}
+
+// grow_component() as ONE flat loop: every iteration is either a "pop" (membership test of `cur`) or one step of
+// the search for the next pixel (one direction of one node). The refinement kernel runs one of these per lane;
+// lanes whose walks are at different depths still execute the same loop body, so a warp is not serialised the
+// way it is by the nested, data-dependent loops above. Same visits in the same order.
+__device__ void grow_component_flat(Component& c, cand_t* cand, const uint32_t* table, int bits, uint32_t* dfs,
+                                    const int* roots, int nroots, int w, int h)
+{
+    c.swx = c.swy = c.sw = 0; c.n = 0; c.peak = 0; c.peak_x = c.peak_y = 0; c.poisoned = false;
+    int ir = 0;
+    uint32_t cur = kRoot, parent = kRoot;
+    bool pop = false;
+    for (;;)
+    {
+        if (cur == kRoot && !pop)
+        {
+            if (ir == nroots) break;
+            cur = (uint32_t)roots[ir++]; parent = kRoot; pop = true;
+        }
+        if (pop)
+        {
+            const cand_t cc = cand[cur];
+            const int r = cand_r(cc);
+            const bool member = r != 0 && r > (c.peak >> 4);   // alive => r > 15 already
+            if (r != 0) cand[cur] = cc & ~0xFFFFull;           // member or not, it is zeroed
+            if (member)
+            {
+                const int x = cand_x(cc), y = cand_y(cc);
+                if (r > c.peak) { c.peak = r; c.peak_x = x; c.peak_y = y; }
+                c.swx += (unsigned long long)(r * x);
+                c.swy += (unsigned long long)(r * y);
+                c.sw  += (unsigned long long)r;
+                c.n++;
+                if (x + 1 >= w - kMargin || x - 1 < kMargin || y + 1 >= h - kMargin || y - 1 < kMargin)
+                    c.poisoned = true;
+                dfs[cur] = parent << 3;
+            }
+            else
+                cur = parent;
+            pop = false;
+            continue;
+        }
+        // one step of the advance: the next direction of `cur`, or back to its parent
+        const uint32_t st = dfs[cur];
+        const int d = (int)(st & 7);
+        if (d == 4) { cur = st >> 3; continue; }
+        dfs[cur] = st + 1;
+        const cand_t pc = cand[cur];
+        int nx = cand_x(pc), ny = cand_y(pc);
+        if      (d == 0) ny -= 1;
+        else if (d == 1) ny += 1;
+        else if (d == 2) nx -= 1;
+        else             nx += 1;
+        if (nx < kMargin || nx >= w - kMargin || ny < kMargin || ny >= h - kMargin) continue;
+        const int q = table_lookup(cand, table, bits, ((uint32_t)ny << 16) | (uint32_t)nx);
+        if (q < 0 || cand_r(cand[q]) == 0) continue;           // never pushed, or a stale stack entry
+        parent = cur; cur = (uint32_t)q; pop = true;
     }
 }
 
@@ -510,37 +571,171 @@ cluster_refine_kernel(FrameSet fs, ClusterParams p, cand_t* cand_all, const uint
     signed char* lvl = levels    + (size_t)f * npoints;
     const double scale = (double)(1 << p.level), inv_scale = 1.0 / scale;
 
-    if (tid == 0)
+    // One point's visit of the shared candidate set: its 3x3 seeds, the component grown from them, a record if the
+    // component passes. Points whose seeds lie in different 4-connected regions of the candidate set cannot see
+    // each other's visits (nothing a component does leaves its region), so they may run concurrently.
+    auto visit_point = [&](int i)
     {
-        int nrec = 0;
-        for (int i = 0; i < npoints; i++)
+        const int x = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i],     inv_scale), 0.5));
+        const int y = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i + 1], inv_scale), 0.5));
+        // 3x3 seeds, pushed dx-outer / dy-inner, hence visited in the reverse order
+        int roots[9], nroots = 0;
+        for (int dx = 1; dx >= -1; dx--)
+            for (int dy = 1; dy >= -1; dy--)
+            {
+                const int u = x + dx, v = y + dy;
+                if (u < kMargin || u >= w - kMargin || v < kMargin || v >= h - kMargin) continue; // response is 0 there
+                const int q = table_lookup(fw.cand, fw.table, fw.bits, ((uint32_t)v << 16) | (uint32_t)u);
+                if (q >= 0 && cand_r(fw.cand[q]) != 0) roots[nroots++] = q;
+            }
+        Component c;
+        grow_component_flat(c, fw.cand, fw.table, fw.bits, fw.dfs, roots, nroots, w, h);
+        if (c.poisoned || c.n < kComponentMinN || c.peak <= kPeakMin) return;
+        const int k = atomicAdd(&s_nrec, 1);
+        if (k < record_cap)
+        {
+            ComponentRecord r;
+            r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
+            r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x; r.tag = i;
+            rec[k] = r;
+        }
+    };
+
+    // Which points share a region? Every point floods the regions of its seeds over the STATIC candidate graph,
+    // lowering a per-candidate mark (kept in the dfs array, which the visits only use afterwards) to its own index
+    // and expanding only where it lowered one: when all floods are done every candidate of a region carries the
+    // smallest index of the points seeded in it. Points are then united through the marks of their seeds; each
+    // group is visited, in index order, by one thread.
+    __shared__ int s_fallback;
+    __shared__ uint16_t s_parent[kRefineMaxPoints];
+    if (tid == 0) { s_nrec = 0; s_fallback = npoints > kRefineMaxPoints || fw.n > 65535; }
+    for (int i = tid; i < fw.n; i += kClusterThreads) fw.dfs[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    if (!s_fallback)
+    {
+        for (int i = tid; i < npoints; i += kClusterThreads)
+        {
+            s_parent[i] = (uint16_t)i;
+            if (lvl[i] != p.level + 1) continue;
+            const int x = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i],     inv_scale), 0.5));
+            const int y = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i + 1], inv_scale), 0.5));
+            // a candidate is claimed (its mark lowered) when it is PUSHED, so it is on the stack at most once
+            uint16_t stk[kRefineStack];
+            int sp = 0;
+            bool overflow = false;
+            auto claim = [&](int q)
+            {
+                if (atomicMin(&fw.dfs[q], (uint32_t)i) <= (uint32_t)i) return;             // a point with a smaller index owns it (or this one does already)
+                if (sp == kRefineStack) { overflow = true; return; }
+                stk[sp++] = (uint16_t)q;
+            };
+            for (int dx = -1; dx <= 1; dx++)
+                for (int dy = -1; dy <= 1; dy++)
+                {
+                    const int u = x + dx, v = y + dy;
+                    if (u < kMargin || u >= w - kMargin || v < kMargin || v >= h - kMargin) continue;
+                    const int q = table_lookup(fw.cand, fw.table, fw.bits, ((uint32_t)v << 16) | (uint32_t)u);
+                    if (q >= 0) claim(q);
+                }
+            while (sp > 0 && !overflow)
+            {
+                const cand_t cc = fw.cand[stk[--sp]];
+                const int cx = cand_x(cc), cy = cand_y(cc);
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                {
+                    const int nx = cx + (d == 2 ? -1 : d == 3 ? 1 : 0), ny = cy + (d == 0 ? -1 : d == 1 ? 1 : 0);
+                    if (nx < kMargin || nx >= w - kMargin || ny < kMargin || ny >= h - kMargin) continue;
+                    const int q = table_lookup(fw.cand, fw.table, fw.bits, ((uint32_t)ny << 16) | (uint32_t)nx);
+                    if (q >= 0) claim(q);
+                }
+            }
+            if (overflow) s_fallback = 1;
+        }
+    }
+    __syncthreads();
+    if (s_fallback)
+    {
+        // (more points than the group table holds, or a region too large for a flood's stack: one thread, index order)
+        if (tid == 0)
+            for (int i = 0; i < npoints; i++)
+                if (lvl[i] == p.level + 1) visit_point(i);
+    }
+    else
+    {
+        // a point joins the owner of its seeds' region (the mark; <= its own index: it flooded them too). Points whose
+        // seeds carry different marks bridge regions: those few unions are left to one thread.
+        __shared__ int s_nbridge;
+        __shared__ uint16_t s_bridge[kRefineMaxPoints];
+        if (tid == 0) s_nbridge = 0;
+        __syncthreads();
+        for (int i = tid; i < npoints; i += kClusterThreads)
         {
             if (lvl[i] != p.level + 1) continue;
             const int x = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i],     inv_scale), 0.5));
             const int y = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i + 1], inv_scale), 0.5));
-            // 3x3 seeds, pushed dx-outer / dy-inner, hence visited in the reverse order
-            int roots[9], nroots = 0;
-            for (int dx = 1; dx >= -1; dx--)
-                for (int dy = 1; dy >= -1; dy--)
+            uint32_t lo = (uint32_t)i, hi = 0; bool any = false;
+            for (int dx = -1; dx <= 1; dx++)
+                for (int dy = -1; dy <= 1; dy++)
                 {
                     const int u = x + dx, v = y + dy;
-                    if (u < kMargin || u >= w - kMargin || v < kMargin || v >= h - kMargin) continue; // response is 0 there
+                    if (u < kMargin || u >= w - kMargin || v < kMargin || v >= h - kMargin) continue;
                     const int q = table_lookup(fw.cand, fw.table, fw.bits, ((uint32_t)v << 16) | (uint32_t)u);
-                    if (q >= 0 && cand_r(fw.cand[q]) != 0) roots[nroots++] = q;
+                    if (q < 0) continue;
+                    const uint32_t m = fw.dfs[q];
+                    lo = min(lo, m); hi = max(hi, m); any = true;
                 }
-            Component c;
-            grow_component(c, fw.cand, fw.table, fw.bits, fw.dfs, roots, nroots, w, h);
-            if (c.poisoned || c.n < kComponentMinN || c.peak <= kPeakMin) continue;
-            if (nrec < record_cap)
-            {
-                ComponentRecord r;
-                r.swx = c.swx; r.swy = c.swy; r.sw = c.sw;
-                r.peak_xy = ((uint32_t)c.peak_y << 16) | (uint32_t)c.peak_x; r.tag = i;
-                rec[nrec] = r;
-            }
-            nrec++;
+            s_parent[i] = (uint16_t)lo;
+            if (any && hi != lo) s_bridge[atomicAdd(&s_nbridge, 1)] = (uint16_t)i;
         }
-        s_nrec = nrec;
+        __syncthreads();
+        if (tid == 0 && s_nbridge > 0)
+        {
+            auto find = [&](int a) { while (s_parent[a] != a) { s_parent[a] = s_parent[s_parent[a]]; a = s_parent[a]; } return a; };
+            for (int b = 0; b < s_nbridge; b++)
+            {
+                const int i = s_bridge[b];
+                const int x = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i],     inv_scale), 0.5));
+                const int y = __double2int_rz(__dadd_rn(rescale_coord(xy[2*i + 1], inv_scale), 0.5));
+                for (int dx = -1; dx <= 1; dx++)
+                    for (int dy = -1; dy <= 1; dy++)
+                    {
+                        const int u = x + dx, v = y + dy;
+                        if (u < kMargin || u >= w - kMargin || v < kMargin || v >= h - kMargin) continue;
+                        const int q = table_lookup(fw.cand, fw.table, fw.bits, ((uint32_t)v << 16) | (uint32_t)u);
+                        if (q < 0) continue;
+                        const int ra = find(i), rb = find((int)fw.dfs[q]);
+                        if (ra != rb) s_parent[max(ra, rb)] = (uint16_t)min(ra, rb);
+                    }
+            }
+        }
+        __syncthreads();
+        // every point's group = the root of its chain (chains only ever point to smaller indices)
+        int my_root[(kRefineMaxPoints + kClusterThreads - 1) / kClusterThreads];
+#pragma unroll
+        for (int k = 0; k < (kRefineMaxPoints + kClusterThreads - 1) / kClusterThreads; k++)
+        {
+            const int i = tid + k * kClusterThreads;
+            int a = i < npoints ? i : 0;
+            while (s_parent[a] != a) a = s_parent[a];
+            my_root[k] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < (kRefineMaxPoints + kClusterThreads - 1) / kClusterThreads; k++)
+        {
+            const int i = tid + k * kClusterThreads;
+            if (i < npoints) s_parent[i] = (uint16_t)my_root[k];
+        }
+        __syncthreads();
+        // (points dealt to the warps round-robin: fewer diverging walks per warp)
+        for (int i0 = 0; i0 < npoints; i0 += kClusterThreads)
+        {
+            const int i = i0 + (tid & 31) * (kClusterThreads / 32) + (tid >> 5);
+            if (i >= npoints || s_parent[i] != i) continue;    // the group's first point leads it
+            for (int j = i; j < npoints; j++)
+                if (s_parent[j] == i && lvl[j] == p.level + 1) visit_point(j);
+        }
     }
     __syncthreads();
     const int nrec = s_nrec;

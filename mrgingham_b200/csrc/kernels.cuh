@@ -71,6 +71,12 @@ struct GatherSrc { const uint8_t* data; size_t pitch; };
 cudaError_t launch_gather_frames(const GatherSrc* srcs, int n, int rows, int cols, uint8_t* dst, size_t dst_pitch,
                                  size_t dst_frame_stride, cudaStream_t stream);
 
+// Kpre3: 16-bit frames -> 8-bit frames as the reference CLI does it (mrgingham-from-image.cc:83-93):
+// [normalize(0,65535) + CLAHE(8) on 16 bits if clahe], then convertTo(CV_8U, 255/65535). preproc16.cu
+size_t preproc16_scratch_bytes(int nframes);
+cudaError_t launch_preprocess16(const uint16_t* src, size_t src_frame_stride_elems, int src_pitch_elems, int w, int h, int nframes,
+                                bool clahe, uint8_t* dst, int dst_pitch, size_t dst_frame_stride, void* scratch, cudaStream_t stream);
+
 // K1 (simple variant): ChESS response, one thread per pixel, emits candidates
 cudaError_t launch_chess_sparse_simple(const FrameSet& fs, cand_t* cand, uint32_t* counts,
                                        int cand_capacity, cudaStream_t stream);

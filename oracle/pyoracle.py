@@ -206,6 +206,51 @@ def normalize_clahe(image):
     return out
 
 
+_u16p = ctypes.POINTER(ctypes.c_uint16)
+
+
+def _check_image16(image):
+    image = np.asarray(image)
+    assert image.ndim == 2 and image.dtype == np.uint16 and (image.shape[1] == 1 or image.strides[1] == 2) and image.strides[0] % 2 == 0
+    return image
+
+
+def convert16to8(image):
+    """cv::Mat::convertTo(CV_8U, 255./65535.) of a 16-bit image (mrgingham-from-image.cc:93)"""
+    image = _check_image16(image)
+    h, w = image.shape
+    out = np.empty((h, w), dtype=np.uint8)
+    oracle_lib().preproc_oracle_convert16to8(_ptr(image, _u16p), w, h, image.strides[0] // 2, _ptr(out, _u8p))
+    return out
+
+
+def normalize16(image):
+    """cv::normalize(image, image, 0, 65535, NORM_MINMAX) for 16-bit images (mrgingham-from-image.cc:90)"""
+    image = _check_image16(image)
+    h, w = image.shape
+    out = np.empty((h, w), dtype=np.uint16)
+    oracle_lib().preproc_oracle_normalize16(_ptr(image, _u16p), w, h, image.strides[0] // 2, _ptr(out, _u16p))
+    return out
+
+
+def clahe16(image, clip_limit=8.0):
+    """cv::createCLAHE(clip_limit).apply(image) for 16-bit images, 8x8 tiles (mrgingham-from-image.cc:91)"""
+    image = _check_image16(image)
+    h, w = image.shape
+    out = np.empty((h, w), dtype=np.uint16)
+    oracle_lib().preproc_oracle_clahe16(_ptr(image, _u16p), w, h, image.strides[0] // 2, ctypes.c_double(clip_limit), _ptr(out, _u16p))
+    return out
+
+
+def chain16(image, clahe=False):
+    """the CLI's handling of a 16-bit image (mrgingham-from-image.cc:83-93): [normalize + CLAHE(8)], then 8 bits"""
+    image = _check_image16(image)
+    h, w = image.shape
+    out = np.empty((h, w), dtype=np.uint8)
+    oracle_lib().preproc_oracle_chain16(_ptr(image, _u16p), w, h, image.strides[0] // 2, int(bool(clahe)), _ptr(out, _u8p))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference itself (oracle/_ref)
 # ---------------------------------------------------------------------------------------------
