@@ -153,6 +153,7 @@ struct mrg_b200_detector
     // board finder: the frames of the chunk being worked on, kept on the device across the level loop
     std::mutex   boards_mtx;
     DeviceBuffer boards_frames, boards_gather;
+    mrg_b200_detector* boards_helper = nullptr;   // second detector of the board finder (find_boards): chunks alternate between the two
     DeviceBuffer mixed_stage, mixed_srcs;     // mrg_b200_find_corners_mixed_batch(): one size group, contiguous; its sources
 
     struct Pending
@@ -507,6 +508,7 @@ API int mrg_b200_detector_create(mrg_b200_detector** out, const mrg_b200_detecto
 API void mrg_b200_detector_destroy(mrg_b200_detector* det)
 {
     if (!det) return;
+    if (det->boards_helper) { mrg_b200_detector_destroy(det->boards_helper); det->boards_helper = nullptr; }
     DeviceGuard dg(det->device);
     for (int k = 0; k < mrg_b200_detector::kBlobDepth; k++)
     {
@@ -1381,44 +1383,73 @@ int find_boards(mrg_b200_detector* det, const uint8_t* images, int on_device, in
     if (doblobs && level != 0) { MSG("The blob detector works at image_pyramid_level 0 only."); return -1; }
     std::lock_guard<std::mutex> g(det->boards_mtx);
     const int npts = gridn * gridn;
+    // Between the GPU passes of a chunk (corners at one level, refinement at one level) the host looks for grids,
+    // and the GPU has nothing to do. So when the batch is longer than one chunk (max_frames), two detectors -- this
+    // one and a helper it owns, with its own streams and scratch -- take the chunks in turns on two host threads:
+    // one's grid search runs beside the other's kernels (1024 4K frames, 14x14: 15.6 k boards/s against 11.9 k for
+    // one chunk at a time; cutting a single chunk into smaller ones for this loses more than it wins).
     const int chunk = std::max(1, det->cfg.max_frames);
-    for (int f0 = 0; f0 < nframes; f0 += chunk)
+    const int nchunks = (nframes + chunk - 1) / chunk;
+    if (nchunks >= 2 && !det->boards_helper)
     {
-        const int n = std::min(chunk, nframes - f0);
-        const uint8_t* d = images + (size_t)f0 * fstride;
-        size_t dpitch = pitch, dfstride = fstride;
-        if (!on_device)
-        {
-            // the frames go to the device once and stay there for every level and refinement pass
-            DEVICE_GUARD(det);
-            cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : det->own_stream;
-            dpitch = pitch == (size_t)cols ? (size_t)cols : (size_t)round_up(cols, 16);
-            dfstride = dpitch * rows;
-            if (det->boards_frames.ensure(dfstride * n)) return -1;
-            if (det->stage_via_pinned)
-            {
-                if (det->h_stage.ensure(dfstride * n)) return -1;
-                if (!det->h_stage_free) CUDA_TRY(cudaEventCreateWithFlags(&det->h_stage_free, cudaEventDisableTiming));
-                else                    CUDA_TRY(cudaEventSynchronize(det->h_stage_free));
-                uint8_t* hp = (uint8_t*)det->h_stage.p;
-                for (int i = 0; i < n; i++)
-                    for (int y = 0; y < rows; y++) memcpy(hp + i * dfstride + (size_t)y * dpitch, d + i * fstride + (size_t)y * pitch, cols);
-                CUDA_TRY(cudaMemcpyAsync(det->boards_frames.p, hp, dfstride * n, cudaMemcpyHostToDevice, stream));
-                CUDA_TRY(cudaEventRecord(det->h_stage_free, stream));
-            }
-            else if (dpitch == pitch && fstride == dfstride)
-                CUDA_TRY(cudaMemcpyAsync(det->boards_frames.p, d, dfstride * n, cudaMemcpyHostToDevice, stream));
-            else
-                for (int i = 0; i < n; i++)
-                    CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)det->boards_frames.p + i * dfstride, dpitch, d + i * fstride, pitch, cols, rows,
-                                               cudaMemcpyHostToDevice, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            d = (const uint8_t*)det->boards_frames.p;
-        }
-        if (find_boards_chunk(det, d, n, rows, cols, dpitch, dfstride, gridn, level, doblobs, refine, strict_level0,
-                              xy_out + (size_t)2 * npts * f0, levels_out ? levels_out + (size_t)npts * f0 : nullptr, found_out + f0, stream_)) return -1;
+        mrg_b200_detector_config hc = det->cfg;
+        hc.device = det->device;
+        if (mrg_b200_detector_create(&det->boards_helper, &hc)) det->boards_helper = nullptr;       // (then: one detector, as before)
     }
-    return 0;
+    if (stream_ && nchunks >= 2 && det->boards_helper)
+    {
+        DEVICE_GUARD(det);
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream_));       // device frames may come from work queued there; the helper runs elsewhere
+    }
+    auto run_chunks = [&](mrg_b200_detector* dd, int first, int step, void* dstream) -> int
+    {
+        for (int c = first; c < nchunks; c += step)
+        {
+            const int f0 = c * chunk, n = std::min(chunk, nframes - f0);
+            const uint8_t* d = images + (size_t)f0 * fstride;
+            size_t dpitch = pitch, dfstride = fstride;
+            if (!on_device)
+            {
+                // the frames go to the device once and stay there for every level and refinement pass
+                DEVICE_GUARD(dd);
+                cudaStream_t stream = dstream ? (cudaStream_t)dstream : dd->own_stream;
+                dpitch = pitch == (size_t)cols ? (size_t)cols : (size_t)round_up(cols, 16);
+                dfstride = dpitch * rows;
+                if (dd->boards_frames.ensure(dfstride * n)) return -1;
+                if (dd->stage_via_pinned)
+                {
+                    if (dd->h_stage.ensure(dfstride * n)) return -1;
+                    if (!dd->h_stage_free) CUDA_TRY(cudaEventCreateWithFlags(&dd->h_stage_free, cudaEventDisableTiming));
+                    else                   CUDA_TRY(cudaEventSynchronize(dd->h_stage_free));
+                    uint8_t* hp = (uint8_t*)dd->h_stage.p;
+                    for (int i = 0; i < n; i++)
+                        for (int y = 0; y < rows; y++) memcpy(hp + i * dfstride + (size_t)y * dpitch, d + i * fstride + (size_t)y * pitch, cols);
+                    CUDA_TRY(cudaMemcpyAsync(dd->boards_frames.p, hp, dfstride * n, cudaMemcpyHostToDevice, stream));
+                    CUDA_TRY(cudaEventRecord(dd->h_stage_free, stream));
+                }
+                else if (dpitch == pitch && fstride == dfstride)
+                    CUDA_TRY(cudaMemcpyAsync(dd->boards_frames.p, d, dfstride * n, cudaMemcpyHostToDevice, stream));
+                else
+                    for (int i = 0; i < n; i++)
+                        CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)dd->boards_frames.p + i * dfstride, dpitch, d + i * fstride, pitch, cols, rows,
+                                                   cudaMemcpyHostToDevice, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                d = (const uint8_t*)dd->boards_frames.p;
+            }
+            if (find_boards_chunk(dd, d, n, rows, cols, dpitch, dfstride, gridn, level, doblobs, refine, strict_level0,
+                                  xy_out + (size_t)2 * npts * f0, levels_out ? levels_out + (size_t)npts * f0 : nullptr, found_out + f0, dstream)) return -1;
+        }
+        return 0;
+    };
+    if (nchunks >= 2 && det->boards_helper)
+    {
+        int rc_b = 0;
+        std::thread tb([&] { rc_b = run_chunks(det->boards_helper, 1, 2, nullptr); });
+        const int rc_a = run_chunks(det, 0, 2, nullptr);
+        tb.join();
+        return rc_a || rc_b ? -1 : 0;
+    }
+    return run_chunks(det, 0, 1, stream_);
 }
 }   // namespace
 

@@ -804,7 +804,7 @@ cudaError_t launch_cluster_refine(const FrameSet& fs, const ClusterParams& p_in,
     ClusterParams p = p_in;
     p.smem_cands = checked_smem_cands(p_in);
     const size_t smem = cluster_smem_bytes(p.smem_cands);
-    if (smem > 48 * 1024)
+    if (smem + 8 * 1024 > 48 * 1024)       // (the kernel's static arrays count against the 48 KB default too)
     {
         // per device, idempotent and cheap: set on every launch rather than tracking devices
         cudaError_t e = cudaFuncSetAttribute(cluster_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
