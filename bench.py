@@ -630,7 +630,7 @@ def content_table(a, content, po, torch, dev):
     for key, name, cfg in CONTENT_KINDS:
         fr = content[key]
         d = api.Detector(max_frames=32, max_rows=H, max_cols=W, max_points=4096, candidate_capacity=1 << 21, device=dev.index,
-                         **(cfg or {}))
+                         kernel_variant=a.kernel_variant, **(cfg or {}))
         t = torch.from_numpy(np.stack([fr[i % nd] for i in range(nd * reps)])).to(dev)
         d.set_profiling(True)
         # K1 alone (mrg_b200_chess_candidates_batch): its candidate counts against the oracle's dense response
