@@ -158,6 +158,90 @@ BW_HD void step_bwd(const PlaneRef& P, BitWindow& W, int& x, int& y, int& k, int
     x += dir_dx(a); y += dir_dy(a); k = (a + 4) & 7;
 }
 
+// ---- borders in SEGMENTS --------------------------------------------------------------------------------------
+// A long border would keep the lane that follows it busy long after every other lane has finished, so borders are
+// cut at SEGMENT STARTS, states that can be recognised locally both by a scan of the plane and by a walker that
+// arrives at them:
+//   * the candidate starts below (first pixel of a component / of a hole),
+//   * row cuts: a state whose run holds W or E, at a pixel with y % 256 == 0,
+//   * column cuts: a state whose run holds N or S, at a pixel with x % 256 == 0.
+// A border cannot run further than that down or up a side, or along a top or a bottom, without meeting one, so
+// segments stay short. Each
+// segment start is walked FORWARD to the next one by its own lane (length, area sum, smallest discovery position of
+// its states); a candidate then follows the chain of segments from its own -- one hash look-up per segment instead
+// of one step per state -- until it is back at itself (it is where the scan discovers the border) or meets a
+// segment holding a state the scan reaches earlier (it is not).
+constexpr int kCutMask = 255;
+
+// the state of pixel (x,y) whose run of background neighbours holds direction d0 (which must be background):
+// *k = where the trace leaves; false if the pixel has no foreground neighbour at all
+BW_HD bool state_after(const PlaneRef& P, BitWindow& W, int x, int y, int d0, int* k)
+{
+    const uint32_t m = W.nbr8(P, x, y);
+    const int s0 = (d0 + 1) & 7;
+    const uint32_t r = ((m | (m << 8)) >> s0) & 0x7Fu;             // directions d0+1 .. d0+7
+    if (!r) return false;
+    *k = (s0 + ffs32(r) - 1) & 7;
+    return true;
+}
+
+// discovery position of the state (x,y,k) (or -1), whether it is a segment start, and, if it is a candidate start
+// (first pixel of a component: its run holds W, NW, N, NE; pixel left of a hole's first: it leaves towards NE with E in
+// its run), the position at which the raster scan would discover a border there (else -1)
+BW_HD void classify_state(const PlaneRef& P, BitWindow& W, int x, int y, int k, int* disc, bool* is_start, int* cand_pos)
+{
+    const uint32_t m = W.nbr8(P, x, y);
+    const uint32_t r = ((m | (m << 8)) >> k) & 0xFFu;              // bit i = direction k + i; bit 0 (k itself) is set
+    const int hb = 31 - clz32(r);                                  // run of the state = directions k+hb+1 .. k+7
+    const bool hasW = ((4 - k) & 7) > hb, hasN = ((2 - k) & 7) > hb, hasE = ((0 - k) & 7) > hb, hasS = ((6 - k) & 7) > hb;
+    const bool hasNW = ((3 - k) & 7) > hb, hasNE = ((1 - k) & 7) > hb;
+    int d = -1;
+    if (hasW) d = y * P.w + x;
+    else if (hasE && x + 1 < P.w) d = y * P.w + x + 1;
+    *disc = d;
+    const bool outer = hasW && hasNW && hasN && hasNE, hole = k == 1 && hasE && x + 1 < P.w;
+    *cand_pos = outer ? y * P.w + x : hole ? y * P.w + x + 1 : -1;
+    *is_start = outer || (k == 1 && hasE) || ((hasW || hasE) && (y & kCutMask) == 0) || ((hasN || hasS) && (x & kCutMask) == 0);
+}
+
+// (x,y,k) -> its successor, with the successor's discovery position and whether it is a segment start
+BW_HD void step_fwd_ex(const PlaneRef& P, BitWindow& W, int& x, int& y, int& k, int* disc, bool* is_start)
+{
+    const int qx = x + dir_dx(k), qy = y + dir_dy(k);
+    const uint32_t m = W.nbr8(P, qx, qy);
+    const int s0 = (k + 5) & 7;
+    const uint32_t rot = ((m | (m << 8)) >> s0) & 0xFFu;
+    const int j = ffs32(rot) - 1;                                  // run of the new state = directions s0 .. s0+j-1
+    x = qx; y = qy; k = (s0 + j) & 7;
+    const bool hasW = ((4 - s0) & 7) < j, hasN = ((2 - s0) & 7) < j, hasE = ((0 - s0) & 7) < j, hasS = ((6 - s0) & 7) < j;
+    const bool hasNW = ((3 - s0) & 7) < j, hasNE = ((1 - s0) & 7) < j;
+    int d = -1;
+    if (hasW) d = qy * P.w + qx;
+    else if (hasE && qx + 1 < P.w) d = qy * P.w + qx + 1;
+    *disc = d;
+    *is_start = (hasW && hasNW && hasN && hasNE) || (k == 1 && hasE) || ((hasW || hasE) && (qy & kCutMask) == 0) || ((hasN || hasS) && (qx & kCutMask) == 0);
+}
+
+// key of a state within a chunk: job << 33 | y << 18 | x << 3 | k
+BW_HD unsigned long long state_key(int job, int x, int y, int k)
+{
+    return (unsigned long long)job << 33 | (unsigned long long)y << 18 | (unsigned long long)x << 3 | (unsigned long long)k;
+}
+
+// cut masks of one plane word (cur / left / right = words wd, wd-1, wd+1 of row y; up / dn = word wd of rows y-1, y+1):
+// foreground pixels with background to the W / to the E on rows y % 256 == 0, and with background to the N / to the S
+// at x % 256 == 0. The state meant is the one whose run holds that neighbour (state_after with d0 = 4 / 0 / 2 / 6).
+BW_HD void cut_masks(uint32_t cur, uint32_t left, uint32_t right, uint32_t up, uint32_t dn, int wd, int y,
+                     uint32_t* cutW, uint32_t* cutE, uint32_t* cutN, uint32_t* cutS)
+{
+    const uint32_t Wn = (cur << 1) | (left >> 31), En = (cur >> 1) | (right << 31);
+    const bool row = (y & kCutMask) == 0, col = ((wd * 32) & kCutMask) == 0;
+    *cutW = row ? cur & ~Wn : 0u;
+    *cutE = row ? cur & ~En : 0u;
+    *cutN = col ? cur & ~up & 1u : 0u;
+    *cutS = col ? cur & ~dn & 1u : 0u;
+}
+
 // Candidate starts, the only places a cycle's smallest discovery position can be:
 //   kind 0: foreground pixel (x,y) whose W, NW, N, NE neighbours are background (first pixel of a component);
 //           *k = where the trace leaves it, false for an isolated pixel (a one-point contour: area 0, never kept)

@@ -16,14 +16,18 @@
 // at its raster-first state -- so every border is followed by its own lane:
 //   B1  blob_binarize_kernel   gray -> 17 bit planes per frame (one pass over the frame, 1 B/px read):
 //                              a thread bit-slices 32 pixels once, each plane is then a handful of word ops
-//   B2a blob_walk_kernel       persistent warps scan the planes tile by tile for candidate first pixels
-//                              of components / holes (word ops); each lane takes a candidate and sends two
-//                              walkers around its border in opposite directions, which either meet (the
-//                              candidate is where OpenCV's scan discovers that border: a record with the
-//                              border's length and exact area is emitted if the area passes the filter)
-//                              or run into a state the scan meets earlier (not the start: dropped).
-//                              Lanes refill from a per-warp list; no marks, no per-plane sequential pass.
-//   B2b blob_points_kernel     one lane per kept border walks it once more: stores its points and sums the
+//   B2a blob_scan_kernel       segment starts by word operations: candidate first pixels of components / holes,
+//                              and cut states on every 64th row / column (borders are followed in segments, so
+//                              that a frame-sized outline does not keep one lane busy for milliseconds)
+//   B2b blob_segment_kernel    one lane per segment start, lanes refilling from the queue: walks to the next
+//                              segment start; length, area sum, earliest discovery position of its states
+//   B2c blob_link_kernel, blob_chain_kernel   segments find their neighbours (one hash look-up each); one lane per
+//                              candidate then follows the chain of segments in both directions
+//                              until the two ends meet (the candidate is where OpenCV's scan discovers that
+//                              border: a record with the border's length and exact area is emitted if the area
+//                              passes the filter) or meets a segment the scan reaches earlier (dropped).
+//                              No marks, no per-plane sequential pass.
+//   B2d blob_points_kernel     one lane per kept border walks it once more: stores its points and sums the
 //                              remaining Green's-theorem moments and the bounding box (exact integers).
 //   B3  blob_contour_warp_kernel  one warp per kept border: convex-hull area from per-column extremes,
 //                              centre, colour test, median point distance by radix selection on the IEEE
@@ -73,7 +77,8 @@ struct BlobGeom
     int nframes;
     unsigned pts_cap;                           // points of the whole chunk
     unsigned rec_cap;
-    unsigned queue_cap;                         // candidate starts of the whole chunk
+    unsigned queue_cap;                         // segment starts of the whole chunk (queue entries, segments, candidate list)
+    unsigned hash_mask;                         // slots of the state -> segment table, minus 1 (a power of two >= 2 * queue_cap)
     size_t plane_words;                         // storage words of one plane: (h + 2) rows of wpr words
     int origin;                                 // word offset of pixel (0,0) in a plane's storage
 };
@@ -83,7 +88,7 @@ __device__ __forceinline__ const uint32_t* plane_ptr(const BlobGeom& g, const ui
 }
 
 // device counters (uint32 each)
-enum { kCntRecords = 0, kCntStatus = 1, kCntPoints = 2, kCntQueue = 3, kCntPointJob = 4, kCntQueueHead = 5, kCntWords = 8 };
+enum { kCntRecords = 0, kCntStatus = 1, kCntPoints = 2, kCntQueue = 3, kCntPointJob = 4, kCntQueueHead = 5, kCntSegs = 6, kCntCands = 7, kCntWords = 8 };
 
 // ------------------------------------------------------------------------------------------------
 // B1: bit planes. plane(f,k)[y][wd] bit b = gray(f, y, 32*wd + b) > thr_k
@@ -167,11 +172,12 @@ blob_binarize_kernel(FrameSet fs, BlobGeom g, uint32_t* __restrict__ planes, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// B2a: candidate starts (blob_scan_kernel) and their verification walks (blob_walk_kernel); see blob_walk.cuh
+// B2a-c: segment starts (blob_scan_kernel), segments (blob_segment_kernel), chains (blob_chain_kernel); see blob_walk.cuh
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileRows  = 16;                  // a tile = 32 words (1024 pixels) x 16 rows of one plane, one warp
 constexpr unsigned kFull = 0xffffffffu;
-// queue entry: job << 32 | kind << 30 | y << 15 | x   (kind 0: first pixel of a component, 1: first pixel of a hole)
+// queue entry: job << 40 | kind << 32 | y << 16 | x   (kind 0: first pixel of a component, 1: first pixel of a hole,
+// 2..5: cut state with background to the W / E / N / S -- the segment starts of blob_walk.cuh)
 
 __global__ void __launch_bounds__(256)
 blob_scan_kernel(BlobGeom g, const uint32_t* __restrict__ planes, unsigned long long* __restrict__ queue,
@@ -191,9 +197,9 @@ blob_scan_kernel(BlobGeom g, const uint32_t* __restrict__ planes, unsigned long 
         const bool in = wd * 32 < g.w;                      // (words past the image are background; so are rows -1 and h)
         // the tile's rows -1 .. rows-1 of this lane's word column, all loads in flight at once; the words of the
         // neighbouring columns come from the neighbouring lanes (lanes 0 and 31 load theirs)
-        uint32_t c[kTileRows + 1], el[kTileRows + 1], er[kTileRows + 1];
+        uint32_t c[kTileRows + 2], el[kTileRows + 1], er[kTileRows + 1];
 #pragma unroll
-        for (int r = 0; r <= kTileRows; r++) c[r] = (in && r <= rows) ? B[(y0 + r - 1) * g.wpr + wd] : 0u;
+        for (int r = 0; r <= kTileRows + 1; r++) c[r] = (in && r <= rows + 1) ? B[(y0 + r - 1) * g.wpr + wd] : 0u;     // rows y0-1 .. y0+rows
         if (lane == 0 || lane == 31)
         {
             const int wn = lane == 0 ? wd - 1 : wd + 1;
@@ -207,14 +213,17 @@ blob_scan_kernel(BlobGeom g, const uint32_t* __restrict__ planes, unsigned long 
             er[r] = lane == 31 ? el[r] : rr;
             el[r] = lane == 0 ? el[r] : l;
         }
-        uint32_t outer[kTileRows], hole[kTileRows];
+        // per row: candidates (kinds 0, 1) and cut states (kinds 2..5: background to the W / E / N / S)
+        uint32_t mk[kTileRows][6];
         unsigned cnt = 0;
 #pragma unroll
         for (int r = 0; r < kTileRows; r++)
         {
-            candidate_masks(c[r + 1], el[r + 1], c[r], el[r], er[r], &outer[r], &hole[r]);
-            if (r >= rows) { outer[r] = 0; hole[r] = 0; }
-            cnt += __popc(outer[r]) + __popc(hole[r]);
+            candidate_masks(c[r + 1], el[r + 1], c[r], el[r], er[r], &mk[r][0], &mk[r][1]);
+            cut_masks(c[r + 1], el[r + 1], er[r + 1], c[r], c[r + 2], wd, y0 + r, &mk[r][2], &mk[r][3], &mk[r][4], &mk[r][5]);
+            mk[r][2] &= ~mk[r][0];                              // (the same state: a component's first pixel on a cut row)
+#pragma unroll
+            for (int q = 0; q < 6; q++) { if (r >= rows) mk[r][q] = 0; cnt += __popc(mk[r][q]); }
         }
         if (__ballot_sync(kFull, cnt != 0))
         {
@@ -228,36 +237,57 @@ blob_scan_kernel(BlobGeom g, const uint32_t* __restrict__ planes, unsigned long 
 #pragma unroll
             for (int r = 0; r < kTileRows; r++)
             {
-                if ((outer[r] | hole[r]) == 0) continue;
-                const unsigned long long hi = (unsigned long long)job << 32 | (unsigned)(y0 + r) << 15 | (unsigned)(wd * 32);
-                uint32_t m = outer[r];
-                while (m) { const int bb = __ffs(m) - 1; m &= m - 1; if (at < g.queue_cap) queue[at] = hi | (unsigned)bb; at++; }
-                m = hole[r];
-                while (m) { const int bb = __ffs(m) - 1; m &= m - 1; if (at < g.queue_cap) queue[at] = hi | 1ull << 30 | (unsigned)bb; at++; }
+                const unsigned long long hi = (unsigned long long)job << 40 | (unsigned long long)(y0 + r) << 16 | (unsigned)(wd * 32);
+#pragma unroll
+                for (int q = 0; q < 6; q++)
+                {
+                    uint32_t m = mk[r][q];
+                    while (m) { const int bb = __ffs(m) - 1; m &= m - 1; if (at < g.queue_cap) queue[at] = hi | (unsigned long long)q << 32 | (unsigned)bb; at++; }
+                }
             }
         }
     }
 }
 
+// One segment of a border: from a segment start to the next one
+struct BlobSegment
+{
+    unsigned long long start, end;               // blobwalk::state_key of its first state / of the next segment's
+    long long a00;                               // sum over its edges of (Px*Qy - Qx*Py)
+    int n;                                       // its states
+    int min_disc;                                // smallest discovery position of its states (INT_MAX: none)
+    int cand_pos;                                // if its first state is a candidate start: its discovery position, else -1
+    unsigned next;                               // the segment that starts where this one ends (blob_link_kernel)
+    unsigned prev, pad;                          // the segment that ends where this one starts
+};
+constexpr unsigned long long kNoKey = ~0ull;
+__device__ __forceinline__ unsigned hash_of(unsigned long long key, unsigned mask)
+{
+    key ^= key >> 29; key *= 0x9E3779B97F4A7C15ull; key ^= key >> 32;
+    return (unsigned)key & mask;
+}
+
+// B2b: every segment start is walked forward to the next one, by its own lane; lanes refill from the queue
 __global__ void __launch_bounds__(128)
-blob_walk_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsigned long long* __restrict__ queue,
-                 BlobRecord* __restrict__ recs, unsigned* __restrict__ counters)
+blob_segment_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsigned long long* __restrict__ queue,
+                    unsigned long long* __restrict__ hkeys, unsigned* __restrict__ hvals, BlobSegment* __restrict__ segs,
+                    unsigned* __restrict__ counters)
 {
     const int lane = threadIdx.x & 31;
     const unsigned qn_all = counters[kCntQueue];
     if (qn_all > g.queue_cap) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(&counters[kCntStatus], 1u); return; }
     const unsigned qn = qn_all;
-    const long long max_steps = 4LL * g.w * g.h + 16;
+    const int max_steps = (int)min(4LL * g.w * g.h + 16, 0x7ffffff0LL);
 
     bool active = false, more = true;
     PlaneRef P; P.B = planes; P.w = g.w; P.h = g.h; P.wpr = g.wpr;
-    BitWindow F, Bk;
-    int fx = 0, fy = 0, fk = 0, bx = 0, by = 0, bk = 0, pos = 0, cnt = 0, sx = 0, sy = 0, sk = 0, job = 0;
+    BitWindow F;
+    int x = 0, y = 0, k = 0, n = 0, min_disc = 0, cand_pos = -1;
+    unsigned seg = 0, myslot = 0; unsigned long long skey = 0;
+    bool fresh = false;
     long long a00 = 0;
-
     for (;;)
     {
-        // idle lanes take the queue's next candidates
         const unsigned idle = __ballot_sync(kFull, !active);
         if (idle && more)
         {
@@ -269,64 +299,140 @@ blob_walk_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsigned
             if (!active && my < qn)
             {
                 const unsigned long long e = queue[my];
-                const int x = (int)(e & 0x7FFFu), y = (int)((e >> 15) & 0x7FFFu);
-                job = (int)(e >> 32); P.B = plane_ptr(g, planes, job);
-                F.init(); Bk.init();
-                pos = y * g.w + x;
+                const int ex = (int)(e & 0xFFFFu), ey = (int)((e >> 16) & 0xFFFFu), kind = (int)((e >> 32) & 7u), job = (int)(e >> 40);
+                P.B = plane_ptr(g, planes, job);
+                F.init();
                 bool ok = true;
-                if ((e >> 30) & 1u) { sx = x - 1; sy = y; sk = 1; }
-                else { sx = x; sy = y; ok = outer_start(P, F, x, y, &sk); }          // false: isolated pixel, area 0
-                if (ok) { fx = bx = sx; fy = by = sy; fk = bk = sk; a00 = 0; cnt = 0; active = true; }
-            }
-        }
-        if (!__any_sync(kFull, active)) { if (!more) break; continue; }
-
-#pragma unroll 1
-        for (int it = 0; it < 8; it++)
-        {
-            if (active)
-            {
-                // Both walkers step every time, as two independent dependency chains; the backward step is thrown
-                // away when the forward one already decided (order of the tests as in blobwalk::verify_start).
-                int discf, discb;
-                const int px = fx, py = fy, qx = bx, qy = by, qk = bk;
-                step_fwd(P, F, fx, fy, fk, &discf);
-                step_bwd(P, Bk, bx, by, bk, &discb);
-                a00 += (long long)(px * fy - fx * py); cnt++;
-                bool drop = discf >= 0 && discf < pos;
-                bool met = !drop && fx == qx && fy == qy && fk == qk;
-                if (!drop && !met)
+                if (kind == 1) { x = ex - 1; y = ey; k = 1; }
+                else { x = ex; y = ey; ok = state_after(P, F, ex, ey, kind == 3 ? 0 : kind == 4 ? 2 : kind == 5 ? 6 : 4, &k); }    // false: isolated pixel, area 0
+                if (ok)
                 {
-                    a00 += (long long)(bx * qy - qx * by); cnt++;
-                    drop = discb >= 0 && discb < pos;
-                    met = !drop && fx == bx && fy == by && fk == bk;
-                }
-                if (!drop && !met && cnt > max_steps) { atomicExch(&counters[kCntStatus], 2u); drop = true; }   // cannot happen
-                if (drop) active = false;
-                else if (met)
-                {
-                    active = false;
-                    // filterByArea: m00 = |a00| / 2 in [20, 80000) -- exact in integers. Everything else is dropped here.
-                    const long long aa = a00 < 0 ? -a00 : a00;
-                    if (aa >= 40 && aa < 160000)
+                    // the state's slot in the table: whoever gets there first owns the segment (a state can be queued twice:
+                    // a row cut that is also a column cut, ...)
+                    skey = state_key(job, x, y, k);
+                    unsigned slot = hash_of(skey, g.hash_mask);
+                    for (;;)
                     {
-                        const unsigned idx = atomicAdd(&counters[kCntRecords], 1u);
-                        const unsigned off = atomicAdd(&counters[kCntPoints], (unsigned)cnt);
-                        if (idx >= g.rec_cap || off > g.pts_cap || (unsigned)cnt > g.pts_cap - off) atomicExch(&counters[kCntStatus], 1u);
-                        else
-                        {
-                            BlobRecord r;
-                            r.frame = job / kNThr; r.thr = job % kNThr; r.seq = pos; r.n = cnt; r.pts_off = off;
-                            r.sx = sx; r.sy = sy; r.sk = sk;
-                            r.xmin = r.xmax = r.ymin = r.ymax = 0;
-                            r.a00 = a00; r.a10 = r.a01 = r.a20 = r.a11 = r.a02 = 0;
-                            r.hull2 = 0; r.cx = r.cy = r.radius = 0; r.colour_ok = 0; r.big = 0;
-                            recs[idx] = r;
-                        }
+                        const unsigned long long old = atomicCAS(&hkeys[slot], kNoKey, skey);
+                        if (old == kNoKey) break;
+                        if (old == skey) { ok = false; break; }
+                        slot = (slot + 1) & g.hash_mask;
+                    }
+                    if (ok)
+                    {
+                        myslot = slot;
+                        int disc; bool st;
+                        classify_state(P, F, x, y, k, &disc, &st, &cand_pos);
+                        min_disc = disc < 0 ? INT_MAX : disc;
+                        n = 0; a00 = 0; active = true; fresh = true;
                     }
                 }
             }
+            // segment indices for the lanes that just started one: one atomic per warp (<= queue entries <= queue_cap)
+            const unsigned starting = __ballot_sync(kFull, fresh);
+            if (starting)
+            {
+                unsigned first = 0;
+                if (lane == 0) first = atomicAdd(&counters[kCntSegs], (unsigned)__popc(starting));
+                first = __shfl_sync(kFull, first, 0);
+                if (fresh) { seg = first + __popc(starting & ((1u << lane) - 1u)); hvals[myslot] = seg; fresh = false; }
+            }
         }
+        if (!__any_sync(kFull, active)) { if (!more) break; continue; }
+#pragma unroll 1
+        for (int it = 0; it < 16; it++)
+        {
+            if (active)
+            {
+                const int px = x, py = y;
+                int disc; bool st;
+                step_fwd_ex(P, F, x, y, k, &disc, &st);
+                a00 += (long long)(px * y - x * py); n++;
+                if (st || n > max_steps)
+                {
+                    if (!st) atomicExch(&counters[kCntStatus], 2u);         // cannot happen
+                    BlobSegment s;
+                    s.start = skey; s.end = state_key((int)(skey >> 33), x, y, k); s.a00 = a00; s.n = n; s.min_disc = min_disc;
+                    s.cand_pos = cand_pos; s.next = s.prev = 0xFFFFFFFFu; s.pad = 0;
+                    segs[seg] = s;
+                    active = false;
+                }
+                else if (disc >= 0 && disc < min_disc) min_disc = disc;
+            }
+        }
+    }
+}
+
+// B2c: segments find their neighbours: one hash look-up each, after which the chains are followed by index
+__global__ void __launch_bounds__(256)
+blob_link_kernel(BlobGeom g, const unsigned long long* __restrict__ hkeys, const unsigned* __restrict__ hvals,
+                 BlobSegment* __restrict__ segs, unsigned* __restrict__ counters)
+{
+    if (counters[kCntStatus]) return;
+    const unsigned nseg = counters[kCntSegs];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nseg; i += gridDim.x * blockDim.x)
+    {
+        const unsigned long long end = segs[i].end;
+        unsigned slot = hash_of(end, g.hash_mask);
+        bool found = true;
+        while (hkeys[slot] != end)
+        {
+            if (hkeys[slot] == kNoKey) { found = false; break; }
+            slot = (slot + 1) & g.hash_mask;
+        }
+        if (!found) { atomicExch(&counters[kCntStatus], 2u); continue; }                 // cannot happen: every segment ends at a segment start
+        const unsigned j = hvals[slot];
+        segs[i].next = j;
+        segs[j].prev = i;
+    }
+}
+
+// B2d: every candidate follows the chain of segments from its own, in both directions at once (as the walkers of
+// single states did before: a candidate that is not its border's start meets a segment holding a state the raster
+// scan reaches earlier within a few hops one way or the other, and is dropped). If the two ends meet instead, the
+// candidate is where the scan discovers the border, whose length and area are then known -- a record is emitted if
+// the area passes the filter.
+__global__ void __launch_bounds__(128)
+blob_chain_kernel(BlobGeom g, const BlobSegment* __restrict__ segs, BlobRecord* __restrict__ recs, unsigned* __restrict__ counters)
+{
+    if (counters[kCntStatus]) return;
+    const unsigned nseg = counters[kCntSegs];
+    for (unsigned c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < nseg; c0 += gridDim.x * blockDim.x)
+    {
+        const int pos = segs[c0].cand_pos;
+        if (pos < 0) continue;                   // (a cut state: not where any border can be discovered)
+        const BlobSegment c = segs[c0];
+        if (c.min_disc < pos) continue;
+        long long a00 = c.a00, n = c.n;
+        unsigned f = c0, b = c0;                 // covered so far: the segments from b forward to f (through c0)
+        bool keep = true;
+        for (unsigned hops = 0; ; hops++)
+        {
+            if (hops > g.queue_cap) { atomicExch(&counters[kCntStatus], 2u); keep = false; break; }    // cannot happen
+            const unsigned fn = segs[f].next;
+            if (fn == b) break;
+            { const BlobSegment& s = segs[fn]; if (s.min_disc < pos) { keep = false; break; } a00 += s.a00; n += s.n; }
+            f = fn;
+            const unsigned bp = segs[b].prev;
+            if (bp == f) break;
+            { const BlobSegment& s = segs[bp]; if (s.min_disc < pos) { keep = false; break; } a00 += s.a00; n += s.n; }
+            b = bp;
+        }
+        if (!keep) continue;
+        // filterByArea: m00 = |a00| / 2 in [20, 80000) -- exact in integers. Everything else is dropped here.
+        const long long aa = a00 < 0 ? -a00 : a00;
+        if (aa < 40 || aa >= 160000) continue;
+        const unsigned idx = atomicAdd(&counters[kCntRecords], 1u);
+        const unsigned off = atomicAdd(&counters[kCntPoints], (unsigned)n);
+        if (idx >= g.rec_cap || off > g.pts_cap || (unsigned long long)n > g.pts_cap - off) { atomicExch(&counters[kCntStatus], 1u); continue; }
+        const int job = (int)(c.start >> 33);
+        BlobRecord r;
+        r.frame = job / kNThr; r.thr = job % kNThr; r.seq = pos; r.n = (int)n; r.pts_off = off;
+        r.sx = (int)((c.start >> 3) & 0x7FFFu); r.sy = (int)((c.start >> 18) & 0x7FFFu); r.sk = (int)(c.start & 7u);
+        r.xmin = r.xmax = r.ymin = r.ymax = 0;
+        r.a00 = a00; r.a10 = r.a01 = r.a20 = r.a11 = r.a02 = 0;
+        r.hull2 = 0; r.cx = r.cy = r.radius = 0; r.colour_ok = 0; r.big = 0;
+        recs[idx] = r;
     }
 }
 
@@ -750,8 +856,9 @@ struct BlobWorkspace
 {
     void* planes = nullptr; void* pts = nullptr; void* recs = nullptr;
     void* scratch = nullptr; void* counters = nullptr; void* queue = nullptr;
-    size_t planes_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0, queue_b = 0;
-    unsigned pts_per_frame = 1u << 21, rec_per_job = 512, queue_per_frame = 1u << 18;
+    void* hkeys = nullptr; void* hvals = nullptr; void* segs = nullptr;
+    size_t planes_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0, queue_b = 0, hkeys_b = 0, hvals_b = 0, segs_b = 0;
+    unsigned pts_per_frame = 1u << 21, rec_per_job = 512, queue_per_frame = 1u << 17;
     BlobRecord* host_recs = nullptr; size_t host_recs_cap = 0;      // pinned
     unsigned* host_counters = nullptr;                              // pinned
     std::vector<unsigned> order, first;
@@ -768,6 +875,7 @@ void blob_workspace_destroy(BlobWorkspace* ws)
     if (!ws) return;
     cudaFree(ws->planes); cudaFree(ws->pts); cudaFree(ws->recs);
     cudaFree(ws->scratch); cudaFree(ws->counters); cudaFree(ws->queue);
+    cudaFree(ws->hkeys); cudaFree(ws->hvals); cudaFree(ws->segs);
     if (ws->host_recs) cudaFreeHost(ws->host_recs);
     if (ws->host_counters) cudaFreeHost(ws->host_counters);
     if (ws->e0) cudaEventDestroy(ws->e0);
@@ -789,7 +897,7 @@ static cudaError_t grow(void** p, size_t* have, size_t want)
 #define BLOB_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
     fprintf(stderr, "%s:%d in %s(): CUDA failure '%s' in " #expr ". Sorry.\n", __FILE__, __LINE__, __func__, cudaGetErrorString(_e)); return -1; } } while (0)
 
-void blob_workspace_reset_capacity(BlobWorkspace* ws) { ws->pts_per_frame = 1u << 21; ws->rec_per_job = 512; ws->queue_per_frame = 1u << 18; }
+void blob_workspace_reset_capacity(BlobWorkspace* ws) { ws->pts_per_frame = 1u << 21; ws->rec_per_job = 512; ws->queue_per_frame = 1u << 17; }
 
 // Enqueues the kernels of one chunk of device-resident frames on `stream` (nothing is waited for; the frames may
 // be overwritten once the first kernel has run, i.e. after whatever is enqueued next on `stream`). Returns 0 / -1.
@@ -829,16 +937,24 @@ int blob_enqueue(BlobWorkspace* ws, const FrameSet& fs, cudaStream_t stream)
     g.rec_cap = (unsigned)std::min<unsigned long long>((unsigned long long)ws->rec_per_job * n * kNThr, 0x7FFFFFFFull);
     g.queue_cap = (unsigned)std::min<unsigned long long>((unsigned long long)ws->queue_per_frame * n, 0x7FFFFFFFull);
     BLOB_TRY(grow(&ws->queue, &ws->queue_b, (size_t)g.queue_cap * 8));
+    unsigned slots = 1024; while (slots < 2ull * g.queue_cap && slots < 0x80000000u) slots <<= 1;
+    g.hash_mask = slots - 1;
+    BLOB_TRY(grow(&ws->hkeys, &ws->hkeys_b, (size_t)slots * 8));
+    BLOB_TRY(grow(&ws->hvals, &ws->hvals_b, (size_t)slots * 4));
+    BLOB_TRY(grow(&ws->segs, &ws->segs_b, (size_t)g.queue_cap * sizeof(BlobSegment)));
     BLOB_TRY(grow(&ws->pts, &ws->pts_b, (size_t)g.pts_cap * 4));
     BLOB_TRY(grow(&ws->recs, &ws->recs_b, (size_t)g.rec_cap * sizeof(BlobRecord)));
     unsigned* counters = (unsigned*)ws->counters;
     BLOB_TRY(cudaMemsetAsync(ws->counters, 0, kCntWords * 4, stream));
     BLOB_TRY(cudaEventRecord(ws->e0, stream));
+    BLOB_TRY(cudaMemsetAsync(ws->hkeys, 0xFF, ((size_t)g.hash_mask + 1) * 8, stream));
     blob_binarize_kernel<<<dim3((g.wpr + 127) / 128, plane_rows(g.h), n), 128, 0, stream>>>(fs, g, (uint32_t*)ws->planes, aligned);
     blob_scan_kernel<<<148 * 8, 256, 0, stream>>>(g, (const uint32_t*)ws->planes, (unsigned long long*)ws->queue, counters,
                                                   (unsigned)ntiles64, nstrips, ncb);
-    blob_walk_kernel<<<148 * 6, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (const unsigned long long*)ws->queue,
-                                                  (BlobRecord*)ws->recs, counters);
+    blob_segment_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (const unsigned long long*)ws->queue,
+                                                     (unsigned long long*)ws->hkeys, (unsigned*)ws->hvals, (BlobSegment*)ws->segs, counters);
+    blob_link_kernel<<<148 * 8, 256, 0, stream>>>(g, (const unsigned long long*)ws->hkeys, (const unsigned*)ws->hvals, (BlobSegment*)ws->segs, counters);
+    blob_chain_kernel<<<148 * 8, 128, 0, stream>>>(g, (const BlobSegment*)ws->segs, (BlobRecord*)ws->recs, counters);
     blob_points_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (BlobRecord*)ws->recs, counters, (uint32_t*)ws->pts);
     blob_contour_warp_kernel<<<148 * 2, kW3Warps * 32, kW3Warps * sizeof(WarpScratch), stream>>>(
         g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts, (BlobRecord*)ws->recs, counters);

@@ -165,3 +165,19 @@ def circle_grid_frame(w, h, n=10, seed=0, noise_sigma=2.0, blur=True):
         f = f + rng.normal(0.0, noise_sigma, size=f.shape).astype(np.float32)
     img = np.clip(np.rint(f), 0, 255).astype(np.uint8)
     return box_blur3(img) if blur else img
+
+
+def camera_frame(w, h, n=10, seed=0, noise_sigma=5.0):
+    """A board the way a camera sees it: the synthetic board on a textured (blurred-noise) background, radial
+    vignetting down to ~55 % in the corners, the 3x3 box blur, and THEN sensor noise of `noise_sigma` grey levels
+    (so the noise reaches the detector unblurred, as shot noise does when the CLI runs with --blur 0)."""
+    rng = np.random.default_rng(seed)
+    board = board_frame(w, h, n, seed=seed, noise_sigma=0.0, blur=False).astype(np.float32)
+    tex = blurred_noise_frame(w, h, seed=seed + 7919, passes=2).astype(np.float32)
+    f = np.where(board == float(BACKGROUND), 0.5 * float(BACKGROUND) + 0.5 * tex, board)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    r2 = ((xx - w / 2.0) / (w / 2.0)) ** 2 + ((yy - h / 2.0) / (h / 2.0)) ** 2
+    f = f * (1.0 - 0.225 * r2)
+    img = box_blur3(np.clip(np.rint(f), 0, 255).astype(np.uint8)).astype(np.float32)
+    img += rng.normal(0.0, noise_sigma, size=img.shape).astype(np.float32)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))

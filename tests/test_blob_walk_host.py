@@ -23,19 +23,25 @@ def lib():
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", SO])
     lib = ctypes.CDLL(SO)
     lib.blob_walk_host_contours.restype = ctypes.c_int
+    lib.blob_walk_host_contours_segments.restype = ctypes.c_int
     return lib
 
 
-def walk_contours(lib, binary):
+def walk_contours(lib, binary, segments=False):
     binary = np.ascontiguousarray(binary, dtype=np.uint8)
     h, w = binary.shape
     xy = np.empty((4 * w * h + 16, 2), dtype=np.int32)
     lens = np.empty(w * h + 16, dtype=np.int32)
     area2 = np.empty(w * h + 16, dtype=np.int64)
-    n = lib.blob_walk_host_contours(binary.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), w, h, binary.strides[0],
-                                    xy.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(xy),
-                                    lens.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-                                    area2.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), len(lens))
+    args = (binary.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), w, h, binary.strides[0],
+            xy.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(xy),
+            lens.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            area2.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), len(lens))
+    if segments:
+        nseg = ctypes.c_int(0)
+        n = lib.blob_walk_host_contours_segments(*args, ctypes.byref(nseg))
+    else:
+        n = lib.blob_walk_host_contours(*args)
     assert n >= 0
     ends = np.cumsum(lens[:n])
     return [xy[e - l:e].copy() for e, l in zip(ends, lens[:n])], area2[:n].copy()
@@ -93,3 +99,39 @@ def test_walk_word_boundaries(lib):
             got, _ = walk_contours(lib, b)
             assert len(got) == len(want)
             assert all(np.array_equal(g, wv) for g, wv in zip(got, want))
+
+
+def test_segment_chains_equal_suzuki_abe(lib):
+    """the segment formulation (candidates + row / column cuts, chained): same contours again, on images large enough
+    to hold several cut rows and columns"""
+    rng = np.random.default_rng(7)
+    nborders = 0
+    for t in range(260):
+        h = int(rng.integers(1, 330)); w = int(rng.integers(1, 400))
+        kind = t % 4
+        if kind == 0:
+            b = rng.random((h, w)) < rng.choice([0.05, 0.3, 0.5, 0.7, 0.95])
+        elif kind == 1:
+            f = rng.random((h, w))
+            for _ in range(int(rng.integers(2, 7))):
+                p = np.pad(f, 1, mode="edge")
+                f = sum(p[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)) / 9
+            b = f > np.quantile(f, rng.uniform(0.2, 0.8))
+        elif kind == 2:
+            b = np.zeros((h, w), dtype=bool)
+            for _ in range(int(rng.integers(1, 14))):
+                y0, x0 = int(rng.integers(0, h)), int(rng.integers(0, w))
+                y1, x1 = int(rng.integers(y0, h)), int(rng.integers(x0, w))
+                b[y0, x0:x1 + 1] = True; b[y1, x0:x1 + 1] = True; b[y0:y1 + 1, x0] = True; b[y0:y1 + 1, x1] = True
+            b ^= rng.random((h, w)) < 0.01
+        else:
+            b = np.ones((h, w), dtype=bool)
+            b &= ~(rng.random((h, w)) < rng.choice([0.0, 0.02, 0.2]))
+        b = b.astype(np.uint8)
+        want = po.blob_find_contours(b)
+        got, area2 = walk_contours(lib, b, segments=True)
+        assert len(got) == len(want), (b.shape, len(got), len(want))
+        for g, wv in zip(got, want):
+            assert np.array_equal(g, wv)
+        nborders += len(want)
+    assert nborders > 20000

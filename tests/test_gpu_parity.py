@@ -432,3 +432,24 @@ def test_candidate_lists_equal_the_oracles_dense_response(api, oracle):
                 assert counts[i] == len(want), (w, h, level, i)
                 assert np.array_equal(np.sort(cand[i, :counts[i]]), want), (w, h, level, i)
         det.close()
+
+
+def test_camera_like_4k_frames(api, oracle):
+    """Not only clean synthetic boards: vignetting, a textured background and sensor noise of sigma 3-8 that reaches
+    the detector unblurred, at 4K. Corner lists at levels 0-2, a refinement chain and the blob list against the oracle."""
+    for seed, sigma in ((1, 3.0), (2, 5.0), (3, 8.0)):
+        img = synth.camera_frame(3840, 2160, 10, seed=seed, noise_sigma=sigma)
+        for level in (0, 1, 2):
+            want = oracle.find_corners(img, level)
+            got = api.find_chessboard_corners_int(img, level)
+            assert np.array_equal(got, want), (seed, sigma, level, len(got), len(want))
+        xy2 = oracle.find_corners(img, 2, want_double=True)
+        if len(xy2):
+            lv = np.full(len(xy2), 2, dtype=np.int8)
+            n_o, xy_o, lv_o = oracle.refine_corners(img, 1, xy2, lv)
+            n_g, xy_g, lv_g = api.refine_chessboard_corners(img, 1, xy2, lv)
+            assert n_g == n_o and np.array_equal(xy_g, xy_o) and np.array_equal(lv_g, lv_o), (seed, sigma)
+    dots = synth.circle_grid_frame(3840, 2160, 10, seed=4).astype(np.float32)
+    dots += np.random.default_rng(5).normal(0.0, 5.0, size=dots.shape).astype(np.float32)
+    dots = np.clip(np.rint(dots), 0, 255).astype(np.uint8)
+    assert np.array_equal(api.find_blobs_int(dots), oracle.find_blobs(dots))
