@@ -30,6 +30,10 @@ def main():
     det.chess_response(np.stack(base * 4))                      # dense response (tiled, TMA): host frames in, int16 out
     det.box_blur(frames, 1); det.box_blur(frames[:16], 2)       # 3x3 blur (HBM-bound kernel), generic radius
     det.preprocess(frames, clahe=True, blur_radius=0)           # min/max, normalisation table, CLAHE tables, CLAHE apply
+    raw16 = torch.from_numpy((np.stack([base[i % 4] for i in range(16)]).astype(np.int32) * 200 + 500).astype(np.uint16).view(np.int16)).cuda()
+    det.preprocess16(raw16, clahe=True, blur_radius=0)           # 16-bit input: min/max, 65536-bin histograms, tables, apply + convert
+    det.preprocess16(raw16, clahe=False, blur_radius=0)
+    det.find_corners_mixed([frames[0], frames[1][:1080, :1920], frames[2]], 0)      # gather kernel
     circles = torch.from_numpy(np.stack([synth.circle_grid_frame(W, H, 10, seed=s % 4) for s in range(n)])).cuda()
     det.find_blobs(circles)                                     # B1, scan, walk, points, contour kernels
     det.find_blobs(frames)
