@@ -591,6 +591,10 @@ def run_ours(a):
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "avg_launch_ms": avg_launch_ms, "bytes_per_launch": bytes_per_launch, "frames_per_launch": frames_per_launch,
                 "k1_share_of_step": cnt.k1_ms / elapsed_ms,
+                # the same bytes over the whole timed region: the fraction of the HBM peak the WHOLE detector runs at. When
+                # k1_share_of_step is well above 1 (short launches: the K1 launches of the two detectors run concurrently),
+                # the per-launch `frac` above understates K1 and this is the number to read.
+                "step_frac": (nloc * a.steps * lvl_px / (elapsed_ms * 1e-3) / 1e9) / peak,
                 "k2_avg_launch_ms": cnt.k2_ms / max(cnt.k1_n, 1),
                 "sustained_frac": (frames_per_launch * lvl_px / (sustained["k1_avg_launch_ms"] * 1e-3) / 1e9 / peak) if sustained and sustained["k1_avg_launch_ms"] > 0 else None,
                 "by_content": by_content}

@@ -145,6 +145,7 @@ struct mrg_b200_detector
     bool profiling = false;
     KernelTimer timers[3];
     int k2_smem_cands = kClusterSmemCands;   // adapted to the candidate counts of the previous batch (collect_locked)
+    int k2_rows = 0, k2_cols = 0, k2_level = -1;   // ... of this geometry
     static constexpr int kBlobDepth = 4;       // chunks of the blob path kept in flight
     BlobWorkspace* blobs[kBlobDepth] = {};
     Slot blob_slot[kBlobDepth];                // their staged frames (host input)
@@ -346,6 +347,11 @@ int enqueue_locked(mrg_b200_detector* det, const uint8_t* images, int on_device,
     DEVICE_GUARD(det);
     for (auto& t : det->timers) t.reset();
 
+    // the clustering kernel's shared memory is sized from the previous batch's candidate counts; frames of another
+    // geometry say nothing about this batch's: start from the largest size again (a list that outgrows the choice
+    // takes the slow global-scratch path)
+    if (rows != det->k2_rows || cols != det->k2_cols || level != det->k2_level)
+    { det->k2_smem_cands = kClusterSmemCands; det->k2_rows = rows; det->k2_cols = cols; det->k2_level = level; }
     const int cap = det->cfg.candidate_capacity;
     if (det->h_xy.ensure(sizeof(int32_t) * 2 * mp * std::max(nframes, 1))) return -1;
     if (det->h_counts.ensure(sizeof(int32_t) * std::max(nframes, 1))) return -1;
