@@ -191,55 +191,57 @@ struct LocalRegion
 __device__ void grow_component_local(Component& c, LocalRegion& g, int seed, int w, int h)
 {
     // Stackless depth-first replay of follow_connected_component() (find_chessboard_corners.cc:228-267) on
-    // the region's local graph. The node being expanded keeps its four neighbour indices (one 32-bit load)
-    // and its next direction in registers; per-node state goes to the local arrays only when the walk
-    // descends to a child, so a neighbour test costs one dependent load (lr[q]) instead of three.
+    // the region's local graph, as ONE flat loop: an iteration is either a "pop" (membership test of `cur`) or one
+    // direction of the node being expanded. Lanes replaying different regions then execute the same loop body
+    // whatever the depth of their walks; the nested loops this replaces left 3-7 active lanes per warp.
+    // The node being expanded keeps its four neighbour indices (one 32-bit load) and its next direction in
+    // registers; per-node state goes to the local arrays only when the walk descends to a child.
     c.swx = c.swy = c.sw = 0; c.n = 0; c.peak = 0; c.peak_x = c.peak_y = 0; c.poisoned = false;
     const uint32_t* nbw_of = reinterpret_cast<const uint32_t*>(&g.nb[0][0]);
     int cur = seed, parent = -1, d = 0;
     uint32_t nbw = 0;
+    bool pop = true;
     for (;;)
     {
-        const int r = g.lr[cur];
-        const bool member = r != 0 && r > (c.peak >> 4);
-        g.lr[cur] = 0;
-        if (member)
+        if (pop)
         {
-            const int x = (int)(g.lkey[cur] & 0xFFFF), y = (int)(g.lkey[cur] >> 16);
-            if (r > c.peak) { c.peak = r; c.peak_x = x; c.peak_y = y; }
-            c.swx += (unsigned long long)(r * x);
-            c.swy += (unsigned long long)(r * y);
-            c.sw  += (unsigned long long)r;
-            c.n++;
-            if (x + 1 >= w - kMargin || x - 1 < kMargin || y + 1 >= h - kMargin || y - 1 < kMargin)
-                c.poisoned = true;
-            g.dfs_parent[cur] = (int8_t)parent;
-            d = 0; nbw = nbw_of[cur];
-        }
-        else
-        {
-            cur = parent;
-            if (cur < 0) break;
-            d = g.dfs_dir[cur]; nbw = nbw_of[cur];
-        }
-        bool found = false;
-        for (;;)
-        {
-            if (d == 4)
+            const int r = g.lr[cur];
+            const bool member = r != 0 && r > (c.peak >> 4);
+            g.lr[cur] = 0;
+            if (member)
             {
-                cur = g.dfs_parent[cur];
+                const int x = (int)(g.lkey[cur] & 0xFFFF), y = (int)(g.lkey[cur] >> 16);
+                if (r > c.peak) { c.peak = r; c.peak_x = x; c.peak_y = y; }
+                c.swx += (unsigned long long)(r * x);
+                c.swy += (unsigned long long)(r * y);
+                c.sw  += (unsigned long long)r;
+                c.n++;
+                if (x + 1 >= w - kMargin || x - 1 < kMargin || y + 1 >= h - kMargin || y - 1 < kMargin)
+                    c.poisoned = true;
+                g.dfs_parent[cur] = (int8_t)parent;
+                d = 0; nbw = nbw_of[cur];
+            }
+            else
+            {
+                cur = parent;
                 if (cur < 0) break;
                 d = g.dfs_dir[cur]; nbw = nbw_of[cur];
-                continue;
             }
-            const int q = (int)(int8_t)(nbw >> (8 * d));
-            d++;
-            if (q < 0 || g.lr[q] == 0) continue;
-            g.dfs_dir[cur] = (uint8_t)d;          // where to resume when the walk comes back to this node
-            parent = cur; cur = q; found = true;
-            break;
+            pop = false;
+            continue;
         }
-        if (!found) break;
+        if (d == 4)
+        {
+            cur = g.dfs_parent[cur];
+            if (cur < 0) break;
+            d = g.dfs_dir[cur]; nbw = nbw_of[cur];
+            continue;
+        }
+        const int q = (int)(int8_t)(nbw >> (8 * d));
+        d++;
+        if (q < 0 || g.lr[q] == 0) continue;
+        g.dfs_dir[cur] = (uint8_t)d;          // where to resume when the walk comes back to this node
+        parent = cur; cur = q; pop = true;
     }
 }
 
