@@ -65,7 +65,9 @@ bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols,
    Python find_board() binds. Corners (or blobs) -> grid of gridn x gridn -> refinement; image_pyramid_level < 0
    tries levels 3,2,1,0 and keeps the first that yields a grid. Returns false when no grid was found, on error,
    or for doblobs with a level other than 0; otherwise calls add_points(xy, gridn*gridn, cookie) once and returns
-   its result. debug, debug_sequence_x/y only produce diagnostics in the reference and are ignored here. */
+   its result. debug_sequence_x/y only produce stderr traces in the reference and are ignored here; so is debug on
+   this (board) entry point -- the corner-level artefacts come from mrg_b200_debug_dump_corners(), the grid finder's
+   Voronoi dump from mrg_b200_voronoi_neighbours(). */
 bool find_chessboard_from_image_array_C(int Nrows, int Ncols,
                                         int stride,
                                         char* imagebuffer, /* const */
@@ -89,6 +91,17 @@ bool find_chessboard_from_image_array_C(int Nrows, int Ncols,
 int mrg_b200_find_chessboard_corners(const uint8_t* image, int Nrows, int Ncols, int stride,
                                      int image_pyramid_level,
                                      int* xy_out, int cap);
+
+/* The reference's --debug artefacts of ONE corner-detector call (find_chessboard_corners.cc:294-315, 346-348,
+   391-392, 400-407, 452-459, 513-541): /tmp/mrgingham-scaled-processed-level%d.png, /tmp/mrgingham-chess-response
+   [-refinement]-level%d[-positive].png (8-bit PNGs with the pixel values cv::normalize + cv::imwrite give) and the
+   self-plotting corner list /tmp/mrgingham-1-corners.vnl (find branch: refined_xy == NULL; the corners as un-quantised
+   doubles, "%f %f") or /tmp/mrgingham-1-corners-refinement-level%d.vnl (refinement branch: pass the arrays as they are
+   AFTER the refinement call; the points whose level equals image_pyramid_level are listed). The C++ adapters and the
+   bridge symbol call this when their `debug` argument is set. Returns 0 or <0. */
+int mrg_b200_debug_dump_corners(const uint8_t* image, int Nrows, int Ncols, int stride,
+                                int image_pyramid_level, const char* debug_image_filename,
+                                const double* refined_xy, const signed char* refined_levels, int Npoints);
 
 /* mrgingham::refine_chessboard_corners_from_image_array(), find_chessboard_corners.cc:591-619.
    xy_inout: Npoints (x,y) doubles in full-resolution pixels, level[]: per-point pyramid level;

@@ -50,7 +50,6 @@ namespace mrgingham
                                                          bool debug = false,
                                                          const char* debug_image_filename = NULL)
     {
-        (void)debug; (void)debug_image_filename;
         int cap = 4096;
         std::vector<int> xy((size_t)2 * cap);
         int n = mrg_b200_find_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
@@ -65,6 +64,9 @@ namespace mrgingham
         // the failure is thrown (the reference's bool cannot carry it).
         if (n < 0) throw std::runtime_error("mrgingham_b200: the GPU corner detector failed (see stderr)");
         for (int i = 0; i < n; i++) points_scaled_out->push_back(PointInt(xy[2*i], xy[2*i + 1]));
+        if (debug)      // the reference's /tmp dumps (find_chessboard_corners.cc:294-315, 452-459, 513-541)
+            mrg_b200_debug_dump_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
+                                        image_pyramid_level, debug_image_filename, NULL, NULL, 0);
         return points_scaled_out->size() > 0;
     }
 
@@ -76,13 +78,15 @@ namespace mrgingham
                                                           bool debug = false,
                                                           const char* debug_image_filename = NULL)
     {
-        (void)debug; (void)debug_image_filename;
         static_assert(sizeof(PointDouble) == 2 * sizeof(double), "PointDouble must be 2 doubles");
         if (points->empty()) return 0;
         const int n = mrg_b200_refine_chessboard_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
                                                          image_pyramid_level, &(*points)[0].x, level, (int)points->size());
         // callers stop refining on "<= 0 points refined" (mrgingham.cc:96): a GPU failure must not pass for that
         if (n < 0) throw std::runtime_error("mrgingham_b200: the GPU corner refinement failed (see stderr)");
+        if (debug)      // the reference's /tmp dumps of a refinement pass (find_chessboard_corners.cc:300-305, 391-392, 513-541)
+            mrg_b200_debug_dump_corners(image_input.data, image_input.rows, image_input.cols, (int)image_input.step,
+                                        image_pyramid_level, debug_image_filename, &(*points)[0].x, level, (int)points->size());
         return n;
     }
 

@@ -21,7 +21,7 @@ EXPORTS = (
     "mrg_b200_find_chessboard_corners", "mrg_b200_refine_chessboard_corners",
     "mrg_b200_detector_create", "mrg_b200_detector_destroy",
     "mrg_b200_find_corners_batch", "mrg_b200_find_corners_batch_enqueue", "mrg_b200_find_corners_batch_collect",
-    "mrg_b200_find_corners_mixed_batch",
+    "mrg_b200_find_corners_mixed_batch", "mrg_b200_debug_dump_corners",
     "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch", "mrg_b200_box_blur_batch",
     "mrg_b200_preprocess_batch", "mrg_b200_preprocess16_batch",
     "find_chessboard_from_image_array_C", "mrg_b200_find_grid_from_points", "mrg_b200_voronoi_neighbours",

@@ -155,6 +155,7 @@ struct mrg_b200_detector
     std::mutex   boards_mtx;
     DeviceBuffer boards_frames, boards_gather;
     mrg_b200_detector* boards_helper = nullptr;   // second detector of the board finder (find_boards): chunks alternate between the two
+    DeviceBuffer dbg_xyd;                      // mrg_b200_debug_dump_corners(): the corners as doubles
     DeviceBuffer mixed_stage, mixed_srcs;     // mrg_b200_find_corners_mixed_batch(): one size group, contiguous; its sources
 
     struct Pending
@@ -529,7 +530,7 @@ API void mrg_b200_detector_destroy(mrg_b200_detector* det)
         for (cudaEvent_t e : { S.staged, S.k1done, S.k2done }) if (e) cudaEventDestroy(e);
     }
     for (DeviceBuffer* b : { &det->big_cand, &det->big_table, &det->big_dfs, &det->big_records, &det->pts, &det->lvls, &det->boards_frames,
-                             &det->boards_gather, &det->mixed_stage, &det->mixed_srcs }) b->release();
+                             &det->boards_gather, &det->mixed_stage, &det->mixed_srcs, &det->dbg_xyd }) b->release();
     if (det->ev_fork) cudaEventDestroy(det->ev_fork);
     if (det->aux_stream) cudaStreamDestroy(det->aux_stream);
     if (det->copy_stream) cudaStreamDestroy(det->copy_stream);
@@ -1114,11 +1115,91 @@ API int mrg_b200_find_blobs(const uint8_t* image, int Nrows, int Ncols, int stri
     return n;
 }
 
+// The corners of one image as un-quantised doubles (what the reference's debug dump prints): the clustering kernel
+// writes them beside the integers when asked to. Returns the count, -1 on failure, -2 if the frame needs the
+// large-list path (the dump is then skipped).
+static int corners_one_dbl(mrg_b200_detector* det, const uint8_t* image, int rows, int cols, int stride, int level, std::vector<double>* xyd)
+{
+    std::lock_guard<std::mutex> g(det->mtx);
+    if (det->pending.active) return -1;
+    DEVICE_GUARD(det);
+    cudaStream_t stream = det->own_stream;
+    mrg_b200_detector::Slot& S = det->slot[0];
+    const int mp = 1 << 14;
+    FrameSet fs;
+    if (stage_frames(det, S, image, 0, 1, rows, cols, (size_t)stride, (size_t)stride * rows, level, stream, stream, &fs, true)) return -1;
+    if (ensure_chunk_scratch(det, S, 1, mp)) return -1;
+    if (det->dbg_xyd.ensure(sizeof(double) * 2 * mp)) return -1;
+    const int cap = det->cfg.candidate_capacity;
+    CUDA_TRY(cudaMemsetAsync(S.counts.p, 0, sizeof(uint32_t), stream));
+    if (chess_sparse(det, fs, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, cap, stream)) return -1;
+    ClusterParams p; p.smem_cands = kClusterSmemCands; p.level = level; p.cand_capacity = cap; p.max_points = mp; p.record_capacity = 2 * mp; p.records = S.records.p;
+    CUDA_TRY(launch_cluster_find(fs, p, (cand_t*)S.cand.p, (uint32_t*)S.counts.p, (uint32_t*)S.table.p, (uint32_t*)S.dfs.p,
+                                 (int32_t*)S.xy.p, (double*)det->dbg_xyd.p, (int32_t*)S.outcounts.p, stream));
+    int32_t n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, S.outcounts.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (n < 0 || n > mp) return -2;
+    xyd->resize((size_t)2 * n);
+    if (n) CUDA_TRY(cudaMemcpy(xyd->data(), det->dbg_xyd.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+// The reference's --debug artefacts of one corner-detector call (debug_dump.cu lists the files).
+// refined_xy == NULL: the find branch (the corners are computed here once more, as doubles); otherwise the refinement
+// branch: the points whose level is image_pyramid_level after the call are the ones that were refined.
+API int mrg_b200_debug_dump_corners(const uint8_t* image, int Nrows, int Ncols, int stride, int image_pyramid_level,
+                                    const char* debug_image_filename,
+                                    const double* refined_xy, const signed char* refined_levels, int Npoints)
+{
+    const int level = image_pyramid_level;
+    if (level < 0 || level > 10 || Nrows <= 0 || Ncols <= 0 || stride < Ncols) return -1;
+    DefaultLease L;
+    if (!L.det) return -1;
+    const bool refinement = refined_xy != nullptr;
+    char filename[256];
+    // the level image
+    int lh = 0, lw = 0;
+    std::vector<uint8_t> limg((size_t)Nrows * Ncols);
+    if (mrg_b200_pyramid_level(L.det, image, Nrows, Ncols, (size_t)stride, level, limg.data(), &lh, &lw)) return -1;
+    snprintf(filename, sizeof(filename), "/tmp/mrgingham-scaled-processed-level%d.png", level);
+    if (write_png_gray8(filename, limg.data(), lw, lh, (size_t)lw)) fprintf(stderr, "Wrote scaled,processed image to %s\n", filename);
+    // the response, as the reference holds it: zeros where ChESS writes nothing
+    std::vector<int16_t> resp((size_t)lw * lh, 0);
+    if (lw > 2 * kMargin && lh > 2 * kMargin &&
+        mrg_b200_chess_response_batch(L.det, limg.data(), 0, 1, lh, lw, (size_t)lw, (size_t)lw * lh, resp.data(), 0, nullptr)) return -1;
+    std::vector<uint8_t> out8(resp.size());
+    normalize_response_u8(resp.data(), resp.size(), out8.data());
+    snprintf(filename, sizeof(filename), "/tmp/mrgingham-chess-response%s-level%d.png", refinement ? "-refinement" : "", level);
+    if (write_png_gray8(filename, out8.data(), lw, lh, (size_t)lw)) fprintf(stderr, "Wrote a normalized ChESS response to %s\n", filename);
+    for (auto& v : resp) if (v < 0) v = 0;
+    normalize_response_u8(resp.data(), resp.size(), out8.data());
+    snprintf(filename, sizeof(filename), "/tmp/mrgingham-chess-response%s-level%d-positive.png", refinement ? "-refinement" : "", level);
+    if (write_png_gray8(filename, out8.data(), lw, lh, (size_t)lw)) fprintf(stderr, "Wrote positive-only, normalized ChESS response to %s\n", filename);
+    // the corners
+    std::vector<double> xyd;
+    if (!refinement)
+    {
+        const int n = corners_one_dbl(L.det, image, Nrows, Ncols, stride, level, &xyd);
+        if (n == -2) { MSG("Too many candidates for the debug corner dump; skipping it."); return 0; }
+        if (n < 0) return -1;
+        snprintf(filename, sizeof(filename), "/tmp/mrgingham-1-corners.vnl");
+    }
+    else
+    {
+        for (int i = 0; i < Npoints; i++)
+            if (refined_levels[i] == level) { xyd.push_back(refined_xy[2*i]); xyd.push_back(refined_xy[2*i + 1]); }
+        snprintf(filename, sizeof(filename), "/tmp/mrgingham-1-corners-refinement-level%d.vnl", level);
+    }
+    fprintf(stderr, "Writing self-plotting corner dump to %s\n", filename);
+    if (!write_corner_vnl(filename, debug_image_filename, xyd.data(), (int)(xyd.size() / 2))) return -1;
+    return 0;
+}
+
 API bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols, int stride, char* imagebuffer,
                                                     int image_pyramid_level, bool doblobs, bool debug,
                                                     bool (*add_points)(int* xy, int N, double scale, void* cookie), void* cookie)
 {
-    (void)debug; // the reference's debug mode only writes /tmp dumps
     // mrgingham_pywrap_cplusplus_bridge.cc:50-56: blobs only at level 0, via find_blobs_from_image_array()
     if (doblobs && image_pyramid_level != 0) return false;
     int cap = 4096;
@@ -1139,6 +1220,8 @@ API bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols, int st
         (*add_points)(xy.data(), 0, 1.0 / kFindGridScale, cookie);
         return false;
     }
+    if (debug && !doblobs && n >= 0)
+        mrg_b200_debug_dump_corners((const uint8_t*)imagebuffer, Nrows, Ncols, stride, image_pyramid_level, nullptr, nullptr, nullptr, 0);
     if (n == 0) return false;
     return (*add_points)(xy.data(), n, 1.0 / kFindGridScale, cookie);
 }

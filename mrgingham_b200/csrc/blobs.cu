@@ -604,6 +604,7 @@ blob_contour_warp_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const 
         if (lane == 0) need = centre_and_colour(r, g, planes);
         need = __shfl_sync(kFull, need, 0);
         if (!need) continue;
+        __syncwarp();                            // (the previous border's readers of the warp's slice are done)
         for (int i = lane; i < bw; i += 32) { S.ylo[i] = INT_MAX; S.yhi[i] = INT_MIN; }
         __syncwarp();
         for (int i = lane; i < n; i += 32)

@@ -55,7 +55,10 @@ __device__ __forceinline__ int table_lookup(const cand_t* cand, const uint32_t* 
     {
         const uint32_t i = table[slot];
         if (i == kEmpty) return -1;
-        if (cand_key(cand[i]) == key) return (int)i;
+        // (only the key's bytes are read: in the refinement kernel other threads clear the RESPONSE bytes of candidates
+        // of their own regions while this probe passes over them)
+        const uint16_t* hw = reinterpret_cast<const uint16_t*>(&cand[i]);
+        if (((uint32_t)hw[1] | ((uint32_t)hw[2] << 16)) == key) return (int)i;
         slot = (slot + 1) & mask;
     }
 }
@@ -139,7 +142,7 @@ __device__ void grow_component_flat(Component& c, cand_t* cand, const uint32_t* 
             const cand_t cc = cand[cur];
             const int r = cand_r(cc);
             const bool member = r != 0 && r > (c.peak >> 4);   // alive => r > 15 already
-            if (r != 0) cand[cur] = cc & ~0xFFFFull;           // member or not, it is zeroed
+            if (r != 0) *reinterpret_cast<uint16_t*>(&cand[cur]) = 0;   // member or not, it is zeroed (the response bytes only)
             if (member)
             {
                 const int x = cand_x(cc), y = cand_y(cc);

@@ -137,6 +137,11 @@ int blob_finish(BlobWorkspace* ws, int32_t* xy_out, int32_t* counts_out, int max
 int blob_find_frames(BlobWorkspace* ws, const FrameSet& fs, int32_t* xy_out, int32_t* counts_out, int max_points,
                      cudaStream_t stream, float* ms_out);
 
+// debug_dump.cu: the reference's --debug artefacts (host code)
+bool write_png_gray8(const char* path, const uint8_t* data, int w, int h, size_t pitch);
+void normalize_response_u8(const int16_t* resp, size_t n, uint8_t* out);
+bool write_corner_vnl(const char* path, const char* debug_image_filename, const double* xy, int n);
+
 // largest shared-memory candidate capacity of the clustering kernel (ClusterParams::smem_cands)
 constexpr int kClusterSmemCands = 4096;
 }

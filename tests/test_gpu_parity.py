@@ -443,7 +443,7 @@ def test_camera_like_4k_frames(api, oracle):
             want = oracle.find_corners(img, level)
             got = api.find_chessboard_corners_int(img, level)
             assert np.array_equal(got, want), (seed, sigma, level, len(got), len(want))
-        xy2 = oracle.find_corners(img, 2, want_double=True)
+        _, xy2 = oracle.find_corners(img, 2, want_double=True)
         if len(xy2):
             lv = np.full(len(xy2), 2, dtype=np.int8)
             n_o, xy_o, lv_o = oracle.refine_corners(img, 1, xy2, lv)

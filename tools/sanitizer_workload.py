@@ -36,3 +36,20 @@ for img in (frames[0], synth.board_frame(403, 351, 10, seed=5), synth.noise_fram
 found, bxy, blv = det.find_boards(frames, gridn=10, level=-1)
 assert found[0] >= 0 and found[1] < 0
 print("preproc + boards ok", found)
+# round 2: 16-bit input, mixed-size batch (gather kernel), parallel refinement, the segment-based blob path on a frame
+# with cut rows / columns (> 256 pixels each way), noise (queue regrowth)
+rng = np.random.default_rng(7)
+img16 = np.clip(synth.board_frame(403, 351, 10, seed=8).astype(np.float64) * 200 + rng.normal(0, 100, size=(351, 403)) + 900, 0, 65535).astype(np.uint16)
+for cl in (False, True):
+    assert np.array_equal(det.preprocess16(img16[None], clahe=cl, blur_radius=0)[0], po.chain16(img16, cl))
+mixed = [frames[0], synth.board_frame(403, 351, 10, seed=9), frames[1], synth.noise_frame(131, 77, seed=10)]
+mxy, mc = det.find_corners_mixed(mixed, 0)
+for i, im in enumerate(mixed):
+    w = po.find_corners(im, 0); assert mc[i] == len(w) and np.array_equal(mxy[i, :mc[i]], w[:1 << 14])
+_, xy2 = po.find_corners(frames[0], 1, want_double=True); lv = np.full(len(xy2), 1, dtype=np.int8)
+n_o, xy_o, lv_o = po.refine_corners(frames[0], 0, xy2, lv)
+n_g, xy_g, lv_g = api.refine_chessboard_corners(frames[0], 0, xy2, lv)
+assert n_g == n_o and np.array_equal(xy_g, xy_o) and np.array_equal(lv_g, lv_o)
+for im in (synth.circle_grid_frame(1280, 720, 10, seed=11), synth.blob_frame(640, 600, seed=12), synth.noise_frame(300, 280, seed=13)):
+    assert np.array_equal(api.find_blobs_int(im), po.find_blobs(im))
+print("round-2 paths ok", mc, n_g)
