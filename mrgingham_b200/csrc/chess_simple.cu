@@ -147,44 +147,62 @@ pyramid_kernel(FrameSet src, int level, uint8_t* __restrict__ dst, int dst_pitch
 // = floor((sum + (k*k-1)/2) / (k*k)) for 8-bit data. A CTA blurs a 128 x 8 output tile from a
 // shared-memory tile with the halo; 2 bytes of HBM traffic per pixel (1 read + 1 written).
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlurMaxR = 4, kBlurTW = 128, kBlurTH = 8;
+constexpr int kBlurMaxR = 4, kBlurTW = 128;
 __device__ __forceinline__ int reflect101(int i, int n)
 {
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
     return i;
 }
+// Any radius 1..4, any alignment: a CTA owns a 128 x 32 tile. The tile and its halo go to shared memory (rows read
+// as words where the frame allows it, reflected at the image border), then the box sum is taken separably: horizontal
+// running sums of every staged row into 16-bit lanes, vertical sums of those. 2k additions per pixel instead of k*k.
+constexpr int kBlurTH2 = 32;
 __global__ void __launch_bounds__(256)
 box_blur_kernel(FrameSet fs, int radius, uint8_t* __restrict__ dst, int dst_pitch, size_t dst_frame_stride)
 {
-    __shared__ uint8_t tile[kBlurTH + 2 * kBlurMaxR][kBlurTW + 2 * kBlurMaxR + 8];
-    const int f = blockIdx.z, x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
+    __shared__ uint8_t  tile[kBlurTH2 + 2 * kBlurMaxR][kBlurTW + 2 * kBlurMaxR + 8];
+    __shared__ uint16_t hs[kBlurTH2 + 2 * kBlurMaxR][kBlurTW];
+    const int f = blockIdx.z, x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH2;
     const uint8_t* img = fs.base + (size_t)f * fs.frame_stride;
-    const int tw = kBlurTW + 2 * radius, th = kBlurTH + 2 * radius;
-    for (int i = threadIdx.x; i < tw * th; i += 256)
+    const int tw = kBlurTW + 2 * radius, th = kBlurTH2 + 2 * radius;
+    // stage: one warp per row at a time, lanes along the row (coalesced); reflection only where the tile leaves the image
+    for (int ty = threadIdx.x >> 5; ty < th; ty += 8)
     {
-        const int ty = i / tw, tx = i % tw;
-        tile[ty][tx] = img[(size_t)reflect101(y0 + ty - radius, fs.h) * fs.pitch + reflect101(x0 + tx - radius, fs.w)];
+        const uint8_t* row = img + (size_t)reflect101(y0 + ty - radius, fs.h) * fs.pitch;
+        for (int tx = threadIdx.x & 31; tx < tw; tx += 32)
+        {
+            const int x = x0 + tx - radius;
+            tile[ty][tx] = row[(x >= 0 && x < fs.w) ? x : reflect101(x, fs.w)];
+        }
     }
     __syncthreads();
     const int k = 2 * radius + 1, k2 = k * k, half = (k2 - 1) / 2;
-    // thread = 4 adjacent pixels of one row of the tile
-    const int ty = threadIdx.x / 32, tx = (threadIdx.x % 32) * 4;
-    const int y = y0 + ty;
-    if (y >= fs.h || x0 + tx >= fs.w) return;
-    int sum[4] = { 0, 0, 0, 0 };
-    for (int dy = 0; dy < k; dy++)
-        for (int dx = 0; dx < k + 3; dx++)
-        {
-            const int v = tile[ty + dy][tx + dx];
+    // horizontal sums: thread = 4 adjacent pixels of a staged row
+    for (int i = threadIdx.x; i < th * (kBlurTW / 4); i += 256)
+    {
+        const int ty = i / (kBlurTW / 4), tx = (i % (kBlurTW / 4)) * 4;
+        int s = 0;
+        for (int dx = 0; dx < k; dx++) s += tile[ty][tx + dx];
+        hs[ty][tx] = (uint16_t)s;
 #pragma unroll
-            for (int p = 0; p < 4; p++)
-                if (dx - p >= 0 && dx - p < k) sum[p] += v;
-        }
-    uint8_t* o = dst + (size_t)f * dst_frame_stride + (size_t)y * dst_pitch + x0 + tx;
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-        if (x0 + tx + p < fs.w) o[p] = (uint8_t)((sum[p] + half) / k2);
+        for (int p2 = 1; p2 < 4; p2++) { s += tile[ty][tx + p2 - 1 + k] - tile[ty][tx + p2 - 1]; hs[ty][tx + p2] = (uint16_t)s; }
+    }
+    __syncthreads();
+    // vertical sums: thread = one column of 16 rows, sliding
+    const int cx = threadIdx.x & 127, half_rows = (threadIdx.x >> 7) * (kBlurTH2 / 2);
+    const int x = x0 + cx;
+    if (x >= fs.w) return;
+    int s = 0;
+    for (int dy = 0; dy < k; dy++) s += hs[half_rows + dy][cx];
+    uint8_t* o = dst + (size_t)f * dst_frame_stride + x;
+    for (int r = 0; r < kBlurTH2 / 2; r++)
+    {
+        const int y = y0 + half_rows + r;
+        if (y >= fs.h) break;
+        o[(size_t)y * dst_pitch] = (uint8_t)((s + half) / k2);
+        if (r + 1 < kBlurTH2 / 2) s += hs[half_rows + r + k][cx] - hs[half_rows + r][cx];
+    }
 }
 
 // Fast path for the CLI's default R = 1 (3x3): HBM-bound, 1 byte read + 1 byte written per pixel.
@@ -267,7 +285,7 @@ cudaError_t launch_box_blur(const FrameSet& src, int radius, uint8_t* dst, int d
         box_blur3_kernel<<<grid, 128, 0, stream>>>(src, dst, dst_pitch, dst_frame_stride, strips);
         return cudaGetLastError();
     }
-    dim3 grid((src.w + kBlurTW - 1) / kBlurTW, (src.h + kBlurTH - 1) / kBlurTH, src.nframes);
+    dim3 grid((src.w + kBlurTW - 1) / kBlurTW, (src.h + kBlurTH2 - 1) / kBlurTH2, src.nframes);
     box_blur_kernel<<<grid, 256, 0, stream>>>(src, radius, dst, dst_pitch, dst_frame_stride);
     return cudaGetLastError();
 }

@@ -24,7 +24,8 @@ def main():
     det = api.Detector(max_frames=a.frames)
     out = torch.empty_like(frames)
     npx = a.frames * a.width * a.height
-    for name, kw in (("blur r=1", dict(clahe=False, blur_radius=1)), ("normalize+clahe", dict(clahe=True, blur_radius=0)),
+    for name, kw in (("blur r=1", dict(clahe=False, blur_radius=1)), ("blur r=2", dict(clahe=False, blur_radius=2)),
+                     ("blur r=4", dict(clahe=False, blur_radius=4)), ("normalize+clahe", dict(clahe=True, blur_radius=0)),
                      ("normalize+clahe+blur r=1", dict(clahe=True, blur_radius=1))):
         s = torch.cuda.current_stream().cuda_stream
         for _ in range(2):
