@@ -136,3 +136,15 @@ def test_blobs_random_frames_match_oracle(api, oracle):
             img = synth.board_frame(max(w, 200), max(h, 160), int(rng.integers(4, 9)), seed=2000 + t)
         img = np.ascontiguousarray(img)
         assert np.array_equal(api.find_blobs_int(img), oracle.find_blobs(img)), (t, kind, img.shape)
+
+
+def test_blobs_wide_and_tall_frames(api, oracle):
+    """coordinates beyond 4096 in x and in y (state keys, queue entries, cut rows / columns far from the origin)"""
+    po = oracle
+    rng = np.random.default_rng(21)
+    wide = synth.blob_frame(7700, 300, seed=41, nblobs=400)
+    tall = np.ascontiguousarray(synth.blob_frame(5100, 260, seed=42, nblobs=300).T)
+    ring = np.full((700, 9000), 200, dtype=np.uint8); ring[40:660, 30:8970] = 60; ring[80:620, 70:8930] = 200      # a border 18 000 states long
+    ring = np.clip(ring.astype(np.int16) + rng.integers(-3, 4, size=ring.shape), 0, 255).astype(np.uint8)
+    for img in (wide, tall, ring):
+        assert np.array_equal(api.find_blobs_int(img), po.find_blobs(img)), img.shape
