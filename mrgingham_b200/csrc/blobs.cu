@@ -253,13 +253,20 @@ blob_scan_kernel(BlobGeom g, const uint32_t* __restrict__ planes, unsigned long 
 struct BlobSegment
 {
     unsigned long long start, end;               // blobwalk::state_key of its first state / of the next segment's
-    long long a00;                               // sum over its edges of (Px*Qy - Qx*Py)
+    long long a00, a10, a01;                     // sums over its edges P->Q of d = Px*Qy - Qx*Py, d*(Px+Qx), d*(Py+Qy)
     int n;                                       // its states
-    int min_disc;                                // smallest discovery position of its states (INT_MAX: none)
-    int cand_pos;                                // if its first state is a candidate start: its discovery position, else -1
-    unsigned next;                               // the segment that starts where this one ends (blob_link_kernel)
-    unsigned prev, pad;                          // the segment that ends where this one starts
+    int pad;
 };
+// What the chains look at first lives in four plain arrays of queue_cap words each (one 4-byte load per hop for the many
+// candidates that are dropped after a hop or two, instead of a 48-byte record): smallest discovery position of the
+// segment's states (INT_MAX: none); the discovery position of its first state if that is a candidate start, else -1;
+// the segment that starts where it ends; the segment that ends where it starts (blob_link_kernel).
+struct SegMeta { int* min_disc; int* cand_pos; unsigned* next; unsigned* prev; };
+__host__ __device__ inline SegMeta seg_meta(void* base, unsigned cap)
+{
+    SegMeta m; m.min_disc = (int*)base; m.cand_pos = m.min_disc + cap; m.next = (unsigned*)(m.cand_pos + cap); m.prev = m.next + cap;
+    return m;
+}
 constexpr unsigned long long kNoKey = ~0ull;
 __device__ __forceinline__ unsigned hash_of(unsigned long long key, unsigned mask)
 {
@@ -271,7 +278,7 @@ __device__ __forceinline__ unsigned hash_of(unsigned long long key, unsigned mas
 __global__ void __launch_bounds__(128)
 blob_segment_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsigned long long* __restrict__ queue,
                     unsigned long long* __restrict__ hkeys, unsigned* __restrict__ hvals, BlobSegment* __restrict__ segs,
-                    unsigned* __restrict__ counters)
+                    void* __restrict__ meta_base, unsigned* __restrict__ counters)
 {
     const int lane = threadIdx.x & 31;
     const unsigned qn_all = counters[kCntQueue];
@@ -285,7 +292,7 @@ blob_segment_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsig
     int x = 0, y = 0, k = 0, n = 0, min_disc = 0, cand_pos = -1;
     unsigned seg = 0, myslot = 0; unsigned long long skey = 0;
     bool fresh = false;
-    long long a00 = 0;
+    long long a00 = 0, a10 = 0, a01 = 0;
     for (;;)
     {
         const unsigned idle = __ballot_sync(kFull, !active);
@@ -324,7 +331,7 @@ blob_segment_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsig
                         int disc; bool st;
                         classify_state(P, F, x, y, k, &disc, &st, &cand_pos);
                         min_disc = disc < 0 ? INT_MAX : disc;
-                        n = 0; a00 = 0; active = true; fresh = true;
+                        n = 0; a00 = a10 = a01 = 0; active = true; fresh = true;
                     }
                 }
             }
@@ -347,14 +354,16 @@ blob_segment_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsig
                 const int px = x, py = y;
                 int disc; bool st;
                 step_fwd_ex(P, F, x, y, k, &disc, &st);
-                a00 += (long long)(px * y - x * py); n++;
+                { const long long d = (long long)(px * y - x * py); a00 += d; a10 += d * (px + x); a01 += d * (py + y); }
+                n++;
                 if (st || n > max_steps)
                 {
                     if (!st) atomicExch(&counters[kCntStatus], 2u);         // cannot happen
                     BlobSegment s;
-                    s.start = skey; s.end = state_key((int)(skey >> 33), x, y, k); s.a00 = a00; s.n = n; s.min_disc = min_disc;
-                    s.cand_pos = cand_pos; s.next = s.prev = 0xFFFFFFFFu; s.pad = 0;
+                    s.start = skey; s.end = state_key((int)(skey >> 33), x, y, k); s.a00 = a00; s.a10 = a10; s.a01 = a01; s.n = n; s.pad = 0;
                     segs[seg] = s;
+                    const SegMeta M = seg_meta(meta_base, g.queue_cap);
+                    M.min_disc[seg] = min_disc; M.cand_pos[seg] = cand_pos;
                     active = false;
                 }
                 else if (disc >= 0 && disc < min_disc) min_disc = disc;
@@ -366,7 +375,7 @@ blob_segment_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const unsig
 // B2c: segments find their neighbours: one hash look-up each, after which the chains are followed by index
 __global__ void __launch_bounds__(256)
 blob_link_kernel(BlobGeom g, const unsigned long long* __restrict__ hkeys, const unsigned* __restrict__ hvals,
-                 BlobSegment* __restrict__ segs, unsigned* __restrict__ counters)
+                 const BlobSegment* __restrict__ segs, void* __restrict__ meta_base, unsigned* __restrict__ counters)
 {
     if (counters[kCntStatus]) return;
     const unsigned nseg = counters[kCntSegs];
@@ -382,8 +391,9 @@ blob_link_kernel(BlobGeom g, const unsigned long long* __restrict__ hkeys, const
         }
         if (!found) { atomicExch(&counters[kCntStatus], 2u); continue; }                 // cannot happen: every segment ends at a segment start
         const unsigned j = hvals[slot];
-        segs[i].next = j;
-        segs[j].prev = i;
+        const SegMeta M = seg_meta(meta_base, g.queue_cap);
+        M.next[i] = j;
+        M.prev[j] = i;
     }
 }
 
@@ -393,39 +403,56 @@ blob_link_kernel(BlobGeom g, const unsigned long long* __restrict__ hkeys, const
 // candidate is where the scan discovers the border, whose length and area are then known -- a record is emitted if
 // the area passes the filter.
 __global__ void __launch_bounds__(128)
-blob_chain_kernel(BlobGeom g, const BlobSegment* __restrict__ segs, BlobRecord* __restrict__ recs, unsigned* __restrict__ counters)
+blob_chain_kernel(BlobGeom g, const uint32_t* __restrict__ planes, const BlobSegment* __restrict__ segs, void* __restrict__ meta_base,
+                  BlobRecord* __restrict__ recs, unsigned* __restrict__ counters)
 {
     if (counters[kCntStatus]) return;
     const unsigned nseg = counters[kCntSegs];
+    const SegMeta M = seg_meta(meta_base, g.queue_cap);
     for (unsigned c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < nseg; c0 += gridDim.x * blockDim.x)
     {
-        const int pos = segs[c0].cand_pos;
+        const int pos = M.cand_pos[c0];
         if (pos < 0) continue;                   // (a cut state: not where any border can be discovered)
+        if (M.min_disc[c0] < pos) continue;
         const BlobSegment c = segs[c0];
-        if (c.min_disc < pos) continue;
-        long long a00 = c.a00, n = c.n;
+        long long a00 = c.a00, a10 = c.a10, a01 = c.a01, n = c.n;
         unsigned f = c0, b = c0;                 // covered so far: the segments from b forward to f (through c0)
         bool keep = true;
         for (unsigned hops = 0; ; hops++)
         {
             if (hops > g.queue_cap) { atomicExch(&counters[kCntStatus], 2u); keep = false; break; }    // cannot happen
-            const unsigned fn = segs[f].next;
+            const unsigned fn = M.next[f];
             if (fn == b) break;
-            { const BlobSegment& s = segs[fn]; if (s.min_disc < pos) { keep = false; break; } a00 += s.a00; n += s.n; }
+            if (M.min_disc[fn] < pos) { keep = false; break; }
+            { const BlobSegment& s = segs[fn]; a00 += s.a00; a10 += s.a10; a01 += s.a01; n += s.n; }
             f = fn;
-            const unsigned bp = segs[b].prev;
+            const unsigned bp = M.prev[b];
             if (bp == f) break;
-            { const BlobSegment& s = segs[bp]; if (s.min_disc < pos) { keep = false; break; } a00 += s.a00; n += s.n; }
+            if (M.min_disc[bp] < pos) { keep = false; break; }
+            { const BlobSegment& s = segs[bp]; a00 += s.a00; a10 += s.a10; a01 += s.a01; n += s.n; }
             b = bp;
         }
         if (!keep) continue;
         // filterByArea: m00 = |a00| / 2 in [20, 80000) -- exact in integers. Everything else is dropped here.
         const long long aa = a00 < 0 ? -a00 : a00;
         if (aa < 40 || aa >= 160000) continue;
+        const int job = (int)(c.start >> 33);
+        {
+            // filterByColor already here (the centre needs only the first-order sums, which the segments carry): a border
+            // whose centre pixel is foreground is rejected whatever else is true of it -- on board frames that is half
+            // of the borders the area filter keeps (the white regions) -- so its points are never stored
+            const double sgn = a00 > 0 ? 1.0 : -1.0;
+            const double m00 = __dmul_rn((double)a00, sgn * 0.5);
+            const double m10 = __dmul_rn((double)a10, sgn * 0.16666666666666666666666666666667);
+            const double m01 = __dmul_rn((double)a01, sgn * 0.16666666666666666666666666666667);
+            const int rx = __double2int_rn(__ddiv_rn(m10, m00)), ry = __double2int_rn(__ddiv_rn(m01, m00));
+            if (rx < 0 || rx >= g.w || ry < 0 || ry >= g.h) continue;
+            const uint32_t* B = plane_ptr(g, planes, job);
+            if ((B[ry * g.wpr + (rx >> 5)] >> (rx & 31)) & 1u) continue;
+        }
         const unsigned idx = atomicAdd(&counters[kCntRecords], 1u);
         const unsigned off = atomicAdd(&counters[kCntPoints], (unsigned)n);
         if (idx >= g.rec_cap || off > g.pts_cap || (unsigned long long)n > g.pts_cap - off) { atomicExch(&counters[kCntStatus], 1u); continue; }
-        const int job = (int)(c.start >> 33);
         BlobRecord r;
         r.frame = job / kNThr; r.thr = job % kNThr; r.seq = pos; r.n = (int)n; r.pts_off = off;
         r.sx = (int)((c.start >> 3) & 0x7FFFu); r.sy = (int)((c.start >> 18) & 0x7FFFu); r.sk = (int)(c.start & 7u);
@@ -857,8 +884,8 @@ struct BlobWorkspace
 {
     void* planes = nullptr; void* pts = nullptr; void* recs = nullptr;
     void* scratch = nullptr; void* counters = nullptr; void* queue = nullptr;
-    void* hkeys = nullptr; void* hvals = nullptr; void* segs = nullptr;
-    size_t planes_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0, queue_b = 0, hkeys_b = 0, hvals_b = 0, segs_b = 0;
+    void* hkeys = nullptr; void* hvals = nullptr; void* segs = nullptr; void* segmeta = nullptr;
+    size_t planes_b = 0, pts_b = 0, recs_b = 0, scratch_b = 0, queue_b = 0, hkeys_b = 0, hvals_b = 0, segs_b = 0, segmeta_b = 0;
     unsigned pts_per_frame = 1u << 21, rec_per_job = 512, queue_per_frame = 1u << 17;
     BlobRecord* host_recs = nullptr; size_t host_recs_cap = 0;      // pinned
     unsigned* host_counters = nullptr;                              // pinned
@@ -876,7 +903,7 @@ void blob_workspace_destroy(BlobWorkspace* ws)
     if (!ws) return;
     cudaFree(ws->planes); cudaFree(ws->pts); cudaFree(ws->recs);
     cudaFree(ws->scratch); cudaFree(ws->counters); cudaFree(ws->queue);
-    cudaFree(ws->hkeys); cudaFree(ws->hvals); cudaFree(ws->segs);
+    cudaFree(ws->hkeys); cudaFree(ws->hvals); cudaFree(ws->segs); cudaFree(ws->segmeta);
     if (ws->host_recs) cudaFreeHost(ws->host_recs);
     if (ws->host_counters) cudaFreeHost(ws->host_counters);
     if (ws->e0) cudaEventDestroy(ws->e0);
@@ -943,6 +970,7 @@ int blob_enqueue(BlobWorkspace* ws, const FrameSet& fs, cudaStream_t stream)
     BLOB_TRY(grow(&ws->hkeys, &ws->hkeys_b, (size_t)slots * 8));
     BLOB_TRY(grow(&ws->hvals, &ws->hvals_b, (size_t)slots * 4));
     BLOB_TRY(grow(&ws->segs, &ws->segs_b, (size_t)g.queue_cap * sizeof(BlobSegment)));
+    BLOB_TRY(grow(&ws->segmeta, &ws->segmeta_b, (size_t)g.queue_cap * 16));
     BLOB_TRY(grow(&ws->pts, &ws->pts_b, (size_t)g.pts_cap * 4));
     BLOB_TRY(grow(&ws->recs, &ws->recs_b, (size_t)g.rec_cap * sizeof(BlobRecord)));
     unsigned* counters = (unsigned*)ws->counters;
@@ -953,9 +981,9 @@ int blob_enqueue(BlobWorkspace* ws, const FrameSet& fs, cudaStream_t stream)
     blob_scan_kernel<<<148 * 8, 256, 0, stream>>>(g, (const uint32_t*)ws->planes, (unsigned long long*)ws->queue, counters,
                                                   (unsigned)ntiles64, nstrips, ncb);
     blob_segment_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (const unsigned long long*)ws->queue,
-                                                     (unsigned long long*)ws->hkeys, (unsigned*)ws->hvals, (BlobSegment*)ws->segs, counters);
-    blob_link_kernel<<<148 * 8, 256, 0, stream>>>(g, (const unsigned long long*)ws->hkeys, (const unsigned*)ws->hvals, (BlobSegment*)ws->segs, counters);
-    blob_chain_kernel<<<148 * 8, 128, 0, stream>>>(g, (const BlobSegment*)ws->segs, (BlobRecord*)ws->recs, counters);
+                                                     (unsigned long long*)ws->hkeys, (unsigned*)ws->hvals, (BlobSegment*)ws->segs, ws->segmeta, counters);
+    blob_link_kernel<<<148 * 8, 256, 0, stream>>>(g, (const unsigned long long*)ws->hkeys, (const unsigned*)ws->hvals, (const BlobSegment*)ws->segs, ws->segmeta, counters);
+    blob_chain_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (const BlobSegment*)ws->segs, ws->segmeta, (BlobRecord*)ws->recs, counters);
     blob_points_kernel<<<148 * 8, 128, 0, stream>>>(g, (const uint32_t*)ws->planes, (BlobRecord*)ws->recs, counters, (uint32_t*)ws->pts);
     blob_contour_warp_kernel<<<148 * 2, kW3Warps * 32, kW3Warps * sizeof(WarpScratch), stream>>>(
         g, (const uint32_t*)ws->planes, (const uint32_t*)ws->pts, (BlobRecord*)ws->recs, counters);
