@@ -43,10 +43,23 @@ inline i64 orient(const P2& a, const P2& b, const P2& c)      // > 0: a,b,c coun
 {
     return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
 }
-// sign of the in-circle determinant: > 0 iff d is strictly inside the circle through the ccw triangle a,b,c
+// sign of the in-circle determinant: > 0 iff d is strictly inside the circle through the ccw triangle a,b,c.
+// The differences are exact in double (|coordinate| <= 2^29); the determinant is evaluated in double first and its sign
+// taken when it clears Shewchuk's static error bound for this expression ((10 + 96 eps) eps times the sum of the
+// absolute terms); only the near-cocircular cases -- which a regular grid has plenty of -- pay for 128-bit integers.
 inline int incircle(const P2& a, const P2& b, const P2& c, const P2& d)
 {
     const i64 ax = a.x - d.x, ay = a.y - d.y, bx = b.x - d.x, by = b.y - d.y, cx = c.x - d.x, cy = c.y - d.y;
+    {
+        const double fax = (double)ax, fay = (double)ay, fbx = (double)bx, fby = (double)by, fcx = (double)cx, fcy = (double)cy;
+        const double bxcy = fbx * fcy, cxby = fcx * fby, cxay = fcx * fay, axcy = fax * fcy, axby = fax * fby, bxay = fbx * fay;
+        const double al = fax * fax + fay * fay, bl = fbx * fbx + fby * fby, cl = fcx * fcx + fcy * fcy;
+        const double det = al * (bxcy - cxby) + bl * (cxay - axcy) + cl * (axby - bxay);
+        const double perm = (std::fabs(bxcy) + std::fabs(cxby)) * al + (std::fabs(cxay) + std::fabs(axcy)) * bl + (std::fabs(axby) + std::fabs(bxay)) * cl;
+        const double bound = 1.2e-15 * perm;          // (10 + 96 * 2^-53) * 2^-53 = 1.11e-15
+        if (det > bound) return 1;
+        if (det < -bound) return -1;
+    }
     const i128 a2 = (i128)ax * ax + (i128)ay * ay, b2 = (i128)bx * bx + (i128)by * by, c2 = (i128)cx * cx + (i128)cy * cy;
     const i128 det = a2 * ((i128)bx * cy - (i128)by * cx) - b2 * ((i128)ax * cy - (i128)ay * cx) + c2 * ((i128)ax * by - (i128)ay * bx);
     return det > 0 ? 1 : det < 0 ? -1 : 0;
