@@ -14,6 +14,7 @@
 #include "../../include/mrgingham_b200.h"
 #include "kernels.cuh"
 #include "find_grid.hh"
+#include <chrono>
 
 using namespace mrgb200;
 
@@ -1368,6 +1369,7 @@ int gather_frames(mrg_b200_detector* det, cudaStream_t stream, const uint8_t* d_
     bool consecutive = true;
     for (size_t k = 1; k < idx.size(); k++) consecutive = consecutive && idx[k] == idx[k - 1] + 1;
     if (consecutive) { *base = d_images + (size_t)idx[0] * fstride; *gpitch = pitch; *gfstride = fstride; return 0; }
+    DEVICE_GUARD(det);       // (also called from the board finder's helper threads)
     const size_t p = (size_t)round_up(cols, 16), fs = p * rows;
     if (det->boards_gather.ensure(fs * idx.size())) return -1;
     for (size_t k = 0; k < idx.size(); )
@@ -1381,6 +1383,20 @@ int gather_frames(mrg_b200_detector* det, cudaStream_t stream, const uint8_t* d_
     *base = (const uint8_t*)det->boards_gather.p; *gpitch = p; *gfstride = fs;
     return 0;
 }
+
+// MRG_B200_BOARDS_TRACE=1: wall-clock time of every phase of a chunk on stderr (where a board call's time goes)
+struct PhaseTrace
+{
+    bool on; std::chrono::steady_clock::time_point t;
+    PhaseTrace() : on(getenv("MRG_B200_BOARDS_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char* what, int level, int frames)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "boards: %-14s level %d  %4d frames  %8.3f ms\n", what, level, frames, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 // One chunk of frames already on the device. level < 0: try levels 3,2,1,0 and keep the first that gives a grid
 // (mrgingham.cc:127-138). strict_level0: a level-0 pass needs pitch == cols, as the reference's corner finder does.
@@ -1396,6 +1412,7 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
     const uint8_t* base; size_t gp, gfs;
     int mp = std::max(det->cfg.max_points, npts);      // output capacity of the corner passes below; grows here, never in det->cfg
     const int first_level = level < 0 ? 3 : level, last_level = level < 0 ? 0 : level;
+    PhaseTrace trace;
     for (int L = first_level; L >= last_level; L--)
     {
         todo.clear();
@@ -1417,12 +1434,14 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
             if (most <= mp) break;
             mp = next_pow2(most);     // more points than room was made for: look again (a capacity private to this call)
         }
+        trace.mark("corners", L, cnt);
         parallel_for(cnt, [&](int k)
         {
             const int i = todo[k];
             if (find_grid_from_points(xy.data() + (size_t)2 * mp * k, counts[k], gridn, xy_out + (size_t)2 * npts * i))
                 found_out[i] = L;
         });
+        trace.mark("grid search", L, cnt);
     }
     if (!refine || doblobs) return 0;
 
@@ -1457,8 +1476,184 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
             memcpy(levels_out + (size_t)npts * todo[k], &tlv[(size_t)npts * k], npts);
             if (nref[k] <= 0) stopped[todo[k]] = 1;
         }
+        trace.mark("refine", L, cnt);
     }
     return 0;
+}
+
+// The same, for chunks of many frames, as a pipeline over two detectors (their streams and scratch): `det` runs the corner
+// passes, `helper` the refinement passes, this thread's pool the grid searches.
+//   * A pass covers ALL frames of the chunk, in place, whenever the frames it is needed for are a fair share of them:
+//     gathering a scattered subset costs more than the pyramid + ChESS + clustering of the frames nobody asked about
+//     (a level-L image is 4^-L of a frame; the gather copies whole frames). Results of frames that already have a grid
+//     are ignored; their points carry level 0 in a refinement pass, which then leaves them alone.
+//   * So the corner pass of level L-1 does not depend on the grid search of level L: it is enqueued before that search
+//     starts and runs beside it (level 0, a full-resolution pass, only when some frame really needs it).
+//   * Refinement at level L needs the searches of the levels above L and the refinement at L+1: it runs on the helper,
+//     on its own host thread, beside the search of level L.
+// Results are those of find_boards_chunk() (same passes over the same pixels, frame by frame).
+int find_boards_chunk_pipelined(mrg_b200_detector* det, mrg_b200_detector* helper, const uint8_t* d_images, int n, int rows, int cols,
+                                size_t pitch, size_t fstride, int gridn, int level, bool strict_level0,
+                                double* xy_out, signed char* levels_out, int32_t* found_out)
+{
+    const int npts = gridn * gridn;
+    cudaStream_t stream = det->own_stream;
+    for (int i = 0; i < n; i++) found_out[i] = -1;
+    int mp = std::max(det->cfg.max_points, npts);
+    const int first_level = level < 0 ? 3 : level, last_level = level < 0 ? 0 : level;
+    PhaseTrace trace;
+    std::vector<signed char> own_levels;
+    if (!levels_out) { own_levels.resize((size_t)npts * n); levels_out = own_levels.data(); }
+    std::vector<char> stopped(n, 0);
+
+    // ---- corner passes on det ----
+    // Results: the points of frame k of the pass at pts[2 * off[k] ...], counts[k] of them -- copied out of the detector's
+    // pinned result buffer compactly (the next pass, which starts before these are looked at, writes there again; a slot
+    // of max_points per frame would be megabytes per pass to copy)
+    std::vector<int32_t> pts, counts;
+    std::vector<size_t> off;
+    std::vector<int> pass_frames;                  // frames of the pass in flight, in result order (empty: all n, in place)
+    auto enqueue = [&](int L, const std::vector<int>& only) -> int
+    {
+        const uint8_t* base = d_images; size_t gp = pitch, gfs = fstride; int cnt = n;
+        pass_frames.clear();
+        if (!only.empty() && (int)only.size() * 2 < n)
+        {
+            if (gather_frames(det, stream, d_images, rows, cols, pitch, fstride, only, &base, &gp, &gfs)) return -1;
+            pass_frames = only; cnt = (int)only.size();
+        }
+        std::lock_guard<std::mutex> g(det->mtx);
+        return enqueue_locked(det, base, 1, cnt, rows, cols, gp, gfs, L, mp, stream);
+    };
+    auto collect = [&](int L) -> int
+    {
+        for (;;)
+        {
+            const int cnt = pass_frames.empty() ? n : (int)pass_frames.size();
+            counts.resize(cnt);
+            {
+                std::lock_guard<std::mutex> g(det->mtx);
+                if (collect_locked(det, nullptr, counts.data())) return -1;
+            }
+            int most = 0;
+            for (int k = 0; k < cnt; k++) most = std::max(most, (int)counts[k]);
+            if (most <= mp)
+            {
+                off.assign(cnt + 1, 0);
+                for (int k = 0; k < cnt; k++) off[k + 1] = off[k] + (size_t)std::max(counts[k], 0);
+                pts.resize(2 * off[cnt]);
+                const int32_t* hxy = (const int32_t*)det->h_xy.p;
+                for (int k = 0; k < cnt; k++)
+                    if (counts[k] > 0) memcpy(&pts[2 * off[k]], hxy + (size_t)2 * mp * k, sizeof(int32_t) * 2 * counts[k]);
+                return 0;
+            }
+            mp = next_pow2(most);                  // more points than room was made for: the same pass again
+            const std::vector<int> again = pass_frames;
+            if (enqueue(L, again)) return -1;
+        }
+    };
+
+    // ---- refinement passes on helper (mrgingham.cc:81-99: level by level while any point of the frame moves) ----
+    auto refine_pass = [&](int L, std::vector<int> who) -> int
+    {
+        const int cnt = (int)who.size();
+        const bool all = cnt * 4 >= n || L >= 2;
+        const uint8_t* base = d_images; size_t gp = pitch, gfs = fstride;
+        if (!all && gather_frames(helper, helper->own_stream, d_images, rows, cols, pitch, fstride, who, &base, &gp, &gfs)) return -1;
+        const int m = all ? n : cnt;
+        std::vector<double> txy((size_t)2 * npts * m, 0.0);
+        std::vector<signed char> tlv((size_t)npts * m, 0);           // level 0: "already refined", never touched
+        std::vector<int32_t> nref(m);
+        for (int k = 0; k < cnt; k++)
+        {
+            const size_t slot = all ? who[k] : k;
+            memcpy(&txy[2 * npts * slot], xy_out + (size_t)2 * npts * who[k], sizeof(double) * 2 * npts);
+            memcpy(&tlv[npts * slot], levels_out + (size_t)npts * who[k], npts);
+        }
+        if (mrg_b200_refine_corners_batch(helper, base, 1, m, rows, cols, gp, gfs, L, txy.data(), tlv.data(), npts, nref.data(), nullptr)) return -1;
+        for (int k = 0; k < cnt; k++)
+        {
+            const size_t slot = all ? who[k] : k;
+            memcpy(xy_out + (size_t)2 * npts * who[k], &txy[2 * npts * slot], sizeof(double) * 2 * npts);
+            memcpy(levels_out + (size_t)npts * who[k], &tlv[npts * slot], npts);
+            if (nref[slot] <= 0) stopped[who[k]] = 1;
+        }
+        return 0;
+    };
+    std::thread refine_thread;
+    int refine_rc = 0, rl = first_level - 1;       // rl: the next refinement level
+    auto join_refine = [&]() { if (refine_thread.joinable()) refine_thread.join(); return refine_rc; };
+    auto refine_who = [&](int L) { std::vector<int> who; for (int i = 0; i < n; i++) if (found_out[i] > L && !stopped[i]) who.push_back(i); return who; };
+
+    int rc = 0;
+    std::vector<int> todo;
+    bool in_flight = false;
+    if (!(first_level == 0 && strict_level0 && rows > 1 && pitch != (size_t)cols))
+    { if (enqueue(first_level, todo)) return -1; in_flight = true; }
+    else MSG("I can only handle continuous arrays (stride == width) currently.");
+    for (int L = first_level; L >= last_level && in_flight; L--)
+    {
+        if (collect(L)) { rc = -1; break; }
+        in_flight = false;
+        trace.mark("corners", L, pass_frames.empty() ? n : (int)pass_frames.size());
+        // what the search of this level looks at; the next level's pass starts before it
+        std::vector<int> frames = pass_frames;                       // frames of xy/counts, in order
+        if (frames.empty()) { frames.resize(n); for (int i = 0; i < n; i++) frames[i] = i; }
+        const std::vector<int32_t> cur_pts = std::move(pts), cur_counts = std::move(counts);
+        const std::vector<size_t> cur_off = std::move(off);
+        todo.clear();
+        for (int i = 0; i < n; i++) if (found_out[i] < 0) todo.push_back(i);
+        const bool speculate = L - 1 >= last_level && L - 1 >= 1 && !todo.empty();
+        if (speculate) { if (enqueue(L - 1, std::vector<int>())) { rc = -1; break; } in_flight = true; }
+        if (rl == L)
+        {
+            if (join_refine()) { rc = -1; break; }
+            std::vector<int> who = refine_who(rl);
+            if (!who.empty()) { const int lv = rl; refine_thread = std::thread([&, lv, who]() { refine_rc = refine_pass(lv, who); }); }
+            rl--;
+        }
+        std::vector<int> slot_of(n, -1);
+        for (size_t k = 0; k < frames.size(); k++) slot_of[frames[k]] = (int)k;
+        const int ntodo = (int)todo.size();
+        parallel_for(ntodo, [&](int t)
+        {
+            const int i = todo[t], k = slot_of[i];
+            if (k < 0) return;
+            if (find_grid_from_points(cur_pts.data() + 2 * cur_off[k], cur_counts[k], gridn, xy_out + (size_t)2 * npts * i))
+            {
+                for (int q = 0; q < npts; q++) levels_out[(size_t)npts * i + q] = (signed char)L;
+                found_out[i] = L;
+            }
+        });
+        trace.mark("grid search", L, ntodo);
+        todo.clear();
+        for (int i = 0; i < n; i++) if (found_out[i] < 0) todo.push_back(i);
+        if (todo.empty() || L == last_level) break;
+        if (!in_flight)
+        {
+            // level 0: full-resolution frames, only those that still have no grid
+            if (L - 1 == 0 && strict_level0 && rows > 1 && pitch != (size_t)cols)
+            { MSG("I can only handle continuous arrays (stride == width) currently."); break; }
+            if (enqueue(L - 1, todo)) { rc = -1; break; }
+            in_flight = true;
+        }
+    }
+    if (in_flight)
+    {
+        // a pass that ran ahead of a search that then found every grid: its results are not needed
+        std::lock_guard<std::mutex> g(det->mtx);
+        if (collect_locked(det, nullptr, nullptr)) rc = -1;
+    }
+    if (join_refine()) rc = -1;
+    trace.mark("refine (tail)", rl + 1, 0);
+    for (; rc == 0 && rl >= 0; rl--)
+    {
+        std::vector<int> who = refine_who(rl);
+        if (who.empty()) continue;
+        if (refine_pass(rl, who)) rc = -1;
+        trace.mark("refine", rl, (int)who.size());
+    }
+    return rc;
 }
 
 int find_boards(mrg_b200_detector* det, const uint8_t* images, int on_device, int nframes, int rows, int cols,
@@ -1479,13 +1674,16 @@ int find_boards(mrg_b200_detector* det, const uint8_t* images, int on_device, in
     // one chunk at a time; cutting a single chunk into smaller ones for this loses more than it wins).
     const int chunk = std::max(1, det->cfg.max_frames);
     const int nchunks = (nframes + chunk - 1) / chunk;
-    if (nchunks >= 2 && !det->boards_helper)
+    // chunks of many frames with refinement: the pipeline over both detectors inside every chunk (chunks one after another)
+    const bool pipelined = !doblobs && refine && std::min(chunk, nframes) >= 16 && !getenv("MRG_B200_BOARDS_SERIAL");
+    if ((nchunks >= 2 || pipelined) && !det->boards_helper)
     {
         mrg_b200_detector_config hc = det->cfg;
         hc.device = det->device;
         if (mrg_b200_detector_create(&det->boards_helper, &hc)) det->boards_helper = nullptr;       // (then: one detector, as before)
     }
-    if (stream_ && nchunks >= 2 && det->boards_helper)
+    const bool piped = pipelined && det->boards_helper;
+    if (stream_ && (nchunks >= 2 || piped) && det->boards_helper)
     {
         DEVICE_GUARD(det);
         CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream_));       // device frames may come from work queued there; the helper runs elsewhere
@@ -1525,11 +1723,17 @@ int find_boards(mrg_b200_detector* det, const uint8_t* images, int on_device, in
                 CUDA_TRY(cudaStreamSynchronize(stream));
                 d = (const uint8_t*)dd->boards_frames.p;
             }
-            if (find_boards_chunk(dd, d, n, rows, cols, dpitch, dfstride, gridn, level, doblobs, refine, strict_level0,
+            if (piped && n >= 16)
+            {
+                if (find_boards_chunk_pipelined(dd, det->boards_helper, d, n, rows, cols, dpitch, dfstride, gridn, level, strict_level0,
+                                                xy_out + (size_t)2 * npts * f0, levels_out ? levels_out + (size_t)npts * f0 : nullptr, found_out + f0)) return -1;
+            }
+            else if (find_boards_chunk(dd, d, n, rows, cols, dpitch, dfstride, gridn, level, doblobs, refine, strict_level0,
                                   xy_out + (size_t)2 * npts * f0, levels_out ? levels_out + (size_t)npts * f0 : nullptr, found_out + f0, dstream)) return -1;
         }
         return 0;
     };
+    if (piped) return run_chunks(det, 0, 1, nullptr);
     if (nchunks >= 2 && det->boards_helper)
     {
         int rc_b = 0;

@@ -208,3 +208,44 @@ def test_find_boards_batch():
         if want is not None:
             assert np.array_equal(xy[i], want)
     det.close()
+
+
+@pytest.mark.gpu
+def test_find_boards_pipelined_equals_serial_and_oracle(monkeypatch):
+    """Chunks of >= 16 frames with refinement take the pipelined path (corner passes over all frames of the chunk ahead of
+    the grid searches, refinement on a second detector beside them): same boards, levels and refined points as the
+    pass-by-pass path (MRG_B200_BOARDS_SERIAL=1) and as the oracle pipeline, on frames that find their grid at different
+    levels, not at all, or only at level 0, from host and device memory, in chunks that end in a short one."""
+    import torch
+    api._require_gpu()
+    w, h, gridn = 1280, 720, 10
+    frames = []
+    for s in range(40):
+        kind = s % 8
+        if kind == 5:
+            frames.append(synth.noise_frame(w, h, seed=100 + s))                                  # no board
+        elif kind == 3:
+            frames.append(synth.board_frame(w, h, gridn, seed=s, noise_sigma=10.0))               # noisy: coarse levels do better
+        elif kind == 6:
+            frames.append(synth.board_frame(w, h, gridn, seed=s, noise_sigma=0.5, blur=False))    # sharp
+        else:
+            frames.append(synth.board_frame(w, h, gridn, seed=s))
+    raw = np.stack(frames)
+    det = api.Detector(max_frames=24, max_points=512)                  # chunks of 24 and 16
+    for level in (-1, 2, 0):
+        monkeypatch.setenv("MRG_B200_BOARDS_SERIAL", "1")
+        f0, xy0, lv0 = det.find_boards(raw, gridn=gridn, level=level)
+        monkeypatch.delenv("MRG_B200_BOARDS_SERIAL")
+        for images in (raw, torch.from_numpy(raw).cuda()):
+            f1, xy1, lv1 = det.find_boards(images, gridn=gridn, level=level)
+            assert np.array_equal(f0, f1), level
+            ok = f0 >= 0
+            assert np.array_equal(xy0[ok], xy1[ok]) and np.array_equal(lv0[ok], lv1[ok]), level
+        if level == -1:
+            assert len(set(int(v) for v in f0)) >= 3, sorted(set(int(v) for v in f0))   # several outcomes in one chunk
+            for i in (0, 3, 5, 6, 27):
+                L, wxy, wlv = oracle_board(raw[i], gridn, level)
+                assert f1[i] == L, i
+                if L >= 0:
+                    assert np.array_equal(xy1[i], wxy) and np.array_equal(lv1[i], wlv), i
+    det.close()
