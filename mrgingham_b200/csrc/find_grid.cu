@@ -4,8 +4,9 @@
 //
 // The reference gets its neighbour graph from Boost.Polygon's voronoi_diagram (find_grid.cc:7,1226). This
 // file builds what the reference reads from that diagram from scratch:
-//   * an exact Delaunay triangulation of the integer sites (sorted insertion outside the current hull,
-//     Lawson flips, all predicates in 128-bit integers), whose edges, minus those between cocircular sites
+//   * an exact Delaunay triangulation of the integer sites (insertion outside the current hull in order of distance
+//     from the centroid, Lawson flips, predicates exact: doubles behind a static error bound, 128-bit integers where
+//     that cannot decide), whose edges, minus those between cocircular sites
 //     (Voronoi edges of zero length, which Boost removes too), are the Voronoi edges;
 //   * per cell, the neighbouring cells in counter-clockwise order in (x,y) (find_grid.cc:40-41: clockwise as
 //     seen in an image), cells visited in sorted-site order as Boost creates them.
@@ -101,16 +102,36 @@ struct Tri { int v[3]; int n[3]; };
 class Triangulation
 {
 public:
-    Triangulation(const std::vector<P2>& pts, const std::vector<int>& order) : P(pts), ord(order) {}
+    Triangulation(const std::vector<P2>& pts, const std::vector<int>& sorted_sites) : P(pts), sorted(sorted_sites) {}
 
     // directed neighbour pairs (a,b), each neighbour relation in both directions; false if no triangle exists
     // (all sites on one line)
     bool run(std::vector<std::pair<int,int>>* nb)
     {
-        const int n = (int)ord.size();
+        const int n = (int)sorted.size();
+        // Insertion order: by distance from (a lattice point near) the centroid, all in exact integers. Every site is then
+        // outside the hull of the sites before it (they lie in the closed disc it is on the rim of, or beyond), and the
+        // triangles it adds are close to Delaunay already: a fraction of the flips that sites sorted by x need on a
+        // regular grid, where each new site first sees a whole column of thin triangles.
+        ord = sorted;
+        {
+            i64 sx = 0, sy = 0;
+            for (int k = 0; k < n; k++) { sx += P[ord[k]].x; sy += P[ord[k]].y; }
+            const i64 cx = sx / n, cy = sy / n;
+            std::vector<std::pair<i64, int>> key(n);
+            for (int k = 0; k < n; k++)
+            {
+                const i64 dx = P[ord[k]].x - cx, dy = P[ord[k]].y - cy;
+                key[k] = std::make_pair(dx * dx + dy * dy, k);         // (ties: in sorted-site order)
+            }
+            std::sort(key.begin(), key.end());
+            for (int k = 0; k < n; k++) ord[k] = sorted[key[k].second];
+        }
         int m = 2;
         while (m < n && orient(P[ord[0]], P[ord[1]], P[ord[m]]) == 0) m++;
         if (m >= n) return false;
+        // the sites before the first one off their common line, in order along the line (seed() fans them out from it)
+        std::sort(ord.begin(), ord.begin() + m, [&](int a, int b) { return P[a].x != P[b].x ? P[a].x < P[b].x : P[a].y < P[b].y; });
         hnext.assign(P.size(), -1); hprev.assign(P.size(), -1); htri.assign(P.size(), -1);
         T.reserve(2 * n);
         seed(m);
@@ -124,17 +145,19 @@ public:
                 // directed edge a -> b, opposite vertex c
                 const int a = T[t].v[(i + 1) % 3], b = T[t].v[(i + 2) % 3], c = T[t].v[i], u = T[t].n[i];
                 if (u < 0) { nb->push_back(std::make_pair(a, b)); nb->push_back(std::make_pair(b, a)); continue; }
+                if (u < (int)t) continue;          // an inner edge is looked at once, from the lower-numbered triangle
                 int j = 0; while (T[u].n[j] != (int)t) j++;
                 // the Voronoi edge between a and b has zero length when the two triangles share a circumcircle
                 if (incircle(P[c], P[a], P[b], P[T[u].v[j]]) == 0) continue;
-                nb->push_back(std::make_pair(a, b));
+                nb->push_back(std::make_pair(a, b)); nb->push_back(std::make_pair(b, a));
             }
         return true;
     }
 
 private:
     const std::vector<P2>& P;
-    const std::vector<int>& ord;
+    const std::vector<int>& sorted;          // distinct sites, sorted by (x,y)
+    std::vector<int> ord;                     // insertion order
     std::vector<Tri> T;
     std::vector<int> hnext, hprev, htri;      // convex hull, counter-clockwise; htri[v] owns the edge v -> hnext[v]
     int last = -1;                            // most recently inserted site (always a hull corner)
@@ -171,13 +194,17 @@ private:
         last = q;
     }
 
-    // p is lexicographically beyond every inserted site, so it is outside the hull and sees `last`
+    // p is at least as far from the centre of the insertion order as every inserted site, so it is strictly outside
+    // their hull: some hull edge has p strictly on its outer side. Found by walking the hull from the last inserted
+    // site (a few dozen corners at most on a few hundred sites), then widened to the whole visible chain lo .. hi.
     bool insert(int p)
     {
-        int lo = last, hi = last;
+        int v = last, guard = (int)P.size() + 1;
+        while (orient(P[v], P[hnext[v]], P[p]) >= 0) { v = hnext[v]; if (--guard < 0) return false; }
+        int lo = v, hi = hnext[v];
         while (orient(P[hi], P[hnext[hi]], P[p]) < 0) hi = hnext[hi];
         while (orient(P[hprev[lo]], P[lo], P[p]) < 0) lo = hprev[lo];
-        if (lo == hi) return false;     // cannot happen for sorted distinct sites
+        if (lo == hi) return false;     // cannot happen for a site outside the hull
         int prev_t = -1, first_t = -1;
         for (int a = lo; a != hi; )
         {
