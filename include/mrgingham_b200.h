@@ -65,9 +65,9 @@ bool find_chessboard_corners_from_image_array_C(int Nrows, int Ncols,
    Python find_board() binds. Corners (or blobs) -> grid of gridn x gridn -> refinement; image_pyramid_level < 0
    tries levels 3,2,1,0 and keeps the first that yields a grid. Returns false when no grid was found, on error,
    or for doblobs with a level other than 0; otherwise calls add_points(xy, gridn*gridn, cookie) once and returns
-   its result. debug_sequence_x/y only produce stderr traces in the reference and are ignored here; so is debug on
-   this (board) entry point -- the corner-level artefacts come from mrg_b200_debug_dump_corners(), the grid finder's
-   Voronoi dump from mrg_b200_voronoi_neighbours(). */
+   its result. debug: the grid finder's /tmp dumps and messages (mrg_b200_find_grid_from_points_debug()) and, for a
+   given level, the corner-level artefacts of mrg_b200_debug_dump_corners(); debug_sequence_x/y >= 0: the grid
+   finder's stderr trace of the walks from the corner nearest to that pixel (bridge.cc:97-104). */
 bool find_chessboard_from_image_array_C(int Nrows, int Ncols,
                                         int stride,
                                         char* imagebuffer, /* const */
@@ -125,6 +125,15 @@ int mrg_b200_find_blobs(const uint8_t* image, int Nrows, int Ncols, int stride,
    The reference's neighbour graph comes from Boost.Polygon's Voronoi diagram; this library builds the same
    graph itself (exact Delaunay triangulation) - see DESIGN.md for what that does and does not pin. */
 int mrg_b200_find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out);
+
+/* The same with the reference's diagnostics (find_grid.cc:1216-1445 with debug / debug_sequence). debug != 0: the
+   self-plotting /tmp/mrgingham-2-voronoi.vnl, /tmp/mrgingham-3-candidates[-detailed].vnl,
+   /tmp/mrgingham-4-outer-edges[-detailed].vnl, /tmp/mrgingham-5-outer-edge-cycles,
+   /tmp/mrgingham-6-identified-outer-edge-cycle (:387-480, :609-778) and the stderr messages that say where the search
+   stopped. debug_sequence_x/y >= 0 (pixels): the stderr trace of every connection considered in the walks that start
+   at the point nearest to that pixel (:216-310, :515-566). */
+int mrg_b200_find_grid_from_points_debug(const int* xy, int npoints, int gridn, double* xy_out,
+                                         int debug, int debug_sequence_x, int debug_sequence_y);
 
 /* The neighbour graph the grid finder walks (the content of the reference's --debug Voronoi dump,
    find_grid.cc:391-430): ring[ring_off[i] .. ring_off[i+1]) = the points whose Voronoi cells share an edge with

@@ -24,11 +24,12 @@ namespace mrgingham
                                       const int gridn, bool debug = false,
                                       const debug_sequence_t& debug_sequence = debug_sequence_t())
     {
-        (void)debug; (void)debug_sequence;
         static_assert(sizeof(PointInt) == 2 * sizeof(int), "PointInt must be 2 ints");
         if (points.empty() || gridn < 2) return false;
         std::vector<double> xy((size_t)2 * gridn * gridn);
-        if (mrg_b200_find_grid_from_points(&points[0].x, (int)points.size(), gridn, xy.data()) != 1) return false;
+        if (mrg_b200_find_grid_from_points_debug(&points[0].x, (int)points.size(), gridn, xy.data(), debug ? 1 : 0,
+                                                 debug_sequence.dodebug ? debug_sequence.pt.x : -1,
+                                                 debug_sequence.dodebug ? debug_sequence.pt.y : -1) != 1) return false;
         for (int i = 0; i < gridn * gridn; i++) points_out.push_back(PointDouble(xy[2*i], xy[2*i + 1]));
         return true;
     }

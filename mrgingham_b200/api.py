@@ -24,7 +24,7 @@ EXPORTS = (
     "mrg_b200_find_corners_mixed_batch", "mrg_b200_debug_dump_corners",
     "mrg_b200_refine_corners_batch", "mrg_b200_find_blobs", "mrg_b200_find_blobs_batch", "mrg_b200_box_blur_batch",
     "mrg_b200_preprocess_batch", "mrg_b200_preprocess16_batch",
-    "find_chessboard_from_image_array_C", "mrg_b200_find_grid_from_points", "mrg_b200_voronoi_neighbours",
+    "find_chessboard_from_image_array_C", "mrg_b200_find_grid_from_points", "mrg_b200_find_grid_from_points_debug", "mrg_b200_voronoi_neighbours",
     "mrg_b200_find_chessboard_from_image_array", "mrg_b200_find_circle_grid_from_image_array", "mrg_b200_find_boards_batch",
     "mrg_b200_chess_response_batch", "mrg_b200_chess_candidates_batch", "mrg_b200_pyramid_level",
     "mrg_b200_last_kernel_ms", "mrg_b200_set_profiling", "mrg_b200_last_candidate_counts", "mrg_b200_version",
@@ -69,6 +69,8 @@ def lib():
         ctypes.c_int, ctypes.c_int, _ADD_POINTS_D, ctypes.c_void_p]
     L.mrg_b200_find_grid_from_points.restype = ctypes.c_int
     L.mrg_b200_find_grid_from_points.argtypes = [_i32p, ctypes.c_int, ctypes.c_int, _f64p]
+    L.mrg_b200_find_grid_from_points_debug.restype = ctypes.c_int
+    L.mrg_b200_find_grid_from_points_debug.argtypes = [_i32p, ctypes.c_int, ctypes.c_int, _f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.mrg_b200_voronoi_neighbours.restype = ctypes.c_int
     L.mrg_b200_voronoi_neighbours.argtypes = [_i32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int]
     L.mrg_b200_find_chessboard_from_image_array.restype = ctypes.c_int
@@ -271,14 +273,21 @@ def find_blobs_int(image, cap=1 << 14):
     return xy[:n].copy()
 
 
-def find_grid_from_points(points, gridn=10):
+def find_grid_from_points(points, gridn=10, debug=False, debug_sequence=None):
     """mrgingham::find_grid_from_points (find_grid.cc:1216-1445): points = (N,2) int PointInt list (x1000);
-    returns the ordered (gridn*gridn, 2) float64 pixel coordinates, or None. Host code: works without a GPU."""
+    returns the ordered (gridn*gridn, 2) float64 pixel coordinates, or None. Host code: works without a GPU.
+    debug: the reference's /tmp/mrgingham-{2..6}-* dumps and stderr messages; debug_sequence = (x, y) in pixels: its
+    stderr trace of the walks from the point nearest to that pixel."""
     pts = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
     out = np.empty((gridn * gridn, 2), dtype=np.float64)
-    if len(pts) == 0 or lib().mrg_b200_find_grid_from_points(_ptr(pts, _i32p), len(pts), int(gridn), _ptr(out, _f64p)) != 1:
+    if len(pts) == 0:
         return None
-    return out
+    if debug or debug_sequence is not None:
+        sx, sy = (-1, -1) if debug_sequence is None else (int(debug_sequence[0]), int(debug_sequence[1]))
+        rc = lib().mrg_b200_find_grid_from_points_debug(_ptr(pts, _i32p), len(pts), int(gridn), _ptr(out, _f64p), int(bool(debug)), sx, sy)
+    else:
+        rc = lib().mrg_b200_find_grid_from_points(_ptr(pts, _i32p), len(pts), int(gridn), _ptr(out, _f64p))
+    return out if rc == 1 else None
 
 
 def voronoi_neighbours(points):

@@ -1384,6 +1384,20 @@ int gather_frames(mrg_b200_detector* det, cudaStream_t stream, const uint8_t* d_
     return 0;
 }
 
+// The reference's debug / debug_sequence of a one-image board call (mrgingham.cc:43-52): set by the entry point around
+// its call, read by the grid search of find_boards_chunk(), which runs in the calling thread for a single frame.
+thread_local const GridDebug* t_grid_debug = nullptr;
+struct GridDebugScope
+{
+    GridDebug d; bool on;
+    GridDebugScope(bool debug, int seq_x, int seq_y) : on(debug || (seq_x >= 0 && seq_y >= 0))
+    {
+        d.dump = debug; d.sequence = seq_x >= 0 && seq_y >= 0; d.seq_x = seq_x; d.seq_y = seq_y;
+        if (on) t_grid_debug = &d;
+    }
+    ~GridDebugScope() { if (on) t_grid_debug = nullptr; }
+};
+
 // MRG_B200_BOARDS_TRACE=1: wall-clock time of every phase of a chunk on stderr (where a board call's time goes)
 struct PhaseTrace
 {
@@ -1438,7 +1452,7 @@ int find_boards_chunk(mrg_b200_detector* det, const uint8_t* d_images, int n, in
         parallel_for(cnt, [&](int k)
         {
             const int i = todo[k];
-            if (find_grid_from_points(xy.data() + (size_t)2 * mp * k, counts[k], gridn, xy_out + (size_t)2 * npts * i))
+            if (find_grid_from_points(xy.data() + (size_t)2 * mp * k, counts[k], gridn, xy_out + (size_t)2 * npts * i, cnt == 1 ? t_grid_debug : nullptr))
                 found_out[i] = L;
         });
         trace.mark("grid search", L, cnt);
@@ -1752,6 +1766,15 @@ API int mrg_b200_find_grid_from_points(const int* xy, int npoints, int gridn, do
     return find_grid_from_points(xy, npoints, gridn, xy_out) ? 1 : 0;
 }
 
+API int mrg_b200_find_grid_from_points_debug(const int* xy, int npoints, int gridn, double* xy_out,
+                                             int debug, int debug_sequence_x, int debug_sequence_y)
+{
+    if (gridn < 2 || npoints < 0 || (npoints > 0 && !xy) || !xy_out) return 0;
+    GridDebug d; d.dump = debug != 0; d.sequence = debug_sequence_x >= 0 && debug_sequence_y >= 0;
+    d.seq_x = debug_sequence_x; d.seq_y = debug_sequence_y;
+    return find_grid_from_points(xy, npoints, gridn, xy_out, &d) ? 1 : 0;
+}
+
 API int mrg_b200_voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* ring, int ring_cap)
 {
     if (npoints <= 0 || !xy || !ring_off || (ring_cap > 0 && !ring)) return -1;
@@ -1800,8 +1823,12 @@ API bool find_chessboard_from_image_array_C(int Nrows, int Ncols, int stride, ch
                                             int debug_sequence_x, int debug_sequence_y,
                                             bool (*add_points)(double* xy, int N, void* cookie), void* cookie)
 {
-    (void)debug; (void)debug_sequence_x; (void)debug_sequence_y;   // diagnostics only in the reference
     if (gridn < 2) return false;
+    // debug: the grid finder's /tmp dumps and messages; debug_sequence_x/y >= 0: its trace of the walks from the point
+    // nearest to that pixel (bridge.cc:97-104). The corner-level artefacts of `debug` come from mrg_b200_debug_dump_corners().
+    GridDebugScope grid_debug(debug, debug_sequence_x, debug_sequence_y);
+    if (debug && !doblobs && image_pyramid_level >= 0)
+        mrg_b200_debug_dump_corners((const uint8_t*)imagebuffer, Nrows, Ncols, stride, image_pyramid_level, nullptr, nullptr, nullptr, 0);
     std::vector<double> xy((size_t)2 * gridn * gridn);
     int rc;
     if (doblobs)

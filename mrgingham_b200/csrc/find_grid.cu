@@ -20,8 +20,11 @@
 #include <climits>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <sys/stat.h>
 #include <map>
 #include <set>
+#include <string>
 #include <vector>
 
 #include "find_grid.hh"
@@ -409,6 +412,7 @@ struct Finder
 {
     const Graph&             g;
     int                      gridn;
+    bool                     debug;
     std::vector<Sequence>    seq;
     std::vector<int>         outer;                        // indices into seq
     std::map<int, std::vector<int>> outer_from;            // first cell -> indices into outer
@@ -423,7 +427,7 @@ struct Finder
         Cycle best = {};
         const int cur = cyc->e[count - 1];
         std::map<int, std::vector<int>>::const_iterator it = outer_from.find(last(cur));
-        if (it == outer_from.end()) return false;
+        if (it == outer_from.end()) { if (debug) fprintf(stderr, "No opposing outer edge\n"); return false; }
         const std::vector<int>& nxt = it->second;
         for (size_t k = 0; k < nxt.size(); k++)
         {
@@ -435,7 +439,7 @@ struct Finder
                 if (count == 2 && is_crossing(g.pts, first(cyc->e[0]), last(cyc->e[0]), first(e), last(e))) continue;
                 cyc->e[count] = e;
                 if (!extend_cycle(cyc, count + 1, start)) continue;
-                if (found) return false;                           // two different cycles: ambiguous
+                if (found) { if (debug) fprintf(stderr, "Found non-unique 4-cycle\n"); return false; }    // two different cycles: ambiguous
                 found = true;
                 best = *cyc;
             }
@@ -457,10 +461,18 @@ struct Finder
     {
         int ia = 0, ib = -1;
         for (int k = 0; k < 4; k++) if (last(b.e[k]) == first(a.e[0])) { ib = k; break; }
-        if (ib < 0) return false;
+        if (ib < 0)
+        {
+            if (debug) fprintf(stderr, "Given outer cycles are NOT equal and opposite: couldn't find a corresponding point in the two cycles\n");
+            return false;
+        }
         for (int k = 0; k < 4; k++)
         {
-            if (first(a.e[ia]) != last(b.e[ib]) || last(a.e[ia]) != first(b.e[ib])) return false;
+            if (first(a.e[ia]) != last(b.e[ib]) || last(a.e[ia]) != first(b.e[ib]))
+            {
+                if (debug) fprintf(stderr, "Given outer cycles are NOT equal and opposite\n");
+                return false;
+            }
             ia = (ia + 1) % 4; ib = (ib + 3) % 4;
         }
         return true;
@@ -481,7 +493,7 @@ struct Finder
         int clockwise;
         if      ( sign[0] &&  sign[1] &&  sign[2] &&  sign[3]) clockwise = 0;
         else if (!sign[0] && !sign[1] && !sign[2] && !sign[3]) clockwise = 1;
-        else return -1;                                            // not convex
+        else { if (debug) fprintf(stderr, "The outer edge cycles aren't convex!\n"); return -1; }
 
         for (int ic = 0; ic < 2; ic++)
         {
@@ -507,13 +519,166 @@ struct Finder
             if (v1x < 0) v1x = -v1x;
             const i64 cross = (v0x * v1y - v0y * v1x) * (v0x * v1y - v0y * v1x);
             const i64 denom = (v0x * v0x + v0y * v0y) * (v1x * v1x + v1y * v1y);
-            if ((cross < 0 ? -cross : cross) * 8 < denom * 1) return -1;        // too close to call (sin^2 < 1/8)
+            if ((cross < 0 ? -cross : cross) * 8 < denom * 1)                   // too close to call (sin^2 < 1/8)
+            {
+                if (debug)
+                {
+                    fprintf(stderr, "Highest 2 edges have a similar orientation. I can't tell clearly which is the more horizontal one\n");
+                    const char* which[2] = { "Highest", "Second-highest" };
+                    for (int q = 0; q < 2; q++)
+                        fprintf(stderr, "  %s edge: (%.2f,%.2f) - (%.2f,%.2f). Highest vertex: (%.2f,%.2f)\n", which[q],
+                                (double)P[first(cyc[ic]->e[edge[q]])].x / (double)kScale, (double)P[first(cyc[ic]->e[edge[q]])].y / (double)kScale,
+                                (double)P[last(cyc[ic]->e[edge[q]])].x / (double)kScale,  (double)P[last(cyc[ic]->e[edge[q]])].y / (double)kScale,
+                                (double)P[lo[q]].x / (double)kScale, (double)P[lo[q]].y / (double)kScale);
+                    fprintf(stderr, "  sin(angle difference) as computed here: %f. Threshold: %f\n",
+                            sqrt((double)(cross < 0 ? -cross : cross) / (double)denom), sqrt(1.0 / 8.0));
+                }
+                return -1;
+            }
             const i64 l = v0y * v1x, r = v1y * v0x;
             top[ic] = (l < 0 ? -l : l) < (r < 0 ? -r : r) ? edge[0] : edge[1];
         }
         return clockwise;
     }
 };
+
+// ---- the reference's --debug artefacts (find_grid.cc:387-480, 609-778) ----
+void make_executable(const char* fn) { chmod(fn, S_IRUSR | S_IRGRP | S_IROTH | S_IWUSR | S_IWGRP | S_IXUSR | S_IXGRP | S_IXOTH); }
+
+void dump_voronoi(const Graph& g)
+{
+    const char* fn = "/tmp/mrgingham-2-voronoi.vnl";
+    FILE* fp = fopen(fn, "w");
+    if (!fp) { fprintf(stderr, "Couldn't open %s for writing\n", fn); return; }
+    fprintf(fp, "#!/usr/bin/feedgnuplot --domain --dataid --with 'lines linecolor 0' --square --maxcurves 100000 --set 'yrange [:] rev'\n");
+    fprintf(fp, "# x id_edge y\n");
+    int i_edge = 0;
+    for (size_t si = 0; si < g.sites.size(); si++)
+    {
+        const int a = g.sites[si];
+        for (int k = g.ring_off[a]; k < g.ring_off[a + 1]; k++, i_edge++)
+        {
+            const int b = g.ring[k];
+            fprintf(fp, "%f %d %f\n", g.pts[a].x / (double)kScale, i_edge, g.pts[a].y / (double)kScale);
+            fprintf(fp, "%f %d %f\n", g.pts[b].x / (double)kScale, i_edge, g.pts[b].y / (double)kScale);
+        }
+    }
+    fclose(fp);
+    make_executable(fn);
+    fprintf(stderr, "Wrote self-plotting voronoi diagram to %s\n", fn);
+}
+
+// the gridn points of a sequence, one line each: the step to the next point, dashes after the last (find_grid.cc:425-480)
+void dump_intervals(FILE* fp, const Graph& g, const Sequence& s, int i_candidate, int gridn)
+{
+    std::vector<int> cells(gridn);
+    sequence_cells(g, s, gridn, cells.data());
+    for (int i = 0; i < gridn; i++)
+    {
+        const P2& p0 = g.pts[cells[i]];
+        if (i == gridn - 1)
+        {
+            fprintf(fp, "%d %d %f %f - - - - - -\n", i_candidate, i, (double)p0.x / (double)kScale, (double)p0.y / (double)kScale);
+            break;
+        }
+        const P2& p1 = g.pts[cells[i + 1]];
+        const double dx = (double)(int)(p1.x - p0.x) / (double)kScale, dy = (double)(int)(p1.y - p0.y) / (double)kScale;
+        fprintf(fp, "%d %d %f %f %f %f %f %f %f %f\n", i_candidate, i,
+                (double)p0.x / (double)kScale, (double)p0.y / (double)kScale, (double)p1.x / (double)kScale, (double)p1.y / (double)kScale,
+                dx, dy, hypot(dx, dy), atan2(dy, dx) * 180.0 / M_PI);
+    }
+}
+
+// which: indices into seq (all of them when null)
+void dump_candidates(const char* basename, const Graph& g, const std::vector<Sequence>& seq, const std::vector<int>* which, int gridn)
+{
+    const std::string sparse = std::string(basename) + ".vnl", dense = std::string(basename) + "-detailed.vnl";
+    const int N = which ? (int)which->size() : (int)seq.size();
+    FILE* fp = fopen(sparse.c_str(), "w");
+    if (!fp) { fprintf(stderr, "Couldn't open %s for writing\n", sparse.c_str()); return; }
+    fprintf(fp, "#!/usr/bin/feedgnuplot --dom --aut --square --rangesizea 3 --w 'vec size screen 0.01,20 fixed fill' --set 'yr [:] rev'\n");
+    fprintf(fp, "# fromx fromy deltax deltay\n");
+    for (int i = 0; i < N; i++)
+    {
+        const Sequence& s = seq[which ? (*which)[i] : i];
+        fprintf(fp, "%f %f %f %f\n", (double)g.pts[s.c0].x / (double)kScale, (double)g.pts[s.c0].y / (double)kScale,
+                s.mean_dx / (double)kScale, s.mean_dy / (double)kScale);
+    }
+    fclose(fp);
+    make_executable(sparse.c_str());
+    fprintf(stderr, "Wrote self-plotting sequence-candidate dump to %s\n", sparse.c_str());
+    fp = fopen(dense.c_str(), "w");
+    if (!fp) { fprintf(stderr, "Couldn't open %s for writing\n", dense.c_str()); return; }
+    fprintf(fp, "# candidateid pointid fromx fromy tox toy deltax deltay len angle\n");
+    for (int i = 0; i < N; i++) dump_intervals(fp, g, seq[which ? (*which)[i] : i], i, gridn);
+    fclose(fp);
+    fprintf(stderr, "Wrote detailed sequence-candidate dump to %s\n", dense.c_str());
+}
+
+// label(cycle, edge): the text between x and y (the cycle number, or "clockwise-top" ...)
+template <class L>
+void dump_cycles(const char* fn, const Finder& F, const Cycle* const* cyc, int ncyc, L label)
+{
+    FILE* fp = fopen(fn, "w");
+    if (!fp) { fprintf(stderr, "Couldn't open %s for writing\n", fn); return; }
+    fprintf(fp, "#!/usr/bin/feedgnuplot --datai --dom --aut --square --rangesizea 3 --w 'vec size screen 0.01,20 fixed fill' --set 'yr [:] rev'\n");
+    fprintf(fp, "# fromx type fromy deltax deltay\n");
+    for (int c = 0; c < ncyc; c++)
+        for (int e = 0; e < 4; e++)
+        {
+            const Sequence& s = F.seq[F.outer[cyc[c]->e[e]]];
+            fprintf(fp, "%f %s %f %f %f\n", (double)F.g.pts[s.c0].x / (double)kScale, label(c, e).c_str(), (double)F.g.pts[s.c0].y / (double)kScale,
+                    s.mean_dx / (double)kScale, s.mean_dy / (double)kScale);
+        }
+    fclose(fp);
+    make_executable(fn);
+    fprintf(stderr, "Wrote outer edge cycle dump to %s\n", fn);
+}
+
+// The walk of step() from one cell with the reference's commentary on stderr (find_grid.cc:216-310): every neighbour
+// considered, why it is rejected, which one is accepted. Same tests in the same order as build_continuations() + step().
+int step_traced(const Graph& g, Walk* w)
+{
+    const int a_e = w->e, b = g.adj[a_e];
+    const double lx = g.adj_dx[a_e], ly = g.adj_dy[a_e], last_len = g.adj_len[a_e];
+    for (int k = g.adj_off[b]; k < g.adj_off[b + 1]; k++)
+    {
+        const int c = g.adj[k];
+        fprintf(stderr, "Considering connection in sequence from (%d,%d) -> (%d,%d); delta (%d,%d) ..... \n",
+                (int)g.pts[b].x / kScale, (int)g.pts[b].y / kScale, (int)g.pts[c].x / kScale, (int)g.pts[c].y / kScale,
+                (int)(g.pts[c].x - g.pts[b].x) / kScale, (int)(g.pts[c].y - g.pts[b].y) / kScale);
+        const double dx = g.adj_dx[k], dy = g.adj_dy[k], len = g.adj_len[k];
+        const double cos_err = (lx * dx + ly * dy) / (last_len * len);
+        if (cos_err < kMinCos)
+        {
+            fprintf(stderr, "..... rejecting. Angle is wrong. I wanted cos_err>=threshold, but saw %f<%f\n", cos_err, kMinCos);
+            continue;
+        }
+        const double ratio = len / last_len;
+        if (ratio < kMinRatio || ratio > kMaxRatio)
+        {
+            fprintf(stderr, "..... rejecting. Lengths are wrong. I wanted abs(length_ratio)<=threshold, but saw %f<%f or %f>%f\n",
+                    ratio, kMinRatio, ratio, kMaxRatio);
+            continue;
+        }
+        if (w->ratio_n > 2)
+        {
+            const double dev = ratio - w->ratio_sum / (double)w->ratio_n;
+            if (dev < -kMaxRatioDeviation || dev > kMaxRatioDeviation)
+            {
+                fprintf(stderr, "..... rejecting. Lengths are wrong. I wanted abs(length_ratio_deviation)<=threshold, but saw %f>%f\n",
+                        fabs(dev), kMaxRatioDeviation);
+                continue;
+            }
+        }
+        w->ratio_sum += ratio;
+        w->ratio_n++;
+        w->e = k;
+        fprintf(stderr, "..... accepting!\n\n");
+        return k;
+    }
+    return -1;
+}
 }   // namespace
 
 int voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* ring, int ring_cap)
@@ -525,13 +690,30 @@ int voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* ring, int
     return g.ring_off[npoints];
 }
 
-bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out)
+bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out, const GridDebug* dbg)
 {
     if (npoints <= 0 || gridn < 2 || !xy || !xy_out) return false;
+    const bool debug = dbg && dbg->dump;
     Graph g;
     if (!build_graph(&g, xy, npoints)) return false;
     build_continuations(&g);
-    Finder F = { g, gridn, {}, {}, {} };
+    if (debug) dump_voronoi(g);
+    Finder F = { g, gridn, debug, {}, {}, {} };
+
+    // debug_sequence: the cell nearest to the given pixel is the one whose walks are narrated (find_grid.cc:515-540)
+    int traced = -1;
+    if (dbg && dbg->sequence)
+    {
+        unsigned long best = (unsigned long)(-1L);
+        for (size_t si = 0; si < g.sites.size(); si++)
+        {
+            const int c = g.sites[si];
+            const long dx = (long)(g.pts[c].x - (i64)kScale * dbg->seq_x), dy = (long)(g.pts[c].y - (i64)kScale * dbg->seq_y);
+            const unsigned long d2 = (unsigned long)(dx * dx + dy * dy);
+            if (d2 < best) { best = d2; traced = c; }
+        }
+        fprintf(stderr, "============== Looking at sequences from (%d,%d)\n", (int)g.pts[traced].x / kScale, (int)g.pts[traced].y / kScale);
+    }
 
     // every run of gridn cells, from every cell towards every neighbour (find_grid.cc:505-566)
     for (size_t si = 0; si < g.sites.size(); si++)
@@ -540,12 +722,14 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
         for (int k = g.adj_off[c]; k < g.adj_off[c + 1]; k++)
         {
             const int c1 = g.adj[k];
+            if (c == traced)
+                fprintf(stderr, "\n\n====== Looking at adjacent point (%d,%d)\n", (int)g.pts[c1].x / kScale, (int)g.pts[c1].y / kScale);
             Walk w = { k, 0.0, 0 };
             double mx = g.adj_dx[k], my = g.adj_dy[k];
             int clast = -1;
             for (int i = 0; i < gridn - 2; i++)
             {
-                const int e = step(g, &w);
+                const int e = c == traced ? step_traced(g, &w) : step(g, &w);
                 if (e < 0) { clast = -1; break; }
                 mx += g.adj_dx[e]; my += g.adj_dy[e];
                 clast = g.adj[e];
@@ -555,12 +739,23 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
             F.seq.push_back(s);
         }
     }
+    if (debug)
+    {
+        dump_candidates("/tmp/mrgingham-3-candidates", g, F.seq, nullptr, gridn);
+        fprintf(stderr, "got %zd points\n", (size_t)npoints);
+        fprintf(stderr, "got %zd sequence candidates\n", F.seq.size());
+    }
 
     // the board's outer edges start at cells that start at least two sequences (find_grid.cc:1244-1275)
     std::map<int, int> started;
     for (size_t i = 0; i < F.seq.size(); i++) started[F.seq[i].c0]++;
     for (size_t i = 0; i < F.seq.size(); i++) if (started[F.seq[i].c0] >= 2) F.outer.push_back((int)i);
-    if (F.outer.size() < 8) return false;
+    if (F.outer.size() < 8)
+    {
+        if (debug) fprintf(stderr, "Too few candidates for an outer edge of the grid. Needed at least 8, got %d\n", (int)F.outer.size());
+        return false;
+    }
+    if (debug) dump_candidates("/tmp/mrgingham-4-outer-edges", g, F.seq, &F.outer, gridn);
     for (size_t i = 0; i < F.outer.size(); i++) F.outer_from[F.first((int)i)].push_back((int)i);
 
     // 4-cycles of outer edges (find_grid.cc:1290-1317)
@@ -574,7 +769,17 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
         cycles.push_back(c);
         for (int k = 0; k < 4; k++) used.insert(c.e[k]);
     }
-    if (cycles.size() < 2) return false;
+    if (debug && !cycles.empty())
+    {
+        std::vector<const Cycle*> all(cycles.size());
+        for (size_t i = 0; i < cycles.size(); i++) all[i] = &cycles[i];
+        dump_cycles("/tmp/mrgingham-5-outer-edge-cycles", F, all.data(), (int)all.size(), [](int c, int) { return std::to_string(c); });
+    }
+    if (cycles.size() < 2)
+    {
+        if (debug) fprintf(stderr, "Found too few 4-cycles. Needed at least 2, got %d\n", (int)cycles.size());
+        return false;
+    }
 
     // exactly one pair of cycles running the same way round in opposite directions (find_grid.cc:1329-1353)
     int pair[2] = { -1, -1 };
@@ -582,15 +787,26 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
         for (size_t b = a + 1; b < cycles.size(); b++)
             if (F.opposite(cycles[a], cycles[b]))
             {
-                if (pair[0] >= 0) return false;
+                if (pair[0] >= 0)
+                {
+                    if (debug) fprintf(stderr, "Found more than one equal-and-opposite pair of outer-edge cycles. Giving up\n");
+                    return false;
+                }
                 pair[0] = (int)a; pair[1] = (int)b;
             }
-    if (pair[0] < 0) return false;
+    if (pair[0] < 0)
+    {
+        if (debug) fprintf(stderr, "Didn't find any equal-and-opposite pairs of outer-edge cycles. Giving up\n");
+        return false;
+    }
 
     const Cycle* cyc[2] = { &cycles[pair[0]], &cycles[pair[1]] };
     int top[2];
     const int cw = F.orient_cycles(cyc, top);
     if (cw < 0) return false;
+    if (debug)
+        dump_cycles("/tmp/mrgingham-6-identified-outer-edge-cycle", F, cyc, 2, [&](int c, int e)
+                    { return std::string(c == cw ? "clockwise" : "counterclockwise") + (top[c] == e ? "-top" : ""); });
 
     // rows run from the i-th cell of the left edge to the i-th cell of the right edge (find_grid.cc:1385-1433)
     std::map<int, std::vector<int>> seq_from;
@@ -609,7 +825,12 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
     for (int i = 1; i < gridn; i++)
     {
         rows[i] = from_to(left[i], right[i]);
-        if (rows[i] < 0 || from_to(right[i], left[i]) < 0) return false;
+        if (rows[i] < 0) { if (debug) fprintf(stderr, "Couldn't find sequence in row %d\n", i); return false; }
+        if (from_to(right[i], left[i]) < 0)
+        {
+            if (debug) fprintf(stderr, "Row %d: left-to-right sequence was found, but right-to-left sequence doesn't exist!\n", i);
+            return false;
+        }
     }
     for (int i = 0; i < gridn; i++)
     {
@@ -620,6 +841,7 @@ bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out
             xy_out[2 * (i * gridn + k) + 1] = (double)g.pts[cells[k]].y / (double)kScale;
         }
     }
+    if (debug) fprintf(stderr, "Success. Found grid\n");
     return true;
 }
 

@@ -11,5 +11,12 @@ namespace mrgb200
 // exceed ring_cap; only ring_cap entries are written) or <0.
 int voronoi_neighbours(const int* xy, int npoints, int* ring_off, int* ring, int ring_cap);
 
-bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out);
+// The reference's diagnostics (find_grid.cc:387-423, 425-480, 609-778 and the fprintf(stderr) of :216-343, :505-566,
+// :1216-1445): dump = its `debug` (the self-plotting /tmp/mrgingham-2-voronoi.vnl, -3-candidates[-detailed].vnl,
+// -4-outer-edges[-detailed].vnl, -5-outer-edge-cycles, -6-identified-outer-edge-cycle and the messages that say why a
+// grid was not found); sequence = its debug_sequence (a trace on stderr of every connection considered from the point
+// nearest to (seq_x, seq_y), in pixels).
+struct GridDebug { bool dump; bool sequence; int seq_x, seq_y; };
+
+bool find_grid_from_points(const int* xy, int npoints, int gridn, double* xy_out, const GridDebug* debug = nullptr);
 }

@@ -315,6 +315,17 @@ def ref_grid_lib():
     return _ref_grid
 
 
+def ref_find_grid_from_points_debug(points, gridn, debug=True, debug_sequence=None):
+    """the compiled reference's find_grid_from_points() with its diagnostics on (files under /tmp, text on stderr)"""
+    pts = np.ascontiguousarray(points, dtype=np.int32).reshape(-1, 2)
+    out = np.empty((gridn * gridn, 2), dtype=np.float64)
+    L = ref_grid_lib()
+    L.ref_find_grid_from_points_debug.restype = ctypes.c_int
+    sx, sy = (-1, -1) if debug_sequence is None else (int(debug_sequence[0]), int(debug_sequence[1]))
+    r = L.ref_find_grid_from_points_debug(_ptr(pts, _i32p), len(pts), gridn, _ptr(out, _f64p), int(bool(debug)), sx, sy)
+    return out if r == 1 else None
+
+
 def ref_find_grid_from_points(points, gridn):
     """mrgingham::find_grid_from_points (find_grid.cc:1216). points: int32 [n,2] scaled by 1000.
     Returns float64 [gridn*gridn, 2] or None."""

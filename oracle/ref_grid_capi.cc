@@ -65,6 +65,24 @@ API int ref_find_grid_from_points(const int* xy, int n, int gridn, double* out)
     return 1;
 }
 
+// The same with the reference's diagnostics switched on: debug (the /tmp/mrgingham-{2..6}-* dumps and stderr messages,
+// find_grid.cc:387-480, 609-778) and debug_sequence (the stderr trace from the point nearest to pixel (sx, sy); sx < 0: off).
+API int ref_find_grid_from_points_debug(const int* xy, int n, int gridn, double* out, int debug, int sx, int sy)
+{
+    std::vector<mrgingham::PointInt> pts;
+    pts.reserve(n);
+    for(int i = 0; i < n; i++) pts.push_back(mrgingham::PointInt(xy[2*i], xy[2*i+1]));
+    std::vector<mrgingham::PointDouble> grid;
+    mrgingham::debug_sequence_t ds = {};
+    if(sx >= 0 && sy >= 0) { ds.dodebug = true; ds.pt.x = sx; ds.pt.y = sy; }
+    const bool found = mrgingham::find_grid_from_points(grid, pts, gridn, debug != 0, ds);
+    fflush(stderr);
+    if(!found) return 0;
+    if((int)grid.size() != gridn*gridn) return -1;
+    for(int i = 0; i < gridn*gridn; i++) { out[2*i] = grid[i].x; out[2*i+1] = grid[i].y; }
+    return 1;
+}
+
 // The whole board pipeline on one image. level < 0: the reference's 3,2,1,0 loop. Returns the level the board
 // was found at, or -1. levels_out (gridn*gridn, may be NULL when !refine): the level each point was refined to.
 API int ref_find_chessboard_from_image_array(const uint8_t* image, int rows, int cols, int stride,

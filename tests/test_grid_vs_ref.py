@@ -169,3 +169,66 @@ def test_grid_equals_reference_randomised_sweep():
         assert same(api.find_grid_from_points(pts, gridn), want), (seed, gridn, rot, persp, noise)
         n_found += want is not None
     assert 100 < n_found < 400
+
+
+_DUMPS = ["/tmp/mrgingham-2-voronoi.vnl", "/tmp/mrgingham-3-candidates.vnl", "/tmp/mrgingham-3-candidates-detailed.vnl",
+          "/tmp/mrgingham-4-outer-edges.vnl", "/tmp/mrgingham-4-outer-edges-detailed.vnl",
+          "/tmp/mrgingham-5-outer-edge-cycles", "/tmp/mrgingham-6-identified-outer-edge-cycle"]
+
+
+def _with_diagnostics(fn):
+    """run fn() with fd 2 captured; returns (result, stderr text, {dump file: content or None}); the dumps are removed"""
+    import os
+    import sys
+    import tempfile
+    for f in _DUMPS:
+        if os.path.exists(f):
+            os.remove(f)
+    sys.stderr.flush()
+    saved = os.dup(2)
+    with tempfile.TemporaryFile(mode="w+b") as tmp:
+        os.dup2(tmp.fileno(), 2)
+        try:
+            res = fn()
+        finally:
+            os.dup2(saved, 2)
+            os.close(saved)
+        tmp.seek(0)
+        text = tmp.read().decode()
+    files = {}
+    for f in _DUMPS:
+        files[f] = open(f).read() if os.path.exists(f) else None
+        if files[f] is not None:
+            os.remove(f)
+    return res, text, files
+
+
+def test_grid_debug_artefacts_equal_reference():
+    """F4 for the grid finder: the reference's `debug` dumps (Voronoi edges, sequence candidates, outer edges, 4-cycles,
+    the identified pair; find_grid.cc:387-480, 609-778), its stderr messages and its `debug_sequence` trace
+    (:216-310, :515-566), byte for byte against find_grid.cc compiled over the Voronoi stand-in -- on boards that are
+    found and on inputs that fail at each stage."""
+    cases = []
+    for gridn, seed in ((10, 1), (6, 2), (14, 3)):
+        cases.append((board_points(gridn, 1920, 1080, seed, extras=3)[0], gridn))
+    pts10 = np.sort(board_points(10, 1280, 960, 4)[0].view('i4,i4'), order=['f1', 'f0'], axis=0).view(np.int32)
+    cases.append((pts10[:57], 10))                                   # half a board: too few outer edges / cycles
+    cases.append((np.delete(pts10, 45, axis=0), 10))                 # a corner missing inside
+    cases.append((np.vstack([pts10, pts10 + np.array([9000000, 0])]).astype(np.int32), 10))    # two boards
+    cases.append((board_points(8, 1280, 960, 5)[0], 10))             # wrong gridn
+    rng = np.random.default_rng(11)
+    cases.append((rng.integers(0, 3000000, (80, 2)).astype(np.int32), 6))
+    outcomes = set()
+    for pts, gridn in cases:
+        pts = np.ascontiguousarray(pts, dtype=np.int32)
+        at = (int(pts[len(pts) // 3][0]) // 1000, int(pts[len(pts) // 3][1]) // 1000)
+        for debug, seq in ((True, None), (True, at), (False, at)):
+            want, wtext, wfiles = _with_diagnostics(lambda: po.ref_find_grid_from_points_debug(pts, gridn, debug, seq))
+            got, gtext, gfiles = _with_diagnostics(lambda: api.find_grid_from_points(pts, gridn, debug=debug, debug_sequence=seq))
+            assert (want is None) == (got is None) and (want is None or np.array_equal(want, got))
+            assert gfiles == wfiles, [f for f in _DUMPS if gfiles[f] != wfiles[f]]
+            assert gtext == wtext, (gridn, len(pts), debug, seq)
+            if debug:
+                assert wfiles[_DUMPS[0]] is not None and wfiles[_DUMPS[1]] is not None
+            outcomes.add(wtext.strip().splitlines()[-1] if wtext.strip() else "")
+    assert "Success. Found grid" in outcomes and len(outcomes) >= 3, outcomes
