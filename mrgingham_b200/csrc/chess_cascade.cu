@@ -54,7 +54,7 @@ constexpr int kWarpPx   = 32 * kLanePx;        // 256
 constexpr int kCHalo    = 16;                  // staged bytes left/right of the strip: the ring needs 5 + the lanes' aligned 8-byte cells, and a
                                                // TMA box must start on a 16-byte boundary of global memory (anything else is an illegal instruction)
 constexpr int kBlkRows  = 11;                  // rows per TMA stage == unroll of the row loop == register window
-constexpr int kL2QCarry = 384;                 // per-warp queue of flagged 8-pixel row cells: >= 31 carried over + 352 of one block ...
+constexpr int kL2QCarry = 512;                 // per-warp queue of flagged 8-pixel row cells: >= 31 carried over + 352 of one block, a power of two (slot = position & 511) ...
 constexpr int kL2QBlock = 352;                 // ... or one block's worth when nothing is carried (the queue then restarts at 0 every block)
 constexpr int kL3QCap   = 288;                 // per-warp queue of pixels for the exact test (>= 31 waiting + 256 of one L2 batch)
 
@@ -73,8 +73,9 @@ struct CascadeParams
 };
 
 // head/tail count entries since the CTA started (a CTA never queues anywhere near 2^32 of them); the slot of
-// entry p is p % cap. The capacities are not powers of two: every KB of shared memory per warp decides how many
-// CTAs fit a SM.
+// entry p is p % cap. Only the carried L2 queue's capacity is a power of two (512 instead of the 384 it needs: 5 CTAs
+// still fit a SM, and the slot arithmetic of the flagged-cell loop gets shorter: +0.5-1 %); the others are as small as
+// they can be, because every KB of shared memory per warp decides how many CTAs fit a SM.
 // CARRY: flagged cells that do not fill a batch of 32 wait for the next block's (three staged blocks are then held,
 // four stages needed); !CARRY: every block settles its own cells, the last batch partly empty (two held, three stages).
 template<bool CARRY> struct WarpQueues
@@ -435,7 +436,7 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
                 const uint32_t low = flagbits & (0u - flagbits);
                 flagbits ^= low;
                 q->l2q[pos] = (uint16_t)(low * 32u + (uint32_t)lane);
-                if (++pos == Q::kL2QCap) pos = 0;
+                if (CARRY) pos = (pos + 1) % Q::kL2QCap; else ++pos;
             } while (flagbits);
         }
         __syncwarp();
