@@ -53,3 +53,15 @@ assert n_g == n_o and np.array_equal(xy_g, xy_o) and np.array_equal(lv_g, lv_o)
 for im in (synth.circle_grid_frame(1280, 720, 10, seed=11), synth.blob_frame(640, 600, seed=12), synth.noise_frame(300, 280, seed=13)):
     assert np.array_equal(api.find_blobs_int(im), po.find_blobs(im))
 print("round-2 paths ok", mc, n_g)
+# the pipelined board finder (chunks of >= 16 frames: corner passes over all frames ahead of the grid searches, refinement on
+# the helper detector from a second host thread) against the pass-by-pass form
+small_boards = np.stack([synth.board_frame(640, 480, 6, seed=20 + s, noise_sigma=(8.0 if s % 3 == 0 else 2.0)) for s in range(15)] +
+                        [synth.noise_frame(640, 480, seed=40)])
+det3 = api.Detector(max_frames=16, max_points=512)
+f1, xy1, lv1 = det3.find_boards(small_boards, gridn=6, level=-1)
+os.environ["MRG_B200_BOARDS_SERIAL"] = "1"
+f0, xy0, lv0 = det3.find_boards(small_boards, gridn=6, level=-1)
+del os.environ["MRG_B200_BOARDS_SERIAL"]
+ok = f0 >= 0
+assert np.array_equal(f0, f1) and np.array_equal(xy0[ok], xy1[ok]) and np.array_equal(lv0[ok], lv1[ok]) and f0[15] < 0
+print("pipelined boards ok", f1)
