@@ -61,7 +61,11 @@ constexpr int kL3QCap   = 288;                 // per-warp queue of pixels for t
 template<int NW> struct Geo
 {
     static constexpr int kStripW   = kWarpPx * NW;
-    static constexpr int kRowBytes = kStripW + 2 * kCHalo;
+    // A staged row is the strip plus its halos, rounded up to an ODD number of 16-byte units (TMA boxes come in multiples
+    // of 16 bytes): the lanes of an L2 batch read the same columns of up to 11 consecutive rows (cells along a vertical
+    // edge), and with 800-byte rows every fourth row starts in the same bank -- 3.1 wavefronts per 64-bit load measured
+    // where 1 would do; with 816 bytes it is every eighth row.
+    static constexpr int kRowBytes = ((kStripW + 2 * kCHalo) / 16 % 2 == 0) ? kStripW + 2 * kCHalo + 16 : kStripW + 2 * kCHalo;
     static constexpr int kStageBytes = ((kRowBytes * kBlkRows + 127) / 128) * 128;
 };
 

@@ -29,3 +29,16 @@ for k, s, e, n, st in hot:
     print(f"--- around {k}")
     for d in data[max(0, k - 8):k + 3]:
         print(f"   {d[0]:5d} smp {d[3]:6d} ex {d[2]:9d}  {d[1].strip()[:100]}")
+# shared-memory wavefronts: ideal against actual, per load/store instruction (bank conflicts)
+try:
+    iw = hdr.index('L1 Wavefronts Shared'); ii = hdr.index('L1 Wavefronts Shared Ideal')
+    tw = ti = 0; per = []
+    for k, r in enumerate(rows[2:]):
+        if len(r) <= max(iw, ii): continue
+        w = float(r[iw] or 0); i_ = float(r[ii] or 0)
+        if w > 0: per.append((w, i_, k, int(r[ie] or 0), r[isrc].strip()[:70])); tw += w; ti += i_
+    print(f"# shared-memory wavefronts: {tw:.0f} against {ti:.0f} ideal ({tw / max(ti, 1):.2f}x)")
+    for w, i_, k, e, s in sorted(per, reverse=True)[:24]:
+        print(f"{k:5d} wavefronts {w:12.0f} ideal {i_:12.0f} ({w / max(i_, 1):.2f}x) executed {e:9d}  {s}")
+except ValueError:
+    pass
