@@ -249,3 +249,14 @@ def test_find_boards_pipelined_equals_serial_and_oracle(monkeypatch):
                 if L >= 0:
                     assert np.array_equal(xy1[i], wxy) and np.array_equal(lv1[i], wlv), i
     det.close()
+    # a detector whose configured max_points is smaller than a board's corner count: the corner passes of the pipeline
+    # grow their own capacity and run again (the detector's configuration is left alone)
+    small = api.Detector(max_frames=16, max_points=32)
+    f2, xy2, lv2 = small.find_boards(raw[:16], gridn=gridn, level=-1)
+    monkeypatch.setenv("MRG_B200_BOARDS_SERIAL", "1")
+    f3, xy3, lv3 = small.find_boards(raw[:16], gridn=gridn, level=-1)
+    monkeypatch.delenv("MRG_B200_BOARDS_SERIAL")
+    ok = f3 >= 0
+    assert ok.sum() >= 10 and np.array_equal(f2, f3) and np.array_equal(xy2[ok], xy3[ok]) and np.array_equal(lv2[ok], lv3[ok])
+    assert small.max_points == 32
+    small.close()
