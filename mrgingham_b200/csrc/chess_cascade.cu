@@ -437,10 +437,19 @@ chess_cascade_kernel(const __grid_constant__ CUtensorMap tmap, FrameSet fs, Casc
             if (CARRY) pos %= Q::kL2QCap;          // (without carry the queue restarts at 0 every block: no wrap)
             do
             {
+                // two cells per round: the loop runs as often as the busiest lane has pairs of flagged rows (+0.5 %; four
+                // per round measured the same)
                 const uint32_t low = flagbits & (0u - flagbits);
                 flagbits ^= low;
                 q->l2q[pos] = (uint16_t)(low * 32u + (uint32_t)lane);
                 if (CARRY) pos = (pos + 1) % Q::kL2QCap; else ++pos;
+                if (flagbits)
+                {
+                    const uint32_t low2 = flagbits & (0u - flagbits);
+                    flagbits ^= low2;
+                    q->l2q[pos] = (uint16_t)(low2 * 32u + (uint32_t)lane);
+                    if (CARRY) pos = (pos + 1) % Q::kL2QCap; else ++pos;
+                }
             } while (flagbits);
         }
         __syncwarp();
